@@ -1,0 +1,428 @@
+// bt_api.cu — the C-ABI runtime declared in include/bevy_terrain_b200.h: contexts, the atlas
+// (GpuTileAtlas mirror), views (TerrainViewData mirror) and the per-frame entry points.
+// The preprocessor lives in bt_preprocess.cu, the f64 host math in host_math.cpp.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bt_device.cuh"
+#include "bt_kernels.h"
+#include "bt_runtime.h"
+
+using btd::ViewUniforms;
+
+void bt_context::set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> g(error_mutex);
+    error = buf;
+}
+
+extern "C" {
+
+uint32_t bt_abi_version(void) { return BT_ABI_VERSION; }
+
+bt_status bt_context_create(int32_t device, bt_context** out) {
+    if (!out) return BT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        // no CPU fallback: the caller gets an error, never silently different results
+        (void)cudaGetLastError();
+        return BT_ERR_CUDA;
+    }
+    bt_context* ctx = new bt_context();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return BT_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    if (prop.major < 10) {  // kernels are built for sm_100a only
+        delete ctx;
+        return BT_ERR_CUDA;
+    }
+    *out = ctx;
+    return BT_OK;
+}
+
+void bt_context_destroy(bt_context* ctx) { delete ctx; }
+
+const char* bt_last_error(const bt_context* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+bt_status bt_context_synchronize(bt_context* ctx) {
+    if (!ctx) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaDeviceSynchronize());
+    return BT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// terrain / atlas
+// ------------------------------------------------------------------------------------------------
+bt_status bt_terrain_create(bt_context* ctx, const bt_terrain_desc* desc, bt_terrain** out) {
+    if (!ctx || !desc || !out) return BT_ERR_INVALID_ARG;
+    if (desc->attachment_count == 0 || desc->attachment_count > 8 || desc->lod_count == 0 || desc->lod_count > 31 || desc->atlas_size == 0) {
+        ctx->set_error("bt_terrain_create: invalid attachment_count/lod_count/atlas_size");
+        return BT_ERR_INVALID_ARG;
+    }
+    for (uint32_t i = 0; i < desc->attachment_count; ++i) {
+        const bt_attachment_config& a = desc->attachments[i];
+        if ((a.format != BT_FORMAT_R16 && a.format != BT_FORMAT_RGBA8) || a.texture_size <= 2 * a.border_size) {
+            ctx->set_error("bt_terrain_create: attachment %u: unsupported format %u or texture_size <= 2*border", i, a.format);
+            return BT_ERR_INVALID_ARG;
+        }
+    }
+    if (desc->attachments[0].format != BT_FORMAT_R16) {
+        ctx->set_error("bt_terrain_create: attachment 0 must be the R16 height attachment");
+        return BT_ERR_INVALID_ARG;
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    bt_terrain* t = new bt_terrain();
+    t->ctx = ctx;
+    t->desc = *desc;
+    for (uint32_t i = 0; i < desc->attachment_count; ++i) {
+        const bt_attachment_config& a = desc->attachments[i];
+        const size_t px = a.format == BT_FORMAT_R16 ? 2 : 4;
+        t->tile_bytes[i] = (size_t)a.texture_size * a.texture_size * px;
+        cudaError_t e = cudaMalloc(&t->atlas[i], t->tile_bytes[i] * desc->atlas_size);
+        if (e == cudaSuccess) e = cudaMemset(t->atlas[i], 0, t->tile_bytes[i] * desc->atlas_size);  // wgpu zero-initialises textures
+        if (e != cudaSuccess) {
+            ctx->set_error("bt_terrain_create: atlas allocation of %zu bytes failed: %s", t->tile_bytes[i] * desc->atlas_size, cudaGetErrorString(e));
+            bt_terrain_destroy(t);
+            return e == cudaErrorMemoryAllocation ? BT_ERR_OUT_OF_MEMORY : BT_ERR_CUDA;
+        }
+    }
+    *out = t;
+    return BT_OK;
+}
+
+void bt_terrain_destroy(bt_terrain* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    for (int i = 0; i < 8; ++i) if (t->atlas[i]) cudaFree(t->atlas[i]);
+    delete t;
+}
+
+static bt_status atlas_slot(bt_terrain* t, uint32_t attachment, uint32_t atlas_index, size_t bytes, unsigned char** ptr) {
+    if (!t) return BT_ERR_INVALID_ARG;
+    if (attachment >= t->desc.attachment_count || atlas_index >= t->desc.atlas_size || bytes != t->tile_bytes[attachment]) {
+        t->ctx->set_error("atlas access: attachment %u index %u bytes %zu out of range (tile is %zu bytes)", attachment, atlas_index,
+                          bytes, attachment < 8 ? t->tile_bytes[attachment] : 0);
+        return BT_ERR_INVALID_ARG;
+    }
+    *ptr = static_cast<unsigned char*>(t->atlas[attachment]) + t->tile_bytes[attachment] * atlas_index;
+    return BT_OK;
+}
+
+bt_status bt_atlas_upload_tile(bt_terrain* t, uint32_t attachment, uint32_t atlas_index, const void* texels, size_t bytes, void* stream) {
+    unsigned char* dst;
+    if (!texels) return BT_ERR_INVALID_ARG;
+    bt_status s = atlas_slot(t, attachment, atlas_index, bytes, &dst);
+    if (s != BT_OK) return s;
+    BT_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
+    BT_CUDA(t->ctx, cudaMemcpyAsync(dst, texels, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_atlas_copy_tile(bt_terrain* t, uint32_t attachment, uint32_t atlas_index, const void* device_texels, size_t bytes, void* stream) {
+    unsigned char* dst;
+    if (!device_texels) return BT_ERR_INVALID_ARG;
+    bt_status s = atlas_slot(t, attachment, atlas_index, bytes, &dst);
+    if (s != BT_OK) return s;
+    BT_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
+    BT_CUDA(t->ctx, cudaMemcpyAsync(dst, device_texels, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_atlas_download_tile(bt_terrain* t, uint32_t attachment, uint32_t atlas_index, void* texels, size_t bytes) {
+    unsigned char* src;
+    if (!texels) return BT_ERR_INVALID_ARG;
+    bt_status s = atlas_slot(t, attachment, atlas_index, bytes, &src);
+    if (s != BT_OK) return s;
+    BT_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
+    BT_CUDA(t->ctx, cudaMemcpy(texels, src, bytes, cudaMemcpyDeviceToHost));
+    return BT_OK;
+}
+
+bt_status bt_atlas_device_ptr(bt_terrain* t, uint32_t attachment, void** out) {
+    if (!t || !out || attachment >= t->desc.attachment_count) return BT_ERR_INVALID_ARG;
+    *out = t->atlas[attachment];
+    return BT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// view
+// ------------------------------------------------------------------------------------------------
+bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out) {
+    if (!t || !desc || !out) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = t->ctx;
+    if (desc->geometry_tile_count == 0 || desc->tree_size == 0 || desc->grid_size == 0) {
+        ctx->set_error("bt_view_create: geometry_tile_count, tree_size and grid_size must be non-zero");
+        return BT_ERR_INVALID_ARG;
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    bt_view* v = new bt_view();
+    v->terrain = t;
+    v->desc = *desc;
+    const uint32_t sides = t->desc.kind == BT_KIND_SPHERICAL ? 6u : 1u;
+    v->tile_tree_entries = sides * t->desc.lod_count * desc->tree_size * desc->tree_size;
+    const size_t cap = desc->geometry_tile_count;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc((void**)&v->d_uniforms, sizeof(ViewUniforms));
+    alloc((void**)&v->d_final_tiles, cap * sizeof(bt_tile));          // final_tiles — terrain_view_bind_group.rs:139-142
+    alloc((void**)&v->d_temporary_tiles, 2 * cap * sizeof(bt_tile));  // temporary_tiles (two halves instead of a double-ended stack)
+    alloc((void**)&v->d_indirect, sizeof(bt_indirect));
+    alloc((void**)&v->d_select_status, sizeof(btd::SelectStatus));
+    alloc((void**)&v->d_gen_status, sizeof(btd::GenStatus));
+    alloc((void**)&v->d_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+    if (e == cudaSuccess) e = cudaMemset(v->d_indirect, 0, sizeof(bt_indirect));
+    if (e == cudaSuccess) e = cudaMemset(v->d_select_status, 0, sizeof(btd::SelectStatus));
+    if (e == cudaSuccess) e = cudaMemset(v->d_gen_status, 0, sizeof(btd::GenStatus));
+    if (e == cudaSuccess) e = cudaMemset(v->d_tile_tree, 0xFF, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+    // pinned staging so bt_view_update is a pair of truly asynchronous copies
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_uniforms, sizeof(ViewUniforms), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_readback, sizeof(btd::SelectStatus) + sizeof(bt_indirect) + sizeof(btd::GenStatus), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->staging_free, cudaEventDisableTiming);
+    if (e == cudaSuccess && desc->max_vertices) {
+        e = cudaMalloc((void**)&v->d_vertices, desc->max_vertices * sizeof(bt_vertex));
+        v->vertex_capacity = desc->max_vertices;
+    }
+    if (e != cudaSuccess) {
+        ctx->set_error("bt_view_create: %s", cudaGetErrorString(e));
+        bt_view_destroy(v);
+        return e == cudaErrorMemoryAllocation ? BT_ERR_OUT_OF_MEMORY : BT_ERR_CUDA;
+    }
+    *out = v;
+    return BT_OK;
+}
+
+void bt_view_destroy(bt_view* v) {
+    if (!v) return;
+    cudaSetDevice(v->terrain->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(v->d_uniforms); cudaFree(v->d_final_tiles); cudaFree(v->d_temporary_tiles); cudaFree(v->d_indirect);
+    cudaFree(v->d_select_status); cudaFree(v->d_gen_status); cudaFree(v->d_tile_tree); cudaFree(v->d_vertices);
+    if (v->h_uniforms) cudaFreeHost(v->h_uniforms);
+    if (v->h_tile_tree) cudaFreeHost(v->h_tile_tree);
+    if (v->h_readback) cudaFreeHost(v->h_readback);
+    if (v->staging_free) cudaEventDestroy(v->staging_free);
+    delete v;
+}
+
+bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) {
+    if (!v || !f) return BT_ERR_INVALID_ARG;
+    bt_terrain* t = v->terrain;
+    bt_context* ctx = t->ctx;
+    if (f->tile_tree_entry_count != v->tile_tree_entries || !f->tile_tree) {
+        ctx->set_error("bt_view_update: tile_tree_entry_count %u, expected sides*lod_count*tree_size^2 = %u", f->tile_tree_entry_count, v->tile_tree_entries);
+        return BT_ERR_INVALID_ARG;
+    }
+    if (f->view_config.tree_size != v->desc.tree_size || (uint32_t)f->view_config.grid_size != v->desc.grid_size ||
+        f->view_config.vertices_per_row != 2 * (v->desc.grid_size + 2) ||
+        f->view_config.vertices_per_tile != 2 * v->desc.grid_size * (v->desc.grid_size + 2)) {
+        ctx->set_error("bt_view_update: view_config tree_size/grid_size/vertices_per_* disagree with the view");
+        return BT_ERR_INVALID_ARG;
+    }
+    if (f->approximation.origin_lod > 30) {
+        ctx->set_error("bt_view_update: origin_lod %u > 30", f->approximation.origin_lod);
+        return BT_ERR_INVALID_ARG;
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaEventSynchronize(v->staging_free));  // previous async copies out of the staging buffers are done
+    ViewUniforms& U = *static_cast<ViewUniforms*>(v->h_uniforms);
+    std::memset(&U, 0, sizeof(U));
+    U.view_config = f->view_config;
+    U.spherical = t->desc.kind == BT_KIND_SPHERICAL;
+    U.texture_size = t->desc.attachments[0].texture_size;
+    U.tile_tree_entries = v->tile_tree_entries;
+    U.approximation = f->approximation;
+    U.culling = f->culling;
+    // TerrainConfigUniform::from_tile_atlas — terrain_bind_group.rs:84-93
+    U.terrain_config.lod_count = t->desc.lod_count;
+    U.terrain_config.min_height = t->desc.min_height;
+    U.terrain_config.max_height = t->desc.max_height;
+    U.terrain_config.scale = (float)t->desc.scale;
+    for (uint32_t i = 0; i < t->desc.attachment_count; ++i) {  // AttachmentUniform::new — terrain_bind_group.rs:60-72
+        const bt_attachment_config& a = t->desc.attachments[i];
+        const float center = (float)(a.texture_size - 2 * a.border_size);
+        U.attachments[i].size = center;
+        U.attachments[i].scale = center / (float)a.texture_size;
+        U.attachments[i].offset = (float)a.border_size / (float)a.texture_size;
+    }
+    U.mesh = t->desc.transform;
+    std::memcpy(U.view_world_position, f->view_world_position, sizeof(float) * 3);
+    std::memcpy(v->h_tile_tree, f->tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaMemcpyAsync(v->d_uniforms, v->h_uniforms, sizeof(ViewUniforms), cudaMemcpyHostToDevice, s));
+    BT_CUDA(ctx, cudaMemcpyAsync(v->d_tile_tree, v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaMemcpyHostToDevice, s));
+    BT_CUDA(ctx, cudaEventRecord(v->staging_free, s));
+    v->h2d_bytes_last_update = sizeof(ViewUniforms) + (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry);
+    v->updated = true;
+    return BT_OK;
+}
+
+bt_status bt_select_tiles(bt_view* v, uint32_t flags, void* stream) {
+    if (!v) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    if (!v->updated) { ctx->set_error("bt_select_tiles: bt_view_update has not been called"); return BT_ERR_INVALID_ARG; }
+    if (flags & BT_FLAG_FRUSTUM_CULL) {
+        ctx->set_error("bt_select_tiles: BT_FLAG_FRUSTUM_CULL is not implemented (the reference does not cull at this commit either)");
+        return BT_ERR_INVALID_ARG;
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, bt_launch_select_tiles(v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->desc.geometry_tile_count, v->d_indirect,
+                                        v->d_select_status, v->terrain->desc.kind == BT_KIND_SPHERICAL, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_gen_vertices(bt_view* v, uint32_t flags, void* stream, bt_vertex_buffer* out) {
+    if (!v) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    if (!v->updated) { ctx->set_error("bt_gen_vertices: bt_view_update has not been called"); return BT_ERR_INVALID_ARG; }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v->desc.max_vertices == 0) {
+        // grow-on-demand mode: needs the tile count on the host (one small blocking readback);
+        // views created with max_vertices stay fully asynchronous
+        bt_indirect ind;
+        BT_CUDA(ctx, cudaMemcpyAsync(&ind, v->d_indirect, sizeof(ind), cudaMemcpyDeviceToHost, s));
+        BT_CUDA(ctx, cudaStreamSynchronize(s));
+        if ((uint64_t)ind.vertex_count > v->vertex_capacity) {
+            if (v->d_vertices) BT_CUDA(ctx, cudaFree(v->d_vertices));
+            v->d_vertices = nullptr;
+            v->vertex_capacity = 0;
+            cudaError_t e = cudaMalloc((void**)&v->d_vertices, (size_t)ind.vertex_count * sizeof(bt_vertex));
+            if (e != cudaSuccess) { ctx->set_error("bt_gen_vertices: vertex buffer allocation failed: %s", cudaGetErrorString(e)); return BT_ERR_OUT_OF_MEMORY; }
+            v->vertex_capacity = ind.vertex_count;
+        }
+    }
+    BT_CUDA(ctx, bt_launch_gen_vertices(v->d_uniforms, v->d_final_tiles, v->d_indirect, v->d_tile_tree,
+                                        static_cast<const uint16_t*>(v->terrain->atlas[0]), v->d_vertices, v->vertex_capacity,
+                                        v->d_gen_status, v->terrain->desc.kind == BT_KIND_SPHERICAL, flags, v->desc.grid_size,
+                                        ctx->sm_count, s));
+    if (out) { out->vertices = v->d_vertices; out->capacity = v->vertex_capacity; }
+    return BT_OK;
+}
+
+bt_status bt_view_readback(bt_view* v, bt_tile* tiles, uint32_t capacity, uint32_t* count, bt_indirect* indirect, void* stream) {
+    if (!v) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned char* hb = static_cast<unsigned char*>(v->h_readback);
+    BT_CUDA(ctx, cudaMemcpyAsync(hb, v->d_select_status, sizeof(btd::SelectStatus), cudaMemcpyDeviceToHost, s));
+    BT_CUDA(ctx, cudaMemcpyAsync(hb + sizeof(btd::SelectStatus), v->d_indirect, sizeof(bt_indirect), cudaMemcpyDeviceToHost, s));
+    BT_CUDA(ctx, cudaStreamSynchronize(s));
+    btd::SelectStatus st;
+    std::memcpy(&st, hb, sizeof(st));
+    if (indirect) std::memcpy(indirect, hb + sizeof(btd::SelectStatus), sizeof(bt_indirect));
+    if (count) *count = st.final_count;
+    if (tiles) {
+        const uint32_t n = st.final_count < capacity ? st.final_count : capacity;
+        if (n) {
+            BT_CUDA(ctx, cudaMemcpyAsync(tiles, v->d_final_tiles, (size_t)n * sizeof(bt_tile), cudaMemcpyDeviceToHost, s));
+            BT_CUDA(ctx, cudaStreamSynchronize(s));
+        }
+    }
+    if (st.overflow) { ctx->set_error("select_tiles: tile list exceeded geometry_tile_count = %u", v->desc.geometry_tile_count); return BT_ERR_CAPACITY; }
+    return BT_OK;
+}
+
+bt_status bt_view_select_status(bt_view* v, uint32_t* dropped_parents, void* stream) {
+    if (!v) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    btd::SelectStatus st;
+    BT_CUDA(ctx, cudaMemcpyAsync(&st, v->d_select_status, sizeof(st), cudaMemcpyDeviceToHost, s));
+    BT_CUDA(ctx, cudaStreamSynchronize(s));
+    if (dropped_parents) *dropped_parents = st.dropped_parents;
+    return st.overflow ? BT_ERR_CAPACITY : BT_OK;
+}
+
+bt_status bt_view_download_vertices(bt_view* v, bt_vertex* out, uint64_t first, uint64_t count, void* stream) {
+    if (!v || !out) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    if (first + count > v->vertex_capacity) { ctx->set_error("bt_view_download_vertices: range exceeds the vertex buffer"); return BT_ERR_INVALID_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    btd::GenStatus gs;
+    BT_CUDA(ctx, cudaMemcpyAsync(&gs, v->d_gen_status, sizeof(gs), cudaMemcpyDeviceToHost, s));
+    if (count) BT_CUDA(ctx, cudaMemcpyAsync(out, v->d_vertices + first, count * sizeof(bt_vertex), cudaMemcpyDeviceToHost, s));
+    BT_CUDA(ctx, cudaStreamSynchronize(s));
+    if (gs.overflow) { ctx->set_error("gen_vertices: vertex buffer (%llu vertices) too small", (unsigned long long)v->vertex_capacity); return BT_ERR_CAPACITY; }
+    return BT_OK;
+}
+
+bt_status bt_view_device_ptrs(bt_view* v, bt_tile** final_tiles, bt_indirect** indirect) {
+    if (!v) return BT_ERR_INVALID_ARG;
+    if (final_tiles) *final_tiles = v->d_final_tiles;
+    if (indirect) *indirect = v->d_indirect;
+    return BT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utilities
+// ------------------------------------------------------------------------------------------------
+bt_status bt_generate_mipmaps(bt_context* ctx, uint32_t format, uint32_t texture_size, uint32_t mip_level_count,
+                              const void* device_mip0, void* device_mips_out, void* stream) {
+    if (!ctx || !device_mip0 || !device_mips_out || (format != BT_FORMAT_R16 && format != BT_FORMAT_RGBA8)) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, bt_launch_mipmaps(format, texture_size, mip_level_count, device_mip0, device_mips_out, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_synth_source(bt_context* ctx, uint32_t format, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0,
+                          uint32_t seed, uint32_t holes, void* device_out, void* stream) {
+    if (!ctx || !device_out || (format != BT_FORMAT_R16 && format != BT_FORMAT_RGBA8)) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, bt_launch_synth(format, width, height, x0, y0, seed, holes, device_out, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_device_alloc(bt_context* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) { ctx->set_error("bt_device_alloc(%zu): %s", bytes, cudaGetErrorString(e)); return BT_ERR_OUT_OF_MEMORY; }
+    return BT_OK;
+}
+
+bt_status bt_device_free(bt_context* ctx, void* ptr) {
+    if (!ctx) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaFree(ptr));
+    return BT_OK;
+}
+
+bt_status bt_memcpy_h2d(bt_context* ctx, void* dst_device, const void* src_host, size_t bytes, void* stream) {
+    if (!ctx || (!dst_device && bytes) || (!src_host && bytes)) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    BT_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_memcpy_d2h(bt_context* ctx, void* dst_host, const void* src_device, size_t bytes, void* stream) {
+    if (!ctx || (!dst_host && bytes) || (!src_device && bytes)) return BT_ERR_INVALID_ARG;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    BT_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return BT_OK;
+}
+
+}  // extern "C"

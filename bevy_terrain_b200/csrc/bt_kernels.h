@@ -1,0 +1,60 @@
+// bt_kernels.h — internal launch interface between the C-ABI runtime (bt_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bevy_terrain_b200.h"
+
+namespace btd {
+
+// written by select_tiles_kernel (device), read back by bt_view_select_status / bt_view_readback
+struct SelectStatus {
+    uint32_t final_count;
+    uint32_t dropped_parents;  // parents that still wanted subdivision in the last pass (reference Q2: dropped)
+    uint32_t max_frontier;
+    uint32_t overflow;         // 1 = a tile list exceeded its capacity (unchecked in the reference)
+};
+
+struct GenStatus {
+    uint32_t vertex_count_lo, vertex_count_hi;
+    uint32_t overflow;         // vertex buffer too small for indirect.vertex_count
+    uint32_t _pad;
+};
+
+// one preprocess task = one output tile of one phase (SplitData / DownsampleData / StitchData,
+// src/preprocess/gpu_preprocessor.rs:31-50); slots index the device pyramid store
+struct PyramidTask {
+    bt_tile  tile;
+    uint32_t slot;          // output tile slot
+    uint32_t dataset;       // split: index into the dataset table
+    uint32_t dep[8];        // downsample: 4 child slots; stitch: 8 neighbour slots; 0xFFFFFFFF = invalid
+    uint32_t dep_side[8];   // stitch: neighbour side (for project_to_side)
+    uint32_t _pad[2];
+};
+
+// one contiguous row copy of the halo / root exchange (multi-GPU preprocess)
+struct RowCopy {
+    const void* src;
+    void* dst;
+    uint64_t bytes;   // multiple of 2
+};
+
+struct DatasetDevice {
+    const void* pixels;     // device pointer, row-major
+    uint32_t width, height;
+    float top_left[2], bottom_right[2];
+    uint32_t _pad[2];
+};
+
+}  // namespace btd
+
+extern "C" {
+cudaError_t bt_launch_select_tiles(const void* uniforms, bt_tile* final_tiles, bt_tile* temporary_tiles,
+                                   uint32_t capacity, bt_indirect* indirect, btd::SelectStatus* status,
+                                   int spherical, cudaStream_t stream);
+cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_tile* final_tiles, const bt_indirect* indirect,
+                                   const bt_tile_tree_entry* tile_tree, const uint16_t* height_atlas,
+                                   bt_vertex* vertices, uint64_t vertex_capacity, btd::GenStatus* status,
+                                   int spherical, uint32_t flags, uint32_t grid_size, int sm_count, cudaStream_t stream);
+}

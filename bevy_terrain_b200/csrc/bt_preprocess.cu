@@ -1,0 +1,700 @@
+// bt_preprocess.cu — the preprocessor runtime behind bt_preprocessor_* (C ABI).
+//
+// C++ counterpart of Preprocessor (src/preprocess/preprocessor.rs:214-343: task graph
+// Split -> Barrier -> Downsample per level -> Barrier -> per-LOD Stitch -> Save), of
+// GpuPreprocessor::prepare (src/preprocess/gpu_preprocessor.rs:120-223: per-task uniforms) and of
+// TerrainPreprocessNode::run (src/preprocess/mod.rs:143-217: the dispatch loop).  Differences by
+// design: all tiles of a phase go in ONE launch (no 32-tile write-section cap, no frame pacing),
+// tiles live in a device-resident pyramid store instead of atlas slots + staging buffers, and
+// the deepest-LOD tile rows can be sharded over ranks (bt_shard) with a halo + sub-root exchange
+// that the host performs with NCCL between the exposed phases.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "bt_kernels.h"
+#include "bt_runtime.h"
+
+using btd::DatasetDevice;
+using btd::PyramidTask;
+using btd::RowCopy;
+
+namespace {
+
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+
+struct TileKey {
+    uint32_t side, lod, x, y;
+    bool operator==(const TileKey& o) const { return side == o.side && lod == o.lod && x == o.x && y == o.y; }
+};
+struct TileKeyHash {
+    size_t operator()(const TileKey& k) const {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (uint32_t w : {k.side, k.lod, k.x, k.y}) { h ^= w; h *= 0x100000001b3ull; h ^= h >> 31; }
+        return (size_t)h;
+    }
+};
+
+enum SlotKind : uint8_t { kOwned = 0, kGhost = 1, kReplica = 2 };
+
+struct Store {  // one attachment's device-resident tile pyramid
+    bt_attachment_config cfg{};
+    size_t tile_bytes = 0;
+    uint32_t px = 0;
+    std::unordered_map<TileKey, uint32_t, TileKeyHash> slot_of;
+    std::vector<TileKey> keys;
+    std::vector<uint32_t> exists_from_job;
+    std::vector<uint8_t> kind;
+    unsigned char* arena = nullptr;
+    uint32_t arena_slots = 0;    // slots the arena can hold
+    uint32_t zeroed_slots = 0;   // slots already zero-initialised
+};
+
+struct Job {
+    uint32_t attachment = 0;
+    std::vector<bt_dataset> datasets;
+    std::vector<void*> owned_pixels;  // device copies of host-provided sources
+    bool split_done = false, roots_done = false, halo_done = false, stitched = false;
+};
+
+// NEIGHBOURING_SIDES / SideInfo — src/math/coordinate.rs:9-53
+constexpr uint32_t kNeighbouringSides[6][5] = {{0, 4, 2, 1, 5}, {1, 0, 2, 3, 5}, {2, 0, 4, 3, 1}, {3, 2, 4, 5, 1}, {4, 2, 0, 5, 3}, {5, 4, 0, 1, 3}};
+enum SideInfo : uint8_t { kFixed0, kFixed1, kPosS, kPosT };
+constexpr SideInfo kEven[6][2] = {{kPosS, kPosT}, {kFixed0, kPosT}, {kFixed0, kPosS}, {kPosT, kPosS}, {kPosT, kFixed0}, {kPosS, kFixed0}};
+constexpr SideInfo kOdd[6][2] = {{kPosS, kPosT}, {kPosS, kFixed1}, {kPosT, kFixed1}, {kPosT, kPosS}, {kFixed1, kPosS}, {kFixed1, kPosT}};
+constexpr TileKey kInvalidTile{kInvalid, kInvalid, kInvalid, kInvalid};
+
+// TileCoordinate::neighbour_coordinate — coordinate.rs:227-279
+TileKey neighbour_coordinate(const TileKey& self, int32_t nx, int32_t ny, bool spherical) {
+    const int32_t n = (int32_t)(1u << self.lod);
+    if (!spherical) {
+        if (nx < 0 || ny < 0 || nx >= n || ny >= n) return kInvalidTile;
+        return TileKey{self.side, self.lod, (uint32_t)nx, (uint32_t)ny};
+    }
+    const bool xl = nx < 0, xh = nx >= n, yl = ny < 0, yh = ny >= n;
+    if ((xl || xh) && (yl || yh)) return kInvalidTile;
+    const int edge = xl ? 1 : yl ? 2 : xh ? 3 : yh ? 4 : 0;
+    const uint32_t px = (uint32_t)std::min(std::max(nx, 0), n - 1), py = (uint32_t)std::min(std::max(ny, 0), n - 1);
+    const uint32_t side = kNeighbouringSides[self.side][edge];
+    const uint32_t index = (6 + side - self.side) % 6;
+    const SideInfo* info = (self.side % 2 == 0) ? kEven[index] : kOdd[index];
+    auto pick = [&](SideInfo i) { return i == kFixed0 ? 0u : i == kFixed1 ? (uint32_t)n - 1u : i == kPosS ? px : py; };
+    return TileKey{side, self.lod, pick(info[0]), pick(info[1])};
+}
+
+uint32_t f32_to_u32(float x) {
+    if (!(x > 0.0f)) return 0u;
+    if (x >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)x;
+}
+
+uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << (l + 1)) <= v) ++l; return l; }
+
+}  // namespace
+
+struct bt_preprocessor {
+    bt_context* ctx = nullptr;
+    uint32_t kind = BT_KIND_PLANAR;
+    uint32_t lod_count = 0;
+    bt_shard shard{0, 1};
+    uint32_t root_lod = 0;  // L0 = log2(world): levels below it are computed redundantly on every rank
+    std::vector<Store> stores;
+    std::vector<Job> jobs;
+    // scratch device buffers (grown on demand)
+    PyramidTask* d_tasks = nullptr; size_t d_tasks_cap = 0;
+    DatasetDevice* d_datasets = nullptr; size_t d_datasets_cap = 0;
+    RowCopy* d_copies = nullptr; size_t d_copies_cap = 0;
+
+    bool spherical() const { return kind == BT_KIND_SPHERICAL; }
+
+    // PreprocessDataset::overlapping_tiles — preprocessor.rs:58-66 (f32), intersected with the rows
+    // this rank owns (world == 1: everything)
+    void tile_range(const bt_dataset& d, uint32_t lod, uint32_t lo[2], uint32_t hi[2]) const {
+        const float tc = (float)(1u << lod);
+        for (int k = 0; k < 2; ++k) {
+            lo[k] = f32_to_u32(d.top_left[k] * tc);
+            hi[k] = f32_to_u32(std::ceil(d.bottom_right[k] * tc));
+        }
+    }
+    // rows [y0, y1) of `lod` owned by this rank; levels above the root level are owned by everyone
+    void owned_rows(uint32_t lod, uint32_t* y0, uint32_t* y1) const {
+        const uint32_t n = 1u << lod;
+        if (shard.world == 1 || lod < root_lod) { *y0 = 0; *y1 = n; return; }
+        *y0 = (uint32_t)((uint64_t)shard.rank * n / shard.world);
+        *y1 = (uint32_t)((uint64_t)(shard.rank + 1) * n / shard.world);
+    }
+    bool owns(const TileKey& k) const {
+        uint32_t y0, y1;
+        owned_rows(k.lod, &y0, &y1);
+        return k.y >= y0 && k.y < y1;
+    }
+
+    uint32_t get_or_allocate(Store& s, const TileKey& k, uint32_t job, uint8_t kind_) {
+        auto it = s.slot_of.find(k);
+        if (it != s.slot_of.end()) {
+            if (kind_ == kOwned) s.kind[it->second] = kOwned;
+            return it->second;
+        }
+        const uint32_t slot = (uint32_t)s.keys.size();
+        s.slot_of.emplace(k, slot);
+        s.keys.push_back(k);
+        s.exists_from_job.push_back(job);
+        s.kind.push_back(kind_);
+        return slot;
+    }
+    // TileAtlasState::get_tile — tile_atlas.rs:369-381, evaluated at queue-build time of `job`
+    uint32_t get_tile(const Store& s, const TileKey& k, uint32_t job) const {
+        if (k == kInvalidTile) return kInvalid;
+        auto it = s.slot_of.find(k);
+        if (it == s.slot_of.end() || s.exists_from_job[it->second] > job) return kInvalid;
+        return it->second;
+    }
+
+    bt_status ensure_arena(Store& s, cudaStream_t stream) {
+        const uint32_t need = (uint32_t)s.keys.size();
+        if (need > s.arena_slots) {
+            unsigned char* bigger = nullptr;
+            cudaError_t e = cudaMalloc((void**)&bigger, (size_t)need * s.tile_bytes);
+            if (e != cudaSuccess) {
+                ctx->set_error("preprocessor: pyramid store of %u tiles (%zu bytes) does not fit: %s", need, (size_t)need * s.tile_bytes, cudaGetErrorString(e));
+                (void)cudaGetLastError();
+                return BT_ERR_OUT_OF_MEMORY;
+            }
+            if (s.arena) {
+                BT_CUDA(ctx, cudaMemcpyAsync(bigger, s.arena, (size_t)s.zeroed_slots * s.tile_bytes, cudaMemcpyDeviceToDevice, stream));
+                BT_CUDA(ctx, cudaStreamSynchronize(stream));
+                BT_CUDA(ctx, cudaFree(s.arena));
+            }
+            s.arena = bigger;
+            s.arena_slots = need;
+        }
+        if (need > s.zeroed_slots) {  // atlas textures start zeroed (wgpu); split falls through to that content
+            BT_CUDA(ctx, cudaMemsetAsync(s.arena + (size_t)s.zeroed_slots * s.tile_bytes, 0, (size_t)(need - s.zeroed_slots) * s.tile_bytes, stream));
+            s.zeroed_slots = need;
+        }
+        return BT_OK;
+    }
+
+    template <typename T>
+    bt_status upload(T** dev, size_t* cap, const std::vector<T>& host, cudaStream_t stream) {
+        if (host.size() > *cap) {
+            if (*dev) { BT_CUDA(ctx, cudaStreamSynchronize(stream)); BT_CUDA(ctx, cudaFree(*dev)); *dev = nullptr; }
+            BT_CUDA(ctx, cudaMalloc((void**)dev, host.size() * sizeof(T)));
+            *cap = host.size();
+        }
+        if (!host.empty()) {
+            BT_CUDA(ctx, cudaMemcpyAsync(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+            BT_CUDA(ctx, cudaStreamSynchronize(stream));  // `host` is a temporary: make the pageable copy complete
+        }
+        return BT_OK;
+    }
+
+    // ---- task builders -------------------------------------------------------------------------
+    // all tiles (every LOD, every dataset) of a job exist before any task resolves its dependencies:
+    // split_and_downsample is queued for all datasets before the first stitch (preprocessor.rs:298-343)
+    void allocate_job_tiles(uint32_t ji) {
+        Job& j = jobs[ji];
+        Store& s = stores[j.attachment];
+        for (const bt_dataset& d : j.datasets)
+            for (uint32_t lod = d.lod_begin; lod < d.lod_end; ++lod) {
+                uint32_t lo[2], hi[2], y0, y1;
+                tile_range(d, lod, lo, hi);
+                owned_rows(lod, &y0, &y1);
+                for (uint32_t x = lo[0]; x < hi[0]; ++x)
+                    for (uint32_t y = std::max(lo[1], y0); y < std::min(hi[1], y1); ++y)
+                        get_or_allocate(s, TileKey{d.side, lod, x, y}, ji, (lod < root_lod && shard.rank != 0) ? kReplica : kOwned);
+                if (shard.world > 1 && lod >= root_lod) {
+                    if (lod == root_lod) {  // the whole root level is replicated by the sub-root gather
+                        for (uint32_t x = lo[0]; x < hi[0]; ++x)
+                            for (uint32_t y = lo[1]; y < hi[1]; ++y)
+                                if (y < y0 || y >= y1) get_or_allocate(s, TileKey{d.side, lod, x, y}, ji, kReplica);
+                    } else {  // ghost rows that receive the halo strips of the adjacent ranks
+                        for (uint32_t x = lo[0]; x < hi[0]; ++x) {
+                            if (y0 > lo[1]) get_or_allocate(s, TileKey{d.side, lod, x, y0 - 1}, ji, kGhost);
+                            if (y1 < hi[1]) get_or_allocate(s, TileKey{d.side, lod, x, y1}, ji, kGhost);
+                        }
+                    }
+                }
+            }
+    }
+
+    void collect(uint32_t ji, const bt_dataset& d, uint32_t di, uint32_t lod, std::vector<PyramidTask>& out) {
+        Store& s = stores[jobs[ji].attachment];
+        uint32_t lo[2], hi[2], y0, y1;
+        tile_range(d, lod, lo, hi);
+        owned_rows(lod, &y0, &y1);
+        for (uint32_t x = lo[0]; x < hi[0]; ++x)
+            for (uint32_t y = std::max(lo[1], y0); y < std::min(hi[1], y1); ++y) {
+                PyramidTask t;
+                std::memset(&t, 0xFF, sizeof(t));
+                t.tile = bt_tile{d.side, lod, x, y};
+                t.slot = s.slot_of.at(TileKey{d.side, lod, x, y});
+                t.dataset = di;
+                out.push_back(t);
+            }
+    }
+
+    bt_status run_levels(uint32_t ji, uint32_t lod_hi_exclusive, uint32_t lod_lo, bool with_split, cudaStream_t stream) {
+        // downsample levels lod_hi_exclusive-1 ... lod_lo (and the split of the deepest level if asked)
+        Job& j = jobs[ji];
+        Store& s = stores[j.attachment];
+        std::vector<PyramidTask> tasks;
+        if (with_split) {
+            std::vector<DatasetDevice> dd;
+            for (uint32_t di = 0; di < j.datasets.size(); ++di) {
+                const bt_dataset& d = j.datasets[di];
+                DatasetDevice x{};
+                x.pixels = d.pixels;
+                x.width = d.width; x.height = d.height;
+                x.top_left[0] = d.top_left[0]; x.top_left[1] = d.top_left[1];
+                x.bottom_right[0] = d.bottom_right[0]; x.bottom_right[1] = d.bottom_right[1];
+                dd.push_back(x);
+                if (d.lod_end > d.lod_begin) collect(ji, d, di, d.lod_end - 1, tasks);
+            }
+            bt_status st = upload(&d_datasets, &d_datasets_cap, dd, stream);
+            if (st != BT_OK) return st;
+            st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
+            if (st != BT_OK) return st;
+            BT_CUDA(ctx, bt_launch_split(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), d_datasets, stream));
+        }
+        for (int32_t lod = (int32_t)lod_hi_exclusive - 1; lod >= (int32_t)lod_lo; --lod) {
+            tasks.clear();
+            for (uint32_t di = 0; di < j.datasets.size(); ++di) {
+                const bt_dataset& d = j.datasets[di];
+                if ((uint32_t)lod + 1 >= d.lod_end || (uint32_t)lod < d.lod_begin) continue;  // the deepest level is split, not downsampled
+                const size_t first = tasks.size();
+                collect(ji, d, di, (uint32_t)lod, tasks);
+                for (size_t i = first; i < tasks.size(); ++i)  // TileCoordinate::children — coordinate.rs:197-206
+                    for (uint32_t c = 0; c < 4; ++c)
+                        tasks[i].dep[c] = get_tile(s, TileKey{d.side, (uint32_t)lod + 1, (tasks[i].tile.x << 1) + c % 2, (tasks[i].tile.y << 1) + c / 2}, ji);
+            }
+            if (tasks.empty()) continue;
+            // the previous launch may still read d_tasks: stream order makes the upload wait (same stream)
+            bt_status st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
+            if (st != BT_OK) return st;
+            BT_CUDA(ctx, bt_launch_downsample(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), stream));
+        }
+        return BT_OK;
+    }
+
+    bt_status run_split_downsample_job(uint32_t ji, cudaStream_t stream) {
+        Job& j = jobs[ji];
+        Store& s = stores[j.attachment];
+        allocate_job_tiles(ji);
+        bt_status st = ensure_arena(s, stream);
+        if (st != BT_OK) return st;
+        uint32_t lod_end = 0, lod_begin = kInvalid;
+        for (const bt_dataset& d : j.datasets) { lod_end = std::max(lod_end, d.lod_end); lod_begin = std::min(lod_begin, d.lod_begin); }
+        // sharded: stop at the root level; the levels above it follow the sub-root gather
+        const uint32_t lo = shard.world > 1 ? std::max(lod_begin, root_lod) : lod_begin;
+        st = run_levels(ji, lod_end - 1, lo, true, stream);
+        if (st == BT_OK) j.split_done = true;
+        return st;
+    }
+
+    bt_status run_stitch_job(uint32_t ji, cudaStream_t stream) {
+        Job& j = jobs[ji];
+        Store& s = stores[j.attachment];
+        std::vector<PyramidTask> tasks;
+        static const int32_t kOffsets[8][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};  // coordinate.rs:209-218
+        for (uint32_t di = 0; di < j.datasets.size(); ++di) {
+            const bt_dataset& d = j.datasets[di];
+            for (uint32_t lod = d.lod_begin; lod < d.lod_end; ++lod) {
+                const size_t first = tasks.size();
+                collect(ji, d, di, lod, tasks);
+                for (size_t i = first; i < tasks.size(); ++i) {
+                    const TileKey self{tasks[i].tile.side, tasks[i].tile.lod, tasks[i].tile.x, tasks[i].tile.y};
+                    for (int k = 0; k < 8; ++k) {  // TileCoordinate::neighbours — coordinate.rs:208-225
+                        const TileKey nb = neighbour_coordinate(self, (int32_t)self.x + kOffsets[k][0], (int32_t)self.y + kOffsets[k][1], spherical());
+                        tasks[i].dep[k] = get_tile(s, nb, ji);
+                        tasks[i].dep_side[k] = nb.side;
+                    }
+                }
+            }
+        }
+        // stitch reads only neighbour CENTRES, all final after the downsample phase: one launch for every LOD
+        bt_status st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
+        if (st != BT_OK) return st;
+        BT_CUDA(ctx, bt_launch_stitch(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), stream));
+        j.stitched = true;
+        return BT_OK;
+    }
+
+    int pending_job() const {
+        for (size_t i = 0; i < jobs.size(); ++i) if (!jobs[i].stitched) return (int)i;
+        return -1;
+    }
+
+    // ---- multi-GPU exchange layouts ---------------------------------------------------------------
+    // halo: for every dataset LOD above the root level: [top strips of my first owned row][bottom
+    // strips of my last owned row], each strip = border_size rows x center_size pixels of one tile
+    uint64_t halo_bytes(const Job& j) const {
+        if (shard.world == 1) return 0;
+        const Store& s = stores[j.attachment];
+        const bt_dataset& d = j.datasets[0];
+        const uint32_t C = s.cfg.texture_size - 2 * s.cfg.border_size;
+        uint64_t bytes = 0;
+        for (uint32_t lod = std::max(d.lod_begin, root_lod + 1); lod < d.lod_end; ++lod)
+            bytes += 2ull * (1u << lod) * s.cfg.border_size * C * s.px;
+        return bytes;
+    }
+    uint64_t roots_bytes(const Job& j) const {
+        if (shard.world == 1) return 0;
+        const bt_dataset& d = j.datasets[0];
+        if (d.lod_begin > root_lod) return 0;  // no level above the shard boundary is requested... but root tiles still needed by nobody
+        return (uint64_t)(1u << root_lod) * stores[j.attachment].tile_bytes;  // one row of the root level
+    }
+};
+
+extern "C" {
+
+bt_status bt_preprocessor_create(bt_context* ctx, uint32_t kind, const bt_attachment_config* attachments, uint32_t attachment_count,
+                                 uint32_t lod_count, bt_shard shard, bt_preprocessor** out) {
+    if (!ctx || !attachments || !out || attachment_count == 0 || attachment_count > 8 || lod_count == 0 || lod_count > 24) return BT_ERR_INVALID_ARG;
+    if (kind != BT_KIND_PLANAR && kind != BT_KIND_SPHERICAL) return BT_ERR_INVALID_ARG;
+    if (shard.world == 0 || shard.rank >= shard.world || (shard.world & (shard.world - 1)) != 0) {
+        ctx->set_error("bt_preprocessor_create: shard world must be a power of two and rank < world");
+        return BT_ERR_INVALID_ARG;
+    }
+    if (shard.world > 1 && kind == BT_KIND_SPHERICAL) {
+        ctx->set_error("bt_preprocessor_create: sharding a spherical (cross-face stitched) pyramid is not supported yet");
+        return BT_ERR_INVALID_ARG;
+    }
+    bt_preprocessor* p = new bt_preprocessor();
+    p->ctx = ctx;
+    p->kind = kind;
+    p->lod_count = lod_count;
+    p->shard = shard;
+    p->root_lod = ilog2(shard.world);
+    for (uint32_t i = 0; i < attachment_count; ++i) {
+        const bt_attachment_config& a = attachments[i];
+        if ((a.format != BT_FORMAT_R16 && a.format != BT_FORMAT_RGBA8) || a.texture_size <= 2 * a.border_size) {
+            ctx->set_error("bt_preprocessor_create: attachment %u: unsupported format %u (only R16/Rgba8 have shader paths in the reference) or texture_size <= 2*border", i, a.format);
+            delete p;
+            return BT_ERR_INVALID_ARG;
+        }
+        Store s;
+        s.cfg = a;
+        s.px = a.format == BT_FORMAT_R16 ? 2 : 4;
+        s.tile_bytes = (size_t)a.texture_size * a.texture_size * s.px;
+        p->stores.push_back(std::move(s));
+    }
+    *out = p;
+    return BT_OK;
+}
+
+void bt_preprocessor_destroy(bt_preprocessor* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();
+    for (Store& s : p->stores) if (s.arena) cudaFree(s.arena);
+    for (Job& j : p->jobs) for (void* px : j.owned_pixels) cudaFree(px);
+    cudaFree(p->d_tasks); cudaFree(p->d_datasets); cudaFree(p->d_copies);
+    delete p;
+}
+
+bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* datasets, uint32_t count) {
+    if (!p || !datasets || count == 0) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = p->ctx;
+    Job j;
+    j.attachment = datasets[0].attachment_index;
+    if (j.attachment >= p->stores.size()) { ctx->set_error("add_datasets: attachment_index %u out of range", j.attachment); return BT_ERR_INVALID_ARG; }
+    if (p->shard.world > 1 && count != 1) { ctx->set_error("add_datasets: sharded preprocessing takes one dataset per job"); return BT_ERR_INVALID_ARG; }
+    uint32_t side_mask = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        const bt_dataset& d = datasets[i];
+        if (d.attachment_index != j.attachment || d.side >= 6 || d.lod_begin >= d.lod_end || d.lod_end > p->lod_count || !d.pixels || d.width == 0 || d.height == 0) {
+            ctx->set_error("add_datasets: dataset %u invalid (attachment/side/lod_range %u..%u of %u/pixels)", i, d.lod_begin, d.lod_end, p->lod_count);
+            return BT_ERR_INVALID_ARG;
+        }
+        if (!(d.bottom_right[0] > d.top_left[0]) || !(d.bottom_right[1] > d.top_left[1])) { ctx->set_error("add_datasets: empty extent"); return BT_ERR_INVALID_ARG; }
+        if (count > 1 && (side_mask & (1u << d.side))) { ctx->set_error("add_datasets: datasets of one job must lie on distinct sides"); return BT_ERR_INVALID_ARG; }
+        side_mask |= 1u << d.side;
+        if (p->shard.world > 1) {
+            if (d.top_left[0] != 0.0f || d.top_left[1] != 0.0f || d.bottom_right[0] != 1.0f || d.bottom_right[1] != 1.0f || d.lod_end - 1 < p->root_lod) {
+                ctx->set_error("add_datasets: sharded preprocessing needs a full-coverage dataset whose deepest LOD has >= world tile rows");
+                return BT_ERR_INVALID_ARG;
+            }
+        }
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Store& s = p->stores[j.attachment];
+    for (uint32_t i = 0; i < count; ++i) {
+        bt_dataset d = datasets[i];
+        if (!d.pixels_on_device) {  // stage the host image on the device (the reference uploads the Image asset, preprocessor.rs:241-246)
+            void* dev = nullptr;
+            const size_t bytes = (size_t)d.width * d.height * s.px;
+            BT_CUDA(ctx, cudaMalloc(&dev, bytes));
+            cudaError_t e = cudaMemcpy(dev, d.pixels, bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(dev); BT_CUDA(ctx, e); }
+            j.owned_pixels.push_back(dev);
+            d.pixels = dev;
+            d.pixels_on_device = 1;
+        }
+        j.datasets.push_back(d);
+    }
+    p->jobs.push_back(std::move(j));
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_run(bt_preprocessor* p, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    if (p->shard.world != 1) { p->ctx->set_error("bt_preprocessor_run: sharded runs use the phase API (split_downsample / roots / halo / stitch)"); return BT_ERR_INVALID_ARG; }
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    for (int ji; (ji = p->pending_job()) >= 0;) {
+        bt_status st = p->run_split_downsample_job((uint32_t)ji, (cudaStream_t)stream);
+        if (st == BT_OK) st = p->run_stitch_job((uint32_t)ji, (cudaStream_t)stream);
+        if (st != BT_OK) return st;
+    }
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_run_split_downsample(bt_preprocessor* p, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || p->jobs[ji].split_done) { p->ctx->set_error("run_split_downsample: no pending job"); return BT_ERR_INVALID_ARG; }
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    return p->run_split_downsample_job((uint32_t)ji, (cudaStream_t)stream);
+}
+
+bt_status bt_preprocessor_run_stitch(bt_preprocessor* p, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || !p->jobs[ji].split_done) { p->ctx->set_error("run_stitch: run_split_downsample has not run"); return BT_ERR_INVALID_ARG; }
+    const Job& j = p->jobs[ji];
+    if (p->shard.world > 1 && ((p->roots_bytes(j) && !j.roots_done) || (p->halo_bytes(j) && !j.halo_done))) {
+        p->ctx->set_error("run_stitch: the sub-root gather / halo exchange has not been completed on this rank");
+        return BT_ERR_INVALID_ARG;
+    }
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    return p->run_stitch_job((uint32_t)ji, (cudaStream_t)stream);
+}
+
+// ---- multi-GPU: sub-root gather --------------------------------------------------------------------
+bt_status bt_preprocessor_roots_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank) {
+    if (!p || !send_bytes_per_rank) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    *send_bytes_per_rank = ji < 0 ? 0 : p->roots_bytes(p->jobs[ji]);
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_roots_pack(bt_preprocessor* p, void* device_send, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
+    const Job& j = p->jobs[ji];
+    if (p->roots_bytes(j) == 0) return BT_OK;
+    if (!device_send) return BT_ERR_INVALID_ARG;
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    Store& s = p->stores[j.attachment];
+    const uint32_t n = 1u << p->root_lod;
+    for (uint32_t x = 0; x < n; ++x) {  // my single owned row of the root level, x-major
+        const uint32_t slot = s.slot_of.at(TileKey{j.datasets[0].side, p->root_lod, x, p->shard.rank});
+        BT_CUDA(p->ctx, cudaMemcpyAsync(static_cast<unsigned char*>(device_send) + (size_t)x * s.tile_bytes, s.arena + (size_t)slot * s.tile_bytes,
+                                        s.tile_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_roots_unpack_and_finish(bt_preprocessor* p, const void* device_gathered, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
+    Job& j = p->jobs[ji];
+    if (p->roots_bytes(j) == 0) { j.roots_done = true; return BT_OK; }
+    if (!device_gathered) return BT_ERR_INVALID_ARG;
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    Store& s = p->stores[j.attachment];
+    const uint32_t n = 1u << p->root_lod;
+    const uint64_t per_rank = p->roots_bytes(j);
+    for (uint32_t r = 0; r < p->shard.world; ++r) {
+        if (r == p->shard.rank) continue;
+        for (uint32_t x = 0; x < n; ++x) {
+            const uint32_t slot = s.slot_of.at(TileKey{j.datasets[0].side, p->root_lod, x, r});
+            BT_CUDA(p->ctx, cudaMemcpyAsync(s.arena + (size_t)slot * s.tile_bytes,
+                                            static_cast<const unsigned char*>(device_gathered) + (size_t)r * per_rank + (size_t)x * s.tile_bytes,
+                                            s.tile_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        }
+    }
+    // the levels above the shard boundary: every rank computes them (21 tiles at world = 8)
+    bt_status st = p->run_levels((uint32_t)ji, p->root_lod, j.datasets[0].lod_begin, false, (cudaStream_t)stream);
+    if (st == BT_OK) j.roots_done = true;
+    return st;
+}
+
+// ---- multi-GPU: halo strips -----------------------------------------------------------------------
+bt_status bt_preprocessor_halo_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank) {
+    if (!p || !send_bytes_per_rank) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    *send_bytes_per_rank = ji < 0 ? 0 : p->halo_bytes(p->jobs[ji]);
+    return BT_OK;
+}
+
+static bt_status halo_copies(bt_preprocessor* p, const Job& j, unsigned char* buffer, bool pack, std::vector<RowCopy>& out) {
+    Store& s = p->stores[j.attachment];
+    const bt_dataset& d = j.datasets[0];
+    const uint32_t T = s.cfg.texture_size, B = s.cfg.border_size, C = T - 2 * B;
+    const uint64_t per_rank = p->halo_bytes(j);
+    const uint64_t row_bytes = (uint64_t)C * s.px;
+    uint64_t offset = 0;
+    for (uint32_t lod = std::max(d.lod_begin, p->root_lod + 1); lod < d.lod_end; ++lod) {
+        const uint32_t n = 1u << lod;
+        uint32_t y0, y1;
+        p->owned_rows(lod, &y0, &y1);
+        const uint64_t strip = (uint64_t)B * row_bytes, half = (uint64_t)n * strip;
+        for (uint32_t x = 0; x < n; ++x) {
+            for (uint32_t b = 0; b < B; ++b) {
+                if (pack) {
+                    // top strip: first B centre rows of my first row; bottom strip: last B centre rows of my last row
+                    const unsigned char* top = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y0}) * s.tile_bytes + ((size_t)(B + b) * T + B) * s.px;
+                    const unsigned char* bot = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y1 - 1}) * s.tile_bytes + ((size_t)(B + C - B + b) * T + B) * s.px;
+                    out.push_back(RowCopy{top, buffer + offset + (uint64_t)x * strip + (uint64_t)b * row_bytes, row_bytes});
+                    out.push_back(RowCopy{bot, buffer + offset + half + (uint64_t)x * strip + (uint64_t)b * row_bytes, row_bytes});
+                } else {
+                    if (y0 > 0) {  // ghost row above me <- bottom strip of rank-1
+                        unsigned char* dst = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y0 - 1}) * s.tile_bytes + ((size_t)(B + C - B + b) * T + B) * s.px;
+                        out.push_back(RowCopy{buffer + (uint64_t)(p->shard.rank - 1) * per_rank + offset + half + (uint64_t)x * strip + (uint64_t)b * row_bytes, dst, row_bytes});
+                    }
+                    if (y1 < n) {  // ghost row below me <- top strip of rank+1
+                        unsigned char* dst = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y1}) * s.tile_bytes + ((size_t)(B + b) * T + B) * s.px;
+                        out.push_back(RowCopy{buffer + (uint64_t)(p->shard.rank + 1) * per_rank + offset + (uint64_t)x * strip + (uint64_t)b * row_bytes, dst, row_bytes});
+                    }
+                }
+            }
+        }
+        offset += 2 * half;
+    }
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_halo_pack(bt_preprocessor* p, void* device_send, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
+    const Job& j = p->jobs[ji];
+    if (p->halo_bytes(j) == 0) return BT_OK;
+    if (!device_send) return BT_ERR_INVALID_ARG;
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    std::vector<RowCopy> copies;
+    halo_copies(p, j, static_cast<unsigned char*>(device_send), true, copies);
+    bt_status st = p->upload(&p->d_copies, &p->d_copies_cap, copies, (cudaStream_t)stream);
+    if (st != BT_OK) return st;
+    BT_CUDA(p->ctx, bt_launch_row_copy(p->d_copies, (uint32_t)copies.size(), (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_halo_unpack(bt_preprocessor* p, const void* device_gathered, void* stream) {
+    if (!p) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
+    Job& j = p->jobs[ji];
+    if (p->halo_bytes(j) == 0) { j.halo_done = true; return BT_OK; }
+    if (!device_gathered) return BT_ERR_INVALID_ARG;
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    std::vector<RowCopy> copies;
+    halo_copies(p, j, const_cast<unsigned char*>(static_cast<const unsigned char*>(device_gathered)), false, copies);
+    BT_CUDA(p->ctx, cudaStreamSynchronize((cudaStream_t)stream));  // the pack launch may still read d_copies
+    bt_status st = p->upload(&p->d_copies, &p->d_copies_cap, copies, (cudaStream_t)stream);
+    if (st != BT_OK) return st;
+    BT_CUDA(p->ctx, bt_launch_row_copy(p->d_copies, (uint32_t)copies.size(), (cudaStream_t)stream));
+    j.halo_done = true;
+    return BT_OK;
+}
+
+// ---- results --------------------------------------------------------------------------------------
+static bool is_output(const bt_preprocessor* p, const Store& s, uint32_t slot) { (void)p; return s.kind[slot] == kOwned; }
+
+bt_status bt_preprocessor_tile_count(bt_preprocessor* p, uint32_t attachment, uint32_t* count) {
+    if (!p || !count || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    const Store& s = p->stores[attachment];
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < s.keys.size(); ++i) n += is_output(p, s, i);
+    *count = n;
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_list_tiles(bt_preprocessor* p, uint32_t attachment, bt_tile* tiles, uint32_t cap, uint32_t* count) {
+    if (!p || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    const Store& s = p->stores[attachment];
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < s.keys.size(); ++i) {
+        if (!is_output(p, s, i)) continue;
+        if (tiles && n < cap) tiles[n] = bt_tile{s.keys[i].side, s.keys[i].lod, s.keys[i].x, s.keys[i].y};
+        ++n;
+    }
+    if (count) *count = n;
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_tile_device_ptr(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void** out) {
+    if (!p || !tile || !out || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    const Store& s = p->stores[attachment];
+    auto it = s.slot_of.find(TileKey{tile->side, tile->lod, tile->x, tile->y});
+    if (it == s.slot_of.end() || !s.arena || it->second >= s.zeroed_slots) return BT_ERR_NOT_FOUND;
+    *out = s.arena + (size_t)it->second * s.tile_bytes;
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_get_tile(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void* host_out, size_t bytes) {
+    void* dev = nullptr;
+    if (!host_out) return BT_ERR_INVALID_ARG;
+    bt_status st = bt_preprocessor_tile_device_ptr(p, attachment, tile, &dev);
+    if (st != BT_OK) return st;
+    if (bytes != p->stores[attachment].tile_bytes) { p->ctx->set_error("get_tile: expected %zu bytes", p->stores[attachment].tile_bytes); return BT_ERR_INVALID_ARG; }
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    BT_CUDA(p->ctx, cudaMemcpy(host_out, dev, bytes, cudaMemcpyDeviceToHost));
+    return BT_OK;
+}
+
+// bincode 2 "standard" varint (formats/mod.rs:14-24)
+static void put_varint(std::vector<unsigned char>& out, uint64_t v) {
+    if (v < 251) out.push_back((unsigned char)v);
+    else if (v < (1ull << 16)) { out.push_back(251); for (int i = 0; i < 2; ++i) out.push_back((unsigned char)(v >> (8 * i))); }
+    else if (v < (1ull << 32)) { out.push_back(252); for (int i = 0; i < 4; ++i) out.push_back((unsigned char)(v >> (8 * i))); }
+    else { out.push_back(253); for (int i = 0; i < 8; ++i) out.push_back((unsigned char)(v >> (8 * i))); }
+}
+
+// Save tasks + save_tile_config (tile_atlas.rs:77-116,605-613): raw mip-0 texels per tile and the
+// bincode tile list.  Files go to <directory>/<side>_<lod>_<x>_<y>.bin and <directory>/config.tc.
+bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const char* directory) {
+    if (!p || !directory || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = p->ctx;
+    const Store& s = p->stores[attachment];
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaDeviceSynchronize());
+    std::vector<unsigned char> host(s.tile_bytes), tc;
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < s.keys.size(); ++i) n += is_output(p, s, i);
+    put_varint(tc, n);
+    for (uint32_t i = 0; i < s.keys.size(); ++i) {
+        if (!is_output(p, s, i)) continue;
+        const TileKey& k = s.keys[i];
+        BT_CUDA(ctx, cudaMemcpy(host.data(), s.arena + (size_t)i * s.tile_bytes, s.tile_bytes, cudaMemcpyDeviceToHost));
+        const std::string path = std::string(directory) + "/" + std::to_string(k.side) + "_" + std::to_string(k.lod) + "_" + std::to_string(k.x) + "_" + std::to_string(k.y) + ".bin";
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f || std::fwrite(host.data(), 1, host.size(), f) != host.size()) {
+            if (f) std::fclose(f);
+            ctx->set_error("bt_preprocessor_save: cannot write %s", path.c_str());
+            return BT_ERR_IO;
+        }
+        std::fclose(f);
+        put_varint(tc, k.side); put_varint(tc, k.lod); put_varint(tc, k.x); put_varint(tc, k.y);
+    }
+    const std::string path = std::string(directory) + "/config.tc";
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f || std::fwrite(tc.data(), 1, tc.size(), f) != tc.size()) {
+        if (f) std::fclose(f);
+        ctx->set_error("bt_preprocessor_save: cannot write %s", path.c_str());
+        return BT_ERR_IO;
+    }
+    std::fclose(f);
+    return BT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// bt_runtime.h — internal definitions of the opaque C-ABI handles.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/bevy_terrain_b200.h"
+#include "bt_kernels.h"
+
+struct bt_context {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0;
+    std::mutex error_mutex;
+    std::string error;
+    void set_error(const char* fmt, ...);
+};
+
+#define BT_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t bt_e_ = (expr);                                                                \
+        if (bt_e_ != cudaSuccess) {                                                                \
+            (ctx)->set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(bt_e_)); \
+            (void)cudaGetLastError();                                                              \
+            return bt_e_ == cudaErrorMemoryAllocation ? BT_ERR_OUT_OF_MEMORY : BT_ERR_CUDA;        \
+        }                                                                                          \
+    } while (0)
+
+struct bt_terrain {
+    bt_context* ctx = nullptr;
+    bt_terrain_desc desc{};
+    void* atlas[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t tile_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct bt_view {
+    bt_terrain* terrain = nullptr;
+    bt_view_desc desc{};
+    uint32_t tile_tree_entries = 0;
+    void* d_uniforms = nullptr;
+    bt_tile* d_final_tiles = nullptr;
+    bt_tile* d_temporary_tiles = nullptr;
+    bt_indirect* d_indirect = nullptr;
+    btd::SelectStatus* d_select_status = nullptr;
+    btd::GenStatus* d_gen_status = nullptr;
+    bt_tile_tree_entry* d_tile_tree = nullptr;
+    bt_vertex* d_vertices = nullptr;
+    uint64_t vertex_capacity = 0;
+    void* h_uniforms = nullptr;
+    void* h_tile_tree = nullptr;
+    void* h_readback = nullptr;
+    cudaEvent_t staging_free = nullptr;
+    size_t h2d_bytes_last_update = 0;
+    bool updated = false;
+};
+
+extern "C" {
+cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
+                            const btd::PyramidTask* tasks, uint32_t n_tasks, const btd::DatasetDevice* datasets, cudaStream_t stream);
+cudaError_t bt_launch_downsample(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
+                                 const btd::PyramidTask* tasks, uint32_t n_tasks, cudaStream_t stream);
+cudaError_t bt_launch_stitch(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
+                             const btd::PyramidTask* tasks, uint32_t n_tasks, cudaStream_t stream);
+cudaError_t bt_launch_mipmaps(uint32_t format, uint32_t texture_size, uint32_t mip_level_count, const void* mip0,
+                              void* mips_out, cudaStream_t stream);
+cudaError_t bt_launch_synth(uint32_t format, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t seed,
+                            uint32_t holes, void* out, cudaStream_t stream);
+cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream);
+}

@@ -1,0 +1,326 @@
+// gen_vertices.cu — per-tile heightmap-sampled vertex-grid generation (positions + normals).
+//
+// Replaces the vertex stage of the reference's indirect draw (src/shaders/render/vertex.wgsl:85-98,
+// driven by DrawTerrainCommand, src/render/terrain_view_bind_group.rs:274-298) and fuses the
+// height-derived normal of the fragment stage (sample_normal, src/shaders/attachments.wgsl:51-107,
+// blended as src/shaders/render/fragment.wgsl:99-107).
+//
+// Design (B200):
+//   * persistent CTAs (one per SM) stride over work items = (tile, block of CB column strips)
+//   * the reference's triangle-strip index stream visits every grid vertex ~2x (8448 strip
+//     vertices for 65x65 = 4225 unique ones at grid 64, compute_tile_uv functions.wgsl:64-71);
+//     each unique vertex is computed ONCE and scattered to its 2-3 strip positions in a
+//     shared-memory image of the output block — bit-identical to recomputation because the
+//     vertex is a pure function of (tile, column, row)
+//   * the image is written to HBM with TMA 1-D bulk stores (cp.async.bulk.global.shared::cta,
+//     one per strip), double-buffered so the stores of item i overlap the compute of item i+1;
+//     HBM sees only full-line, fully coalesced writes of the 40-B interleaved records
+//   * the uniform block is staged into shared memory with one TMA bulk load + mbarrier
+//   * height texels are gathered with read-only (ld.global.nc) 16-bit loads; lanes walk along
+//     texel rows so one request touches 1-3 cache lines; exact-f32 bilinear weights (no texture
+//     unit: its fixed-point weights are not reproducible)
+#include "bt_device.cuh"
+#include "bt_kernels.h"
+
+namespace btd {
+
+constexpr int GEN_THREADS = 576;       // 18 warps: 2 rounds cover the 17x65 = 1105 vertices of a g=64 work item
+constexpr uint32_t STRIP_PAD = 16;     // bytes between strips in the smem image (bank spreading; keeps 16-B alignment)
+
+struct GenParams {
+    const ViewUniforms* uniforms;
+    const bt_tile* tiles;
+    const bt_indirect* indirect;
+    const bt_tile_tree_entry* tile_tree;
+    const uint16_t* height_atlas;
+    bt_vertex* vertices;
+    uint64_t vertex_capacity;
+    GenStatus* status;
+    uint32_t flags;
+    uint32_t grid_size;        // g
+    uint32_t strips_per_item;  // CB
+    uint32_t items_per_tile;   // ceil(g / CB)
+    uint32_t image_bytes;      // CB * (strip_bytes + STRIP_PAD), per buffer
+};
+
+struct Record {  // one bt_vertex as five 8-byte words
+    float2 w[5];
+};
+
+// bilinear R16 fetch — exact f32 weights, texel centres at i+0.5, clamp-to-edge; operation order
+// of the CPU twin AttachmentData::sample (src/terrain_data/mod.rs:221-264): lerp y, then x
+__device__ __forceinline__ float sample_r16(const uint16_t* __restrict__ layer, uint32_t T, float u, float v) {
+    float Tf = (float)T;
+    float px = u * Tf - 0.5f, py = v * Tf - 0.5f;
+    float fx = floorf(px), fy = floorf(py);
+    float rx = px - fx, ry = py - fy;
+    int ix = (int)fx, iy = (int)fy;
+    int m = (int)T - 1;
+    int x0 = min(max(ix, 0), m), x1 = min(max(ix + 1, 0), m);
+    int y0 = min(max(iy, 0), m), y1 = min(max(iy + 1, 0), m);
+    const uint16_t* r0 = layer + (size_t)y0 * T;
+    const uint16_t* r1 = layer + (size_t)y1 * T;
+    float v00 = (float)__ldg(r0 + x0) / 65535.0f;
+    float v01 = (float)__ldg(r1 + x0) / 65535.0f;
+    float v10 = (float)__ldg(r0 + x1) / 65535.0f;
+    float v11 = (float)__ldg(r1 + x1) / 65535.0f;
+    float a = v00 + (v01 - v00) * ry;
+    float b = v10 + (v11 - v10) * ry;
+    return a + (b - a) * rx;
+}
+
+struct AtlasTile {
+    uint32_t index;
+    Coord c;
+};
+
+// lookup_tile (default variant) — functions.wgsl:232-246,198-206
+__device__ __forceinline__ AtlasTile lookup_tile(const ViewUniforms& U, const bt_tile_tree_entry* __restrict__ tile_tree,
+                                                 Coord c, uint32_t lod) {
+    change_lod(c, lod);
+    const uint32_t ts = U.view_config.tree_size;
+    const uint32_t idx = ((c.side * U.terrain_config.lod_count + c.lod) * ts + c.x % ts) * ts + c.y % ts;
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(tile_tree) + idx);
+    change_lod(c, e.y);
+    return AtlasTile{e.x, c};
+}
+
+// sample_height — attachments.wgsl:7-24,45-49
+__device__ __forceinline__ float sample_height_uv(const ViewUniforms& U, const uint16_t* __restrict__ atlas, uint32_t index, float u, float v) {
+    const uint32_t T = U.texture_size;
+    const float s = sample_r16(atlas + (size_t)index * T * T, T, u, v);
+    return mix(U.terrain_config.min_height, U.terrain_config.max_height, s);
+}
+
+// sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch)
+template <bool SPHERICAL>
+__device__ __forceinline__ Vec3 sample_normal(const ViewUniforms& U, const uint16_t* __restrict__ atlas, const AtlasTile& t,
+                                              float u, float v, Vec3 vertex_normal) {
+    const float side_length = SPHERICAL ? (float)(3.14159265359 / 4.0) * U.terrain_config.scale : U.terrain_config.scale;
+    const float pixels_per_side = U.attachments[0].size * tile_count(t.c.lod);
+    const float distance_between_samples = side_length / pixels_per_side;
+    const float offset = 0.5f / U.attachments[0].size;
+    const float left = sample_height_uv(U, atlas, t.index, u + -offset, v + 0.0f);
+    const float up = sample_height_uv(U, atlas, t.index, u + 0.0f, v + -offset);
+    const float right = sample_height_uv(U, atlas, t.index, u + offset, v + 0.0f);
+    const float down = sample_height_uv(U, atlas, t.index, u + 0.0f, v + offset);
+    const Vec3 sn = normalize3(Vec3{left - right, down - up, distance_between_samples});
+    Vec3 r;
+    if (SPHERICAL) {
+        Vec3 face_up;
+        switch (t.c.side) {
+            case 0: case 1: face_up = Vec3{0.0f, 1.0f, 0.0f}; break;
+            case 2: case 3: face_up = Vec3{0.0f, 0.0f, -1.0f}; break;
+            default: face_up = Vec3{-1.0f, 0.0f, 0.0f}; break;
+        }
+        const Vec3 n = normalize3(vertex_normal);
+        const Vec3 tg = cross3(face_up, n);
+        const Vec3 bt = cross3(n, tg);
+        r = Vec3{(tg.x * sn.x + bt.x * sn.y) + n.x * sn.z, (tg.y * sn.x + bt.y * sn.y) + n.y * sn.z,
+                 (tg.z * sn.x + bt.z * sn.y) + n.z * sn.z};
+    } else {
+        r = Vec3{sn.x, sn.z, sn.y};  // TBN columns (1,0,0),(0,0,1),(0,1,0)
+    }
+    return normalize3(r);
+}
+
+// vertex_info + vertex + vertex_output — vertex.wgsl:30-98
+template <bool SPHERICAL>
+__device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const bt_tile_tree_entry* __restrict__ tile_tree,
+                                                 const uint16_t* __restrict__ atlas, uint32_t flags, const bt_tile& tile,
+                                                 uint32_t tile_index, uint32_t gx, uint32_t gy) {
+    const bt_view_config_uniform& vc = U.view_config;
+    const bt_model_approximation& ap = U.approximation;
+    const float g = vc.grid_size;
+    const Coord c0{tile.side, tile.lod, tile.x, tile.y, (float)gx / g, (float)gy / g};  // compute_tile_uv
+    Vec3 lp = local_position<SPHERICAL>(c0);
+    Vec3 wp = position_local_to_world(U.mesh, lp);
+    Vec3 wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+    const float h0 = ap.approximate_height;
+    const float* e = U.view_world_position;
+    float d = length3(Vec3{(wp.x + h0 * wn.x) - e[0], (wp.y + h0 * wn.y) - e[1], (wp.z + h0 * wn.z) - e[2]});
+    const bool high_precision = (flags & BT_FLAG_HIGH_PRECISION) && d < vc.precision_threshold_distance;
+    if (high_precision) {
+        const Vec3 rel = relative_position(ap, c0);
+        d = length3(Vec3{rel.x + h0 * wn.x, rel.y + h0 * wn.y, rel.z + h0 * wn.z});
+    }
+    // compute_morph — functions.wgsl:35-49
+    Coord c = c0;
+    if (flags & BT_FLAG_MORPH) {
+        const float target_lod = log2_det(2.0f * vc.morph_distance / d);
+        const float ratio = (c0.lod == 0u) ? 0.0f : inverse_mix((float)c0.lod + vc.morph_range, (float)c0.lod, target_lod);
+        const float even_u = (float)(f2u(c0.u * g) & ~1u) / g;
+        const float even_v = (float)(f2u(c0.v * g) & ~1u) / g;
+        c.u = mix(c0.u, even_u, ratio);
+        c.v = mix(c0.v, even_v, ratio);
+    }
+    if (high_precision) {
+        const Vec3 rel = relative_position(ap, c);
+        wp = Vec3{e[0] + rel.x, e[1] + rel.y, e[2] + rel.z};
+    } else {
+        lp = local_position<SPHERICAL>(c);
+        wp = position_local_to_world(U.mesh, lp);
+        wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+    }
+    // compute_blend — functions.wgsl:51-62
+    const float target_lod = fminf(log2_det(vc.blend_distance / d), (float)U.terrain_config.lod_count - 0.00001f);
+    const uint32_t blend_lod = f2u(target_lod);
+    float blend_ratio = 0.0f;
+    if ((flags & BT_FLAG_BLEND) && blend_lod != 0u)
+        blend_ratio = inverse_mix((float)blend_lod + vc.blend_range, (float)blend_lod, target_lod);
+
+    const float a_scale = U.attachments[0].scale, a_offset = U.attachments[0].offset;
+    const AtlasTile ta = lookup_tile(U, tile_tree, c, blend_lod);
+    const float ua = ta.c.u * a_scale + a_offset, va = ta.c.v * a_scale + a_offset;  // attachment_uv
+    float height = sample_height_uv(U, atlas, ta.index, ua, va);
+    Vec3 nrm = wn;
+    if (flags & BT_FLAG_NORMALS) nrm = sample_normal<SPHERICAL>(U, atlas, ta, ua, va, wn);
+    if (blend_ratio > 0.0f) {
+        const AtlasTile tb = lookup_tile(U, tile_tree, c, blend_lod - 1u);
+        const float ub = tb.c.u * a_scale + a_offset, vb = tb.c.v * a_scale + a_offset;
+        height = mix(height, sample_height_uv(U, atlas, tb.index, ub, vb), blend_ratio);
+        if (flags & BT_FLAG_NORMALS) {  // fragment.wgsl:103-107
+            const Vec3 n2 = sample_normal<SPHERICAL>(U, atlas, tb, ub, vb, wn);
+            nrm = Vec3{mix(nrm.x, n2.x, blend_ratio), mix(nrm.y, n2.y, blend_ratio), mix(nrm.z, n2.z, blend_ratio)};
+        }
+    }
+    Record r;  // vertex_output — vertex.wgsl:73-83
+    r.w[0] = make_float2(wp.x + height * wn.x, wp.y + height * wn.y);
+    r.w[1] = make_float2(wp.z + height * wn.z, 1.0f);
+    r.w[2] = make_float2(nrm.x, nrm.y);
+    r.w[3] = make_float2(nrm.z, c.u);
+    r.w[4] = make_float2(c.v, __uint_as_float(tile_index));
+    return r;
+}
+
+__device__ __forceinline__ void store_record(unsigned char* image, uint32_t strip_stride, uint32_t strip, uint32_t k, const Record& r) {
+    float2* dst = reinterpret_cast<float2*>(image + (size_t)strip * strip_stride + (size_t)k * sizeof(bt_vertex));
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = r.w[i];
+}
+
+struct GenSmemHeader {
+    ViewUniforms U;
+    uint64_t bar;
+    uint64_t _pad;
+};
+
+template <bool SPHERICAL>
+__global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    GenSmemHeader& H = *reinterpret_cast<GenSmemHeader*>(smem_raw);
+    unsigned char* images = smem_raw + ((sizeof(GenSmemHeader) + 127) & ~size_t(127));
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&H.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&H.bar, (uint32_t)sizeof(ViewUniforms));
+        bulk_load(&H.U, P.uniforms, (uint32_t)sizeof(ViewUniforms), &H.bar);
+    }
+    mbar_wait(&H.bar, 0);
+    const ViewUniforms& U = H.U;
+
+    const uint32_t g = P.grid_size;
+    const uint32_t vpr = U.view_config.vertices_per_row, vpt = U.view_config.vertices_per_tile;
+    const uint32_t strip_bytes = vpr * (uint32_t)sizeof(bt_vertex);
+    const uint32_t strip_stride = strip_bytes + STRIP_PAD;
+    uint32_t n_tiles = __ldg(&P.indirect->vertex_count) / vpt;
+    const uint64_t cap_tiles = P.vertex_capacity / vpt;
+    if (n_tiles > cap_tiles) {
+        if (blockIdx.x == 0 && tid == 0) P.status->overflow = 1u;
+        n_tiles = (uint32_t)cap_tiles;
+    } else if (blockIdx.x == 0 && tid == 0) {
+        P.status->overflow = 0u;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        const uint64_t n = (uint64_t)n_tiles * vpt;
+        P.status->vertex_count_lo = (uint32_t)n;
+        P.status->vertex_count_hi = (uint32_t)(n >> 32);
+    }
+    const uint32_t n_items = n_tiles * P.items_per_tile;
+
+    uint32_t it = 0;
+    for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const uint32_t tile_index = w / P.items_per_tile;
+        const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
+        const uint32_t n_strips = min(P.strips_per_item, g - c0);
+        const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
+        unsigned char* image = images + (size_t)(it & 1u) * P.image_bytes;
+
+        // the bulk stores issued from this buffer two items ago must have finished READING it
+        if (tid == 0) bulk_wait_read<1>();
+        __syncthreads();
+
+        const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
+        const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
+        const uint32_t n_verts = n_cols * n_rows;
+        for (uint32_t i = tid; i < n_verts; i += GEN_THREADS) {
+            const uint32_t gy = i / n_cols, lx = i - gy * n_cols;  // lanes walk along texel rows
+            const Record r = compute_vertex<SPHERICAL>(U, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
+            // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
+            if (lx < n_strips) {
+                store_record(image, strip_stride, lx, 2u * gy + 1u, r);
+                if (gy == 0u) store_record(image, strip_stride, lx, 0u, r);
+            }
+            // strip `lx-1`: this vertex is (column+1, row 2*gy+1) -> position 2*gy+2 (+ duplicated last index)
+            if (lx >= 1u) {
+                store_record(image, strip_stride, lx - 1u, 2u * gy + 2u, r);
+                if (gy == g) store_record(image, strip_stride, lx - 1u, vpr - 1u, r);
+            }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
+                                 ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
+            for (uint32_t s = 0; s < n_strips; ++s)
+                bulk_store(out + (size_t)s * strip_bytes, image + (size_t)s * strip_stride, strip_bytes);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait<0>();
+}
+
+}  // namespace btd
+
+extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_tile* final_tiles, const bt_indirect* indirect,
+                                              const bt_tile_tree_entry* tile_tree, const uint16_t* height_atlas,
+                                              bt_vertex* vertices, uint64_t vertex_capacity, btd::GenStatus* status,
+                                              int spherical, uint32_t flags, uint32_t grid_size, int sm_count,
+                                              cudaStream_t stream) {
+    using namespace btd;
+    if (grid_size == 0) return cudaErrorInvalidValue;
+    const uint32_t strip_stride = 2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex) + STRIP_PAD;
+    const size_t header = (sizeof(GenSmemHeader) + 127) & ~size_t(127);
+    const size_t budget = 200 * 1024 - header;  // leave L1 some room out of the 227 KiB
+    uint32_t cb = (uint32_t)(budget / (2ull * strip_stride));
+    if (cb > 16u) cb = 16u;
+    if (cb > grid_size) cb = grid_size;
+    if (cb == 0) return cudaErrorInvalidValue;  // grid_size too large for a double-buffered strip
+    GenParams P;
+    P.uniforms = static_cast<const ViewUniforms*>(uniforms);
+    P.tiles = final_tiles;
+    P.indirect = indirect;
+    P.tile_tree = tile_tree;
+    P.height_atlas = height_atlas;
+    P.vertices = vertices;
+    P.vertex_capacity = vertex_capacity;
+    P.status = status;
+    P.flags = flags;
+    P.grid_size = grid_size;
+    P.strips_per_item = cb;
+    P.items_per_tile = (grid_size + cb - 1u) / cb;
+    P.image_bytes = cb * strip_stride;
+    const size_t smem = header + 2ull * P.image_bytes;
+    cudaError_t e = cudaFuncSetAttribute(spherical ? gen_vertices_kernel<true> : gen_vertices_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = sm_count > 0 ? sm_count : 148;
+    if (spherical) gen_vertices_kernel<true><<<grid, GEN_THREADS, smem, stream>>>(P);
+    else gen_vertices_kernel<false><<<grid, GEN_THREADS, smem, stream>>>(P);
+    return cudaGetLastError();
+}

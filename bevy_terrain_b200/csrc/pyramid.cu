@@ -1,0 +1,440 @@
+// pyramid.cu — tile-pyramid preprocessor kernels: split / downsample / stitch (+ mips, synth).
+//
+// Replaces the reference's WGSL compute entry points split.wgsl:46-49, downsample.wgsl:43-46 and
+// stitch.wgsl:121-124 (each dispatched per tile through a buffer "write section" with a
+// texture->buffer->texture round trip, src/preprocess/mod.rs:143-217).  Here the kernels operate
+// directly on the device-resident pyramid store (one arena of T*T-pixel tiles per attachment):
+//   * one launch per phase covers ALL tiles of that phase (task table in device memory)
+//   * every thread produces 16 bytes of output (8 R16 or 4 Rgba8 pixels) and stores it with one
+//     128-bit write: the coalescing the reference's "Todo: respect memory coalescing" asks for
+//   * stitch runs IN PLACE and writes only the border ring: it reads only neighbour CENTRES
+//     (stitch.wgsl:76-96), so there is no ordering hazard between stitch tasks
+// Arithmetic follows the numerics contract (bt_device.cuh): unorm decode v/65535, sums and the
+// mean in f32 in shader order, pack = floor(0.5 + M*clamp(v,0,1)); no FMA contraction.
+#include "bt_device.cuh"
+#include "bt_kernels.h"
+
+namespace btd {
+
+constexpr int PYR_THREADS = 256;
+constexpr uint32_t INVALID_SLOT = 0xFFFFFFFFu;
+
+struct PyramidLayout {
+    unsigned char* arena;   // slot s at arena + s * tile_bytes
+    uint64_t tile_bytes;
+    uint32_t T, B, C, format;
+};
+
+struct Px4 { float v[4]; };
+
+template <int FORMAT> struct Fmt;
+template <> struct Fmt<BT_FORMAT_R16> {
+    using texel = uint16_t;
+    static constexpr int PX_PER_THREAD = 8;
+    static __device__ __forceinline__ Px4 decode(uint16_t t) { return Px4{{(float)t / 65535.0f, 0.0f, 0.0f, 1.0f}}; }
+    static __device__ __forceinline__ uint16_t zero() { return 0; }
+    static __device__ __forceinline__ uint16_t pack(const Px4& p) {  // pack2x16unorm — preprocessing.wgsl:85-88
+        float c = fminf(fmaxf(p.v[0], 0.0f), 1.0f);
+        return (uint16_t)(uint32_t)floorf(0.5f + 65535.0f * c);
+    }
+};
+template <> struct Fmt<BT_FORMAT_RGBA8> {
+    using texel = uchar4;
+    static constexpr int PX_PER_THREAD = 4;
+    static __device__ __forceinline__ Px4 decode(uchar4 t) {
+        return Px4{{(float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f}};
+    }
+    static __device__ __forceinline__ uchar4 zero() { return make_uchar4(0, 0, 0, 0); }
+    static __device__ __forceinline__ uchar4 pack(const Px4& p) {  // pack4x8unorm — preprocessing.wgsl:81-84
+        uchar4 r;
+        r.x = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[0], 0.0f), 1.0f));
+        r.y = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[1], 0.0f), 1.0f));
+        r.z = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[2], 0.0f), 1.0f));
+        r.w = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[3], 0.0f), 1.0f));
+        return r;
+    }
+};
+
+template <typename texel, int N>
+struct alignas(16) Packet { texel t[N]; };
+
+// is_border — preprocessing.wgsl:55-57
+__device__ __forceinline__ bool is_border(const PyramidLayout& L, uint32_t x, uint32_t y) {
+    return !(x >= L.B && x < L.B + L.C && y >= L.B && y < L.B + L.C);
+}
+
+// Writes N consecutive texels of a row; one 128-bit store when the row pitch keeps 16-B alignment.
+template <typename texel, int N>
+__device__ __forceinline__ void store_packet(texel* row, uint32_t x, uint32_t T, const Packet<texel, N>& p, bool aligned) {
+    if (aligned && x + N <= T) {
+        *reinterpret_cast<uint4*>(row + x) = *reinterpret_cast<const uint4*>(&p);
+    } else {
+        for (int i = 0; i < N; ++i) if (x + i < T) row[x + i] = p.t[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split — split.wgsl:18-43
+// ------------------------------------------------------------------------------------------------
+template <int FORMAT>
+__device__ __forceinline__ Px4 source_texel(const DatasetDevice& d, int x, int y) {
+    using F = Fmt<FORMAT>;
+    x = min(max(x, 0), (int)d.width - 1);   // clamp-to-edge (ImageSampler::linear, preprocessor.rs:408-409)
+    y = min(max(y, 0), (int)d.height - 1);
+    return F::decode(__ldg(reinterpret_cast<const typename F::texel*>(d.pixels) + (size_t)y * d.width + (size_t)x));
+}
+
+template <int FORMAT>
+__global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks,
+                                                            const DatasetDevice* __restrict__ datasets) {
+    using F = Fmt<FORMAT>;
+    using texel = typename F::texel;
+    constexpr int N = F::PX_PER_THREAD;
+    const PyramidTask& task = tasks[blockIdx.y];
+    const DatasetDevice d = datasets[task.dataset];
+    const uint32_t packets_per_row = (L.T + N - 1) / N;
+    const uint32_t pid = blockIdx.x * PYR_THREADS + threadIdx.x;
+    if (pid >= packets_per_row * L.T) return;
+    const uint32_t y = pid / packets_per_row, x0 = (pid - y * packets_per_row) * N;
+    texel* row = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes) + (size_t)y * L.T;
+    const bool aligned = ((L.T * sizeof(texel)) % 16 == 0) && (L.tile_bytes % 16 == 0);
+    const float tile_scale = tile_count(task.tile.lod);
+    const float Cf = (float)L.C;
+    Packet<texel, N> out;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t x = x0 + i;
+        if (x >= L.T) { out.t[i] = F::zero(); continue; }
+        if (is_border(L, x, y)) { out.t[i] = F::zero(); continue; }
+        const float tcx = (float)(x - L.B) / Cf, tcy = (float)(y - L.B) / Cf;
+        float sx = ((float)task.tile.x + tcx) / tile_scale;
+        float sy = ((float)task.tile.y + tcy) / tile_scale;
+        sx = (sx - d.top_left[0]) / (d.bottom_right[0] - d.top_left[0]);   // inverse_mix — preprocessing.wgsl:44-46
+        sy = (sy - d.top_left[1]) / (d.bottom_right[1] - d.top_left[1]);
+        const float px = sx * (float)d.width - 0.5f, py = sy * (float)d.height - 0.5f;
+        const float fx = floorf(px), fy = floorf(py);
+        const float rx = px - fx, ry = py - fy;
+        const int ix = (int)fx, iy = (int)fy;
+        const Px4 v00 = source_texel<FORMAT>(d, ix, iy), v10 = source_texel<FORMAT>(d, ix + 1, iy);
+        const Px4 v01 = source_texel<FORMAT>(d, ix, iy + 1), v11 = source_texel<FORMAT>(d, ix + 1, iy + 1);
+        const bool is_valid = v00.v[0] != 0.0f && v10.v[0] != 0.0f && v01.v[0] != 0.0f && v11.v[0] != 0.0f;  // textureGather(0,..)
+        const bool is_inside = (tcx >= 0.0f && tcx <= 1.0f) && (tcy >= 0.0f && tcy <= 1.0f);                    // inside_square
+        if (is_valid && is_inside) {
+            Px4 value;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) value.v[k] = mix(mix(v00.v[k], v10.v[k], rx), mix(v01.v[k], v11.v[k], rx), ry);
+            out.t[i] = F::pack(value);
+        } else {
+            out.t[i] = row[x];  // textureLoad(atlas, coords, atlas_index): keep what earlier datasets wrote
+        }
+    }
+    store_packet<texel, N>(row, x0, L.T, out, aligned);
+}
+
+// ------------------------------------------------------------------------------------------------
+// downsample — downsample.wgsl:12-40
+// ------------------------------------------------------------------------------------------------
+template <int FORMAT>
+__global__ void __launch_bounds__(PYR_THREADS) downsample_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks) {
+    using F = Fmt<FORMAT>;
+    using texel = typename F::texel;
+    constexpr int N = F::PX_PER_THREAD;
+    const PyramidTask& task = tasks[blockIdx.y];
+    const uint32_t packets_per_row = (L.T + N - 1) / N;
+    const uint32_t pid = blockIdx.x * PYR_THREADS + threadIdx.x;
+    if (pid >= packets_per_row * L.T) return;
+    const uint32_t y = pid / packets_per_row, x0 = (pid - y * packets_per_row) * N;
+    texel* row = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes) + (size_t)y * L.T;
+    const bool aligned = ((L.T * sizeof(texel)) % 16 == 0) && (L.tile_bytes % 16 == 0);
+    const uint32_t child_size = L.C / 2u;
+    Packet<texel, N> out;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const uint32_t x = x0 + i;
+        out.t[i] = F::zero();
+        if (x >= L.T || is_border(L, x, y)) continue;
+        const uint32_t tx = x - L.B, ty = y - L.B;
+        const uint32_t cx = 2u * (tx % child_size) + L.B, cy = 2u * (ty % child_size) + L.B;
+        uint32_t child_index = tx / child_size + 2u * (ty / child_size);
+        if (child_index > 3u) child_index = 3u;
+        const uint32_t child_slot = task.dep[child_index];
+        if (child_slot == INVALID_SLOT) continue;  // invalid layer reads as zero -> count == 0 -> 0 (Q3)
+        const texel* child = reinterpret_cast<const texel*>(L.arena + (size_t)child_slot * L.tile_bytes);
+        Px4 sum{{0.0f, 0.0f, 0.0f, 0.0f}};
+        float count = 0.0f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {  // OFFSETS (0,0),(0,1),(1,0),(1,1) — downsample.wgsl:24
+            const uint32_t lx = cx + (uint32_t)(o >> 1), ly = cy + (uint32_t)(o & 1);
+            if (lx >= L.T || ly >= L.T) continue;
+            const Px4 cv = F::decode(child[(size_t)ly * L.T + lx]);
+            const bool is_valid = cv.v[0] != 0.0f || cv.v[1] != 0.0f || cv.v[2] != 0.0f;
+            if (is_valid) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sum.v[k] += cv.v[k];
+                count += 1.0f;
+            }
+        }
+        if (count != 0.0f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sum.v[k] = sum.v[k] / count;
+            out.t[i] = F::pack(sum);
+        }
+    }
+    store_packet<texel, N>(row, x0, L.T, out, aligned);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stitch — stitch.wgsl:12-118 (in place, border ring only)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stitch_project_to_side(uint32_t T, uint32_t cx, uint32_t cy, uint32_t original_side,
+                                                       uint32_t projected_side, uint32_t& ox, uint32_t& oy) {
+    // codes: 0 = PS (x), 1 = PT (y), 2 = NS (T-1-x), 3 = NT (T-1-y); EVEN_LIST / ODD_LIST — stitch.wgsl:18-33
+    const uint32_t index = (6u + projected_side - original_side) % 6u;
+    const unsigned char even_x[6] = {0, 0, 3, 3, 1, 0}, even_y[6] = {1, 1, 0, 2, 2, 1};
+    const unsigned char odd_x[6] = {0, 0, 1, 1, 3, 0}, odd_y[6] = {1, 1, 2, 0, 0, 1};
+    const bool even = (original_side % 2u) == 0u;
+    const uint32_t xc = even ? even_x[index] : odd_x[index];
+    const uint32_t yc = even ? even_y[index] : odd_y[index];
+    const uint32_t cand[4] = {cx, cy, T - 1u - cx, T - 1u - cy};
+    ox = cand[xc];
+    oy = cand[yc];
+}
+
+template <typename texel>
+__global__ void __launch_bounds__(PYR_THREADS) stitch_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks) {
+    const PyramidTask& task = tasks[blockIdx.x];
+    texel* tile = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes);
+    const uint32_t T = L.T, B = L.B, C = L.C, O = L.B + L.C;
+    const uint32_t n_full = 2u * B * T;            // rows [0,B) and [O,T): full rows
+    const uint32_t n_side = 2u * B * (T - 2u * B); // rows [B,O): columns [0,B) and [O,T)
+    for (uint32_t i = threadIdx.x; i < n_full + n_side; i += PYR_THREADS) {
+        uint32_t x, y;
+        if (i < n_full) {
+            const uint32_t r = i / T;
+            x = i - r * T;
+            y = r < B ? r : O + (r - B);
+        } else {
+            const uint32_t j = i - n_full;
+            const uint32_t r = j / (2u * B), k = j - r * (2u * B);
+            y = B + r;
+            x = k < B ? k : O + (k - B);
+        }
+        // neighbour_index — stitch.wgsl:53-74 (first matching region)
+        uint32_t ni;
+        if (y < B) ni = (x < B) ? 4u : (x >= O ? 5u : 0u);
+        else if (y >= O) ni = (x < B) ? 7u : (x >= O ? 6u : 2u);
+        else ni = (x < B) ? 3u : 1u;
+        const uint32_t nslot = task.dep[ni];
+        texel value;
+        if (nslot == INVALID_SLOT) {  // repeat_data — stitch.wgsl:98-103
+            const uint32_t sx = min(max(x, B), B + C - 1u), sy = min(max(y, B), B + C - 1u);
+            value = tile[(size_t)sy * T + sx];
+        } else {                      // neighbour_data — stitch.wgsl:76-96
+            int offx, offy;
+            const int c = (int)C;
+            switch (ni) {
+                case 0: offx = 0; offy = c; break;
+                case 1: offx = -c; offy = 0; break;
+                case 2: offx = 0; offy = -c; break;
+                case 3: offx = c; offy = 0; break;
+                case 4: offx = c; offy = c; break;
+                case 5: offx = -c; offy = c; break;
+                case 6: offx = -c; offy = -c; break;
+                default: offx = c; offy = -c; break;
+            }
+            uint32_t sx, sy;
+            stitch_project_to_side(T, (uint32_t)((int)x + offx), (uint32_t)((int)y + offy), task.tile.side, task.dep_side[ni], sx, sy);
+            const texel* nb = reinterpret_cast<const texel*>(L.arena + (size_t)nslot * L.tile_bytes);
+            if (sx < T && sy < T) value = nb[(size_t)sy * T + sx];
+            else value = texel{};  // out-of-range textureLoad := 0
+        }
+        tile[(size_t)y * T + x] = value;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mip generation at tile load — AttachmentData::generate_mipmaps, src/terrain_data/mod.rs:143-219
+// (integer arithmetic; one level per launch)
+// ------------------------------------------------------------------------------------------------
+__global__ void mip_r16_kernel(const uint16_t* __restrict__ parent, uint16_t* __restrict__ child, uint32_t parent_size) {
+    const uint32_t child_size = parent_size >> 1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= child_size * child_size) return;
+    const uint32_t cy = i / child_size, cx = i - cy * child_size;
+    uint32_t value = 0, count = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t v = parent[(size_t)((cy << 1) + (k & 1)) * parent_size + ((cx << 1) + (k >> 1))];
+        if (v != 0) { value += v; count += 1; }
+    }
+    child[i] = count == 0 ? 0 : (uint16_t)(value / count);
+}
+
+__global__ void mip_rgba8_kernel(const uchar4* __restrict__ parent, uchar4* __restrict__ child, uint32_t parent_size) {
+    const uint32_t child_size = parent_size >> 1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= child_size * child_size) return;
+    const uint32_t cy = i / child_size, cx = i - cy * child_size;
+    uint32_t s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uchar4 v = parent[(size_t)((cy << 1) + (k & 1)) * parent_size + ((cx << 1) + (k >> 1))];
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+    child[i] = make_uchar4((unsigned char)(s[0] / 4), (unsigned char)(s[1] / 4), (unsigned char)(s[2] / 4), (unsigned char)(s[3] / 4));
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic sources: integer-only hash value-noise (NOT part of the reference)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t lattice(uint32_t ix, uint32_t iy, uint32_t seed) {
+    return lowbias32(ix + lowbias32(iy + lowbias32(seed))) >> 16;
+}
+__device__ uint32_t synth_value(uint32_t x, uint32_t y, uint32_t seed) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t o = 0; o < 6; ++o) {
+        const uint32_t k = 8u - o;
+        const uint32_t ix = x >> k, iy = y >> k;
+        const uint64_t fx = x & ((1u << k) - 1u), fy = y & ((1u << k) - 1u), one = 1u << k;
+        const uint64_t v00 = lattice(ix, iy, seed + o), v10 = lattice(ix + 1, iy, seed + o);
+        const uint64_t v01 = lattice(ix, iy + 1, seed + o), v11 = lattice(ix + 1, iy + 1, seed + o);
+        const uint64_t top = v00 * (one - fx) + v10 * fx, bot = v01 * (one - fx) + v11 * fx;
+        const uint32_t v = (uint32_t)((top * (one - fy) + bot * fy) >> (2u * k));
+        sum += v >> (o + 1u);
+    }
+    return sum;
+}
+__device__ __forceinline__ bool synth_hole(uint32_t x, uint32_t y, uint32_t seed) {
+    return lowbias32((x >> 7) + lowbias32((y >> 7) + lowbias32(seed ^ 0x5EED0003u))) % 50u == 0u;
+}
+
+__global__ void synth_kernel(uint32_t format, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t seed,
+                             uint32_t holes, void* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)width * height) return;
+    const uint32_t yy = (uint32_t)(i / width), xx = (uint32_t)(i - (uint64_t)yy * width);
+    const uint32_t x = x0 + xx, y = y0 + yy;
+    const bool hole = holes && synth_hole(x, y, seed);
+    if (format == BT_FORMAT_R16) {
+        uint32_t v = synth_value(x, y, seed);
+        v = v < 1u ? 1u : (v > 65535u ? 65535u : v);
+        reinterpret_cast<uint16_t*>(out)[i] = hole ? 0 : (uint16_t)v;
+    } else {
+        uint32_t c[3];
+#pragma unroll
+        for (uint32_t k = 0; k < 3; ++k) {
+            uint32_t v = synth_value(x, y, seed + 0x100u * (k + 1u)) >> 8;
+            if (k == 0) v = v < 1u ? 1u : v;
+            c[k] = v > 255u ? 255u : v;
+        }
+        reinterpret_cast<uchar4*>(out)[i] = hole ? make_uchar4(0, 0, 0, 0)
+                                                 : make_uchar4((unsigned char)c[0], (unsigned char)c[1], (unsigned char)c[2], 255);
+    }
+}
+
+}  // namespace btd
+
+using namespace btd;
+
+extern "C" cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
+                                       const PyramidTask* tasks, uint32_t n_tasks, const DatasetDevice* datasets,
+                                       cudaStream_t stream) {
+    if (n_tasks == 0) return cudaSuccess;
+    PyramidLayout L{static_cast<unsigned char*>(arena), tile_bytes, T, B, T - 2u * B, format};
+    for (uint32_t first = 0; first < n_tasks; first += 65535u) {  // gridDim.y limit
+        const uint32_t n = (n_tasks - first) < 65535u ? (n_tasks - first) : 65535u;
+        if (format == BT_FORMAT_R16) {
+            const uint32_t packets = ((T + 7) / 8) * T;
+            split_kernel<BT_FORMAT_R16><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
+        } else {
+            const uint32_t packets = ((T + 3) / 4) * T;
+            split_kernel<BT_FORMAT_RGBA8><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
+        }
+    }
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t bt_launch_downsample(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
+                                            const PyramidTask* tasks, uint32_t n_tasks, cudaStream_t stream) {
+    if (n_tasks == 0) return cudaSuccess;
+    PyramidLayout L{static_cast<unsigned char*>(arena), tile_bytes, T, B, T - 2u * B, format};
+    for (uint32_t first = 0; first < n_tasks; first += 65535u) {
+        const uint32_t n = (n_tasks - first) < 65535u ? (n_tasks - first) : 65535u;
+        if (format == BT_FORMAT_R16) {
+            const uint32_t packets = ((T + 7) / 8) * T;
+            downsample_kernel<BT_FORMAT_R16><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first);
+        } else {
+            const uint32_t packets = ((T + 3) / 4) * T;
+            downsample_kernel<BT_FORMAT_RGBA8><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first);
+        }
+    }
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t bt_launch_stitch(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
+                                        const PyramidTask* tasks, uint32_t n_tasks, cudaStream_t stream) {
+    if (n_tasks == 0) return cudaSuccess;
+    PyramidLayout L{static_cast<unsigned char*>(arena), tile_bytes, T, B, T - 2u * B, format};
+    if (format == BT_FORMAT_R16) stitch_kernel<uint16_t><<<n_tasks, PYR_THREADS, 0, stream>>>(L, tasks);
+    else stitch_kernel<uchar4><<<n_tasks, PYR_THREADS, 0, stream>>>(L, tasks);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t bt_launch_mipmaps(uint32_t format, uint32_t texture_size, uint32_t mip_level_count,
+                                         const void* mip0, void* mips_out, cudaStream_t stream) {
+    const unsigned char* parent = static_cast<const unsigned char*>(mip0);
+    unsigned char* dst = static_cast<unsigned char*>(mips_out);
+    uint32_t parent_size = texture_size;
+    const uint32_t px = format == BT_FORMAT_R16 ? 2u : 4u;
+    for (uint32_t level = 1; level < mip_level_count; ++level) {
+        const uint32_t child_size = parent_size >> 1;
+        const uint32_t n = child_size * child_size;
+        if (n == 0) break;
+        if (format == BT_FORMAT_R16)
+            mip_r16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(parent), reinterpret_cast<uint16_t*>(dst), parent_size);
+        else
+            mip_rgba8_kernel<<<(n + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const uchar4*>(parent), reinterpret_cast<uchar4*>(dst), parent_size);
+        parent = dst;
+        dst += (size_t)n * px;
+        parent_size = child_size;
+    }
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t bt_launch_synth(uint32_t format, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0,
+                                       uint32_t seed, uint32_t holes, void* out, cudaStream_t stream) {
+    const uint64_t n = (uint64_t)width * height;
+    if (n == 0) return cudaSuccess;
+    synth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(format, width, height, x0, y0, seed, holes, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// row copies of the multi-GPU halo / root exchange (pack into / unpack from the NCCL buffers)
+// ------------------------------------------------------------------------------------------------
+namespace btd {
+__global__ void row_copy_kernel(const RowCopy* __restrict__ copies) {
+    const RowCopy c = copies[blockIdx.x];
+    const uint16_t* s = static_cast<const uint16_t*>(c.src);
+    uint16_t* d = static_cast<uint16_t*>(c.dst);
+    const uint64_t n = c.bytes / 2;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0 && (c.bytes & 15u) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(s);
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        for (uint64_t i = threadIdx.x; i < c.bytes / 16; i += blockDim.x) d4[i] = s4[i];
+    } else {
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+}
+}  // namespace btd
+
+extern "C" cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    btd::row_copy_kernel<<<n, 256, 0, stream>>>(copies);
+    return cudaGetLastError();
+}

@@ -1,0 +1,408 @@
+/*
+ * bevy_terrain_b200 — C ABI of the B200-native (sm_100a CUDA) implementation of
+ * bevy_terrain's data-parallel hot path:
+ *
+ *   (1) per-frame quadtree tile selection + tile-list / indirect-draw emit
+ *   (2) per-tile heightmap-sampled vertex-grid generation (positions + normals)
+ *   (3) the offline tile-pyramid preprocessor (split / downsample / stitch)
+ *
+ * The reference (kurtkuehnert/bevy_terrain @ 5a88daf) has NO FFI boundary: the hot path sits
+ * behind three Bevy render-graph call points and a set of plain-data uniform/storage structs.
+ * Every entry point below names the reference call point (file:line under /root/reference)
+ * it replaces.  All structs are little-endian PODs whose byte layout equals the encase
+ * std140/std430 layout the reference uploads, so the Rust side can `bytemuck::cast` them.
+ *
+ * Conventions
+ *   - every function returns a bt_status (0 = BT_OK); nothing throws/unwinds across the ABI
+ *   - opaque handles own all device memory; host inputs are copied during the call
+ *   - `stream` arguments are a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *     per-frame calls are stream-ordered and non-blocking except the *_readback calls
+ *   - no allocation on the per-frame path after bt_view_create
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with BT_ERR_CUDA (the CPU oracle under oracle/ is test infrastructure only)
+ */
+#ifndef BEVY_TERRAIN_B200_H
+#define BEVY_TERRAIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_ABI_VERSION 1u
+
+/* ------------------------------------------------------------------------------------------ */
+/* status codes (reference: panics via unwrap/expect, tile_atlas.rs:384; silent frame skip,    */
+/* tiling_prepass.rs:229-237 — replaced by integer codes + sticky error string)                */
+/* ------------------------------------------------------------------------------------------ */
+typedef int32_t bt_status;
+enum {
+    BT_OK               = 0,
+    BT_ERR_INVALID_ARG  = 1,
+    BT_ERR_CAPACITY     = 2, /* tile list / frontier overflow (UNCHECKED in the reference)   */
+    BT_ERR_CUDA         = 3,
+    BT_ERR_NCCL         = 4,
+    BT_ERR_IO           = 5,
+    BT_ERR_OUT_OF_MEMORY = 6,
+    BT_ERR_NOT_FOUND    = 7
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* POD mirrors of the reference's GPU-visible structs                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* TileCoordinate — src/math/coordinate.rs:156-166, src/shaders/types.wgsl:26-30. 16 B.
+ * lod 0 = root (1 tile per side), count(lod) = 1 << lod.  INVALID = all 0xFFFFFFFF.          */
+typedef struct bt_tile { uint32_t side, lod, x, y; } bt_tile;
+
+/* Indirect draw record — src/render/terrain_view_bind_group.rs:66-71, prepare_prepass.wgsl:38-43 */
+typedef struct bt_indirect {
+    uint32_t vertex_count, instance_count, base_vertex, base_instance;
+} bt_indirect;
+
+/* TerrainViewConfigUniform — terrain_view_bind_group.rs:82-116, types.wgsl:10-24. 52 B.      */
+typedef struct bt_view_config_uniform {
+    uint32_t tree_size;
+    uint32_t geometry_tile_count;
+    uint32_t refinement_count;
+    float    grid_size;
+    uint32_t vertices_per_row;
+    uint32_t vertices_per_tile;
+    float    morph_distance;
+    float    blend_distance;
+    float    load_distance;
+    float    subdivision_distance;
+    float    morph_range;
+    float    blend_range;
+    float    precision_threshold_distance;
+} bt_view_config_uniform;
+
+/* SideParameter — src/math/terrain_model.rs:228-249, types.wgsl:78-87. 112 B (std140).       */
+typedef struct bt_side_parameter {
+    int32_t view_xy[2];           /* Rust: origin_xy */
+    float   view_uv[2];           /* Rust: origin_uv */
+    float   c[3];    float _p0;
+    float   c_s[3];  float _p1;
+    float   c_t[3];  float _p2;
+    float   c_ss[3]; float _p3;
+    float   c_st[3]; float _p4;
+    float   c_tt[3]; float _p5;
+} bt_side_parameter;
+
+/* TerrainModelApproximation — terrain_model.rs:252-259, types.wgsl:89-93. 688 B.             */
+typedef struct bt_model_approximation {
+    uint32_t origin_lod;
+    float    approximate_height;
+    uint32_t _pad[2];
+    bt_side_parameter sides[6];
+} bt_model_approximation;
+
+/* CullingUniform — src/render/culling_bind_group.rs:41-55, types.wgsl:99-103. 160 B.
+ * Only world_position is read by the reference shaders (frustum culling is not implemented at
+ * this commit); `planes` is consumed only by the opt-in BT_FLAG_FRUSTUM_CULL extension.      */
+typedef struct bt_culling_uniform {
+    float world_position[3]; float _p0;
+    float view_proj[16];           /* column-major; holds inverse(world_from_view) in the ref */
+    float planes[5][4];
+} bt_culling_uniform;
+
+/* TerrainConfigUniform — src/render/terrain_bind_group.rs:77-93, types.wgsl:3-8. 16 B.       */
+typedef struct bt_terrain_config_uniform {
+    uint32_t lod_count;
+    float    min_height, max_height, scale;
+} bt_terrain_config_uniform;
+
+/* AttachmentConfig (GPU) — terrain_bind_group.rs:47-72, types.wgsl:71-76. 16 B each, x8.     */
+typedef struct bt_attachment_uniform { float size, scale, offset; uint32_t _pad; } bt_attachment_uniform;
+
+/* TileTreeEntry — src/terrain_data/tile_tree.rs:51-65, types.wgsl:55-58. 8 B.
+ * table index = ((side*lod_count + lod)*tree_size + x%tree_size)*tree_size + y%tree_size     */
+typedef struct bt_tile_tree_entry { uint32_t atlas_index, atlas_lod; } bt_tile_tree_entry;
+
+/* Mesh transform consumed by position_local_to_world / normal_local_to_world
+ * (functions.wgsl:14-29; bevy_pbr MeshUniform built at terrain_bind_group.rs:185-205).
+ * world_from_local: column-major 3x4 affine (cols x,y,z,translation);
+ * normal_matrix   : column-major inverse-transpose of the upper 3x3.                          */
+typedef struct bt_mesh_transform {
+    float world_from_local[12];
+    float normal_matrix[9];
+    float _pad[3];
+} bt_mesh_transform;
+
+/* One generated vertex = the fields of VertexOutput (src/shaders/render/vertex.wgsl:14-20)
+ * minus clip_position.  40 B, interleaved.  With BT_FLAG_NORMALS `normal` is the height-derived
+ * surface normal (sample_normal, attachments.wgsl:51-107, blended as fragment.wgsl:99-107),
+ * otherwise the model normal the reference's vertex stage outputs.                            */
+typedef struct bt_vertex {
+    float    position[4];   /* world_position, w = 1 */
+    float    normal[3];
+    float    uv[2];         /* coordinate_uv (after morph) */
+    uint32_t tile_index;
+} bt_vertex;
+
+/* AttachmentFormat ids — src/terrain_data/mod.rs:50-57 (Rgb8 = 5 and Rg16 = 3 are unimplemented
+ * in the reference's shaders, preprocessing.wgsl:3-5, and rejected here).                     */
+enum { BT_FORMAT_RGBA8 = 0, BT_FORMAT_R16 = 1 };
+
+/* TerrainKind — src/math/terrain_model.rs:23-36 */
+enum { BT_KIND_PLANAR = 0, BT_KIND_SPHERICAL = 1 };
+
+/* shader-def flags (src/render/terrain_material.rs:73-228, tiling_prepass.rs:28-79) */
+enum {
+    BT_FLAG_MORPH          = 1u << 1,
+    BT_FLAG_BLEND          = 1u << 2,
+    BT_FLAG_HIGH_PRECISION = 1u << 3,
+    BT_FLAG_NORMALS        = 1u << 4,  /* fuse sample_normal into the vertex record            */
+    BT_FLAG_FRUSTUM_CULL   = 1u << 6   /* extension; default off = reference behaviour          */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* configuration structs (host side)                                                           */
+/* ------------------------------------------------------------------------------------------ */
+
+/* AttachmentConfig — src/terrain_data/mod.rs:88-109 */
+typedef struct bt_attachment_config {
+    uint32_t texture_size;
+    uint32_t border_size;
+    uint32_t mip_level_count;
+    uint32_t format;          /* BT_FORMAT_* */
+} bt_attachment_config;
+
+/* TerrainConfig + TerrainModel — src/terrain.rs:27-49, src/math/terrain_model.rs:40-104 */
+typedef struct bt_terrain_desc {
+    uint32_t kind;            /* BT_KIND_* */
+    uint32_t lod_count;
+    uint32_t atlas_size;      /* number of atlas layers (tile slots) */
+    uint32_t attachment_count;
+    bt_attachment_config attachments[8];
+    float    min_height, max_height;
+    double   scale;           /* TerrainModel::scale(): side_length/2 (planar) or radius       */
+    bt_mesh_transform transform;
+} bt_terrain_desc;
+
+/* Per-frame inputs of one (terrain, view) pair = the Prepare-stage write_buffers of the
+ * reference (terrain_view_bind_group.rs:238-262, gpu_tile_tree.rs:84-95, culling_bind_group.rs:87-101) */
+typedef struct bt_view_frame {
+    bt_view_config_uniform view_config;
+    bt_model_approximation approximation;
+    bt_culling_uniform     culling;
+    float                  view_world_position[3]; /* bevy `view.world_position` (vertex stage) */
+    uint32_t               tile_tree_entry_count;  /* sides*lod_count*tree_size^2               */
+    const bt_tile_tree_entry* tile_tree;           /* host pointer, copied                      */
+    const uint32_t*        origins;                /* host pointer, sides*lod_count uvec2, may be NULL */
+} bt_view_frame;
+
+typedef struct bt_vertex_buffer {
+    bt_vertex* vertices;      /* DEVICE pointer owned by the view, valid until next gen/destroy */
+    uint64_t   capacity;      /* vertices the buffer can hold                                   */
+} bt_vertex_buffer;
+
+typedef struct bt_context bt_context;
+typedef struct bt_terrain bt_terrain;
+typedef struct bt_view    bt_view;
+typedef struct bt_preprocessor bt_preprocessor;
+
+/* ------------------------------------------------------------------------------------------ */
+/* context                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+uint32_t    bt_abi_version(void);
+bt_status   bt_context_create(int32_t device, bt_context** out);
+void        bt_context_destroy(bt_context* ctx);
+const char* bt_last_error(const bt_context* ctx);   /* sticky, per context */
+bt_status   bt_context_synchronize(bt_context* ctx);
+
+/* ------------------------------------------------------------------------------------------ */
+/* terrain = TileAtlas GPU mirror (src/terrain_data/gpu_tile_atlas.rs:208-223):                 */
+/* per attachment one pitched array [atlas_size][texture_size][texture_size] (mip 0)            */
+/* ------------------------------------------------------------------------------------------ */
+bt_status bt_terrain_create(bt_context* ctx, const bt_terrain_desc* desc, bt_terrain** out);
+void      bt_terrain_destroy(bt_terrain* terrain);
+/* = GpuTileAtlas::upload_tiles (gpu_tile_atlas.rs:309-336): host texels (mip 0, row-major) -> slot */
+bt_status bt_atlas_upload_tile(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index,
+                               const void* texels, size_t bytes, void* stream);
+/* device-to-device variant (tile produced by bt_preprocessor stays on the GPU) */
+bt_status bt_atlas_copy_tile(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index,
+                             const void* device_texels, size_t bytes, void* stream);
+bt_status bt_atlas_download_tile(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index,
+                                 void* texels, size_t bytes);
+/* device base pointer of an attachment's atlas array (for zero-copy interop / tests) */
+bt_status bt_atlas_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* view = TerrainViewData (terrain_view_bind_group.rs:118-187): final/temporary tile buffers,   */
+/* indirect record, uniforms, tile-tree table, vertex buffer                                    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct bt_view_desc {
+    uint32_t geometry_tile_count;  /* capacity of final_tiles / temporary_tiles (ref default 1e6) */
+    uint32_t tree_size;
+    uint32_t grid_size;
+    uint32_t _pad;
+    uint64_t max_vertices;         /* vertex buffer capacity in vertices; 0 = grow on demand in bt_gen_vertices */
+} bt_view_desc;
+
+bt_status bt_view_create(bt_terrain* terrain, const bt_view_desc* desc, bt_view** out);
+void      bt_view_destroy(bt_view* view);
+/* Prepare-stage uploads; host structs may live in pageable or pinned memory */
+bt_status bt_view_update(bt_view* view, const bt_view_frame* frame, void* stream);
+
+/* Replaces TilingPrepassNode::run (src/render/tiling_prepass.rs:204-271): prepare_root,
+ * (refine_tiles, prepare_next) x refinement_count, refine_tiles, prepare_render — ONE launch.
+ * Output order is the order a sequential execution of the reference shaders would produce.    */
+bt_status bt_select_tiles(bt_view* view, uint32_t flags, void* stream);
+
+/* Replaces the vertex stage of the indirect draw (DrawTerrainCommand,
+ * terrain_view_bind_group.rs:274-298; vertex.wgsl:85-98) by writing the strip-ordered vertex
+ * stream (indirect.vertex_count records) to a device buffer.                                  */
+bt_status bt_gen_vertices(bt_view* view, uint32_t flags, void* stream, bt_vertex_buffer* out);
+
+/* blocking D2H of final_tiles + indirect (the reference never reads these back; the draw
+ * consumes them on-device)                                                                    */
+bt_status bt_view_readback(bt_view* view, bt_tile* tiles, uint32_t capacity, uint32_t* count,
+                           bt_indirect* indirect, void* stream);
+/* status word written by the last bt_select_tiles (BT_OK / BT_ERR_CAPACITY), plus the number
+ * of parents that still wanted subdivision after the last pass (dropped by the reference, Q2) */
+bt_status bt_view_select_status(bt_view* view, uint32_t* dropped_parents, void* stream);
+bt_status bt_view_download_vertices(bt_view* view, bt_vertex* out, uint64_t first, uint64_t count,
+                                    void* stream);
+/* device pointers (final_tiles, indirect) for zero-copy consumers */
+bt_status bt_view_device_ptrs(bt_view* view, bt_tile** final_tiles, bt_indirect** indirect);
+
+/* ------------------------------------------------------------------------------------------ */
+/* host-side f64 producers of the per-frame inputs (no GPU needed)                              */
+/* ------------------------------------------------------------------------------------------ */
+
+/* TerrainModel — src/math/terrain_model.rs:40-104 (planar / sphere; ellipsoid is out of scope) */
+typedef struct bt_terrain_model {
+    uint32_t kind;             /* BT_KIND_* */
+    uint32_t _pad;
+    double   position[3];
+    double   scale[3];         /* side_length (planar) or radius (sphere), splatted */
+    float    min_height, max_height;
+} bt_terrain_model;
+
+/* TerrainViewConfig — src/terrain_view.rs:19-64 */
+typedef struct bt_terrain_view_config {
+    uint32_t tree_size, geometry_tile_count, refinement_count, grid_size;
+    double   subdivision_tolerance, precision_threshold_distance, load_distance,
+             morph_distance, blend_distance;
+    float    morph_range, blend_range;
+    uint32_t origin_lod;
+    uint32_t _pad;
+} bt_terrain_view_config;
+
+void bt_terrain_model_planar(const double position[3], double side_length, float min_height,
+                             float max_height, bt_terrain_model* out);   /* terrain_model.rs:84-93  */
+void bt_terrain_model_sphere(const double position[3], double radius, float min_height,
+                             float max_height, bt_terrain_model* out);   /* terrain_model.rs:95-104 */
+void bt_terrain_view_config_default(bt_terrain_view_config* out);       /* terrain_view.rs:47-64   */
+/* TerrainModel::scale (terrain_model.rs:183-193) */
+double bt_terrain_model_scale(const bt_terrain_model* model);
+/* MeshUniform equivalent of TerrainModel::transform (terrain_model.rs:196-203) */
+void bt_terrain_model_mesh_transform(const bt_terrain_model* model, bt_mesh_transform* out);
+/* TerrainViewConfigUniform::from_tile_tree o TileTree::new (terrain_view_bind_group.rs:98-115, tile_tree.rs:135-173) */
+void bt_view_config_uniform_from(const bt_terrain_view_config* cfg, const bt_terrain_model* model,
+                                 bt_view_config_uniform* out);
+/* TerrainModelApproximation::compute (terrain_model.rs:263-360) */
+bt_status bt_model_approximation_compute(const bt_terrain_model* model, const double view_world_position[3],
+                                         uint32_t origin_lod, float approximate_height,
+                                         bt_model_approximation* out);
+
+/* Clipmap residency = TileTree (src/terrain_data/tile_tree.rs:94-386) + the request/release/
+ * best-tile bookkeeping of TileAtlasState (src/terrain_data/tile_atlas.rs:369-503), without the
+ * async file I/O: tiles the tree requests are reported to the caller, who uploads them and
+ * marks them loaded.                                                                          */
+typedef struct bt_tile_tree bt_tile_tree;
+bt_status bt_tile_tree_create(const bt_terrain_model* model, const bt_terrain_view_config* cfg,
+                              uint32_t lod_count, uint32_t atlas_size, bt_tile_tree** out);
+void      bt_tile_tree_destroy(bt_tile_tree* tree);
+/* register a tile as existing on disk / in the pyramid (TileAtlasState::existing_tiles) */
+bt_status bt_tile_tree_add_existing(bt_tile_tree* tree, const bt_tile* tiles, uint32_t count);
+/* TileTree::update (tile_tree.rs:268-333) + TileAtlasState::request_tile/release_tile.
+ * Writes up to `cap` (tile, atlas_index) load requests; *count receives the total.            */
+typedef struct bt_tile_load { bt_tile tile; uint32_t atlas_index; uint32_t _pad[3]; } bt_tile_load;
+bt_status bt_tile_tree_update(bt_tile_tree* tree, const double view_world_position[3],
+                              bt_tile_load* loads, uint32_t cap, uint32_t* count);
+/* TileAtlasState::loaded_tile_attachment for all attachments of a tile */
+bt_status bt_tile_tree_mark_loaded(bt_tile_tree* tree, const bt_tile* tile);
+/* TileTree::adjust_to_tile_atlas (tile_tree.rs:363-374) -> entries + origins for bt_view_frame */
+bt_status bt_tile_tree_entries(bt_tile_tree* tree, bt_tile_tree_entry* entries, uint32_t entry_cap,
+                               uint32_t* origins_xy, uint32_t origin_cap);
+void      bt_tile_tree_set_approximate_height(bt_tile_tree* tree, float h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* preprocessor = Preprocessor + TerrainPreprocessNode (src/preprocess/preprocessor.rs:214-343,  */
+/* src/preprocess/mod.rs:143-217) with the pixel kernels of src/shaders/preprocess/{split,downsample,stitch}.wgsl */
+/* ------------------------------------------------------------------------------------------ */
+
+/* PreprocessDataset — preprocessor.rs:36-55.  The source image is given as pixels instead of a
+ * path (decoders are out of scope): `pixels` is a HOST pointer unless `pixels_on_device`.      */
+typedef struct bt_dataset {
+    uint32_t attachment_index;
+    uint32_t side;
+    float    top_left[2];
+    float    bottom_right[2];
+    uint32_t lod_begin, lod_end;     /* lod_range = lod_begin..lod_end (exclusive) */
+    uint32_t width, height;          /* source image size in pixels */
+    uint32_t pixels_on_device;
+    uint32_t _pad;
+    const void* pixels;              /* R16: uint16, Rgba8: 4 x uint8; row-major */
+} bt_dataset;
+
+/* Sharding of the deepest-LOD tile rows over ranks (new; the reference is single-GPU).
+ * world = 1 reproduces the reference schedule.                                               */
+typedef struct bt_shard { uint32_t rank, world; } bt_shard;
+
+bt_status bt_preprocessor_create(bt_context* ctx, uint32_t kind /*BT_KIND_*/,
+                                 const bt_attachment_config* attachments, uint32_t attachment_count,
+                                 uint32_t lod_count, bt_shard shard, bt_preprocessor** out);
+void      bt_preprocessor_destroy(bt_preprocessor* p);
+/* count == 1: Preprocessor::preprocess_tile (preprocessor.rs:298-312) — records the dataset and its
+ * task list; successive calls for one attachment overlay in call order (split.wgsl:36-42
+ * fall-through).  count > 1 (e.g. the 6 cube faces): Preprocessor::preprocess_spherical ordering
+ * (:314-343) — split/downsample ALL datasets, barrier, then per LOD per dataset stitch, so that
+ * cross-face neighbours exist when the stitch tasks resolve them.                             */
+bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* datasets, uint32_t count);
+/* Runs split -> downsample (per level) -> [halo exchange hook] -> stitch on `stream`.
+ * Phases are exposed separately so that a multi-GPU host can run the collective between them. */
+bt_status bt_preprocessor_run_split_downsample(bt_preprocessor* p, void* stream);
+bt_status bt_preprocessor_run_stitch(bt_preprocessor* p, void* stream);
+bt_status bt_preprocessor_run(bt_preprocessor* p, void* stream);          /* both, world == 1 */
+/* multi-GPU hooks: sub-root gather + halo strips (see DESIGN.md "multi-GPU") */
+bt_status bt_preprocessor_halo_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank);
+bt_status bt_preprocessor_halo_pack(bt_preprocessor* p, void* device_send, void* stream);
+bt_status bt_preprocessor_halo_unpack(bt_preprocessor* p, const void* device_gathered, void* stream);
+bt_status bt_preprocessor_roots_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank);
+bt_status bt_preprocessor_roots_pack(bt_preprocessor* p, void* device_send, void* stream);
+bt_status bt_preprocessor_roots_unpack_and_finish(bt_preprocessor* p, const void* device_gathered, void* stream);
+/* results */
+bt_status bt_preprocessor_tile_count(bt_preprocessor* p, uint32_t attachment, uint32_t* count);
+bt_status bt_preprocessor_list_tiles(bt_preprocessor* p, uint32_t attachment, bt_tile* tiles, uint32_t cap, uint32_t* count);
+/* device pointer of one tile's texels (texture_size^2 pixels, mip 0) */
+bt_status bt_preprocessor_tile_device_ptr(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void** out);
+bt_status bt_preprocessor_get_tile(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void* host_out, size_t bytes);
+/* Save (tile_atlas.rs:77-116, formats/mod.rs:9-36): <dir>/<side>_<lod>_<x>_<y>.bin + config.tc */
+bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const char* directory);
+
+/* ------------------------------------------------------------------------------------------ */
+/* utilities                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+/* CPU mip chain at tile load (AttachmentData::generate_mipmaps, terrain_data/mod.rs:143-219)
+ * is replaced by a device kernel operating on an uploaded tile; out is a device pointer pair.  */
+bt_status bt_generate_mipmaps(bt_context* ctx, uint32_t format, uint32_t texture_size, uint32_t mip_level_count,
+                              const void* device_mip0, void* device_mips_out, void* stream);
+/* deterministic integer hash-noise source generator used by bench.py/tests (not part of the
+ * reference; see DESIGN.md "synthetic inputs")                                                */
+bt_status bt_synth_source(bt_context* ctx, uint32_t format, uint32_t width, uint32_t height,
+                          uint32_t x0, uint32_t y0, uint32_t seed, uint32_t holes, void* device_out, void* stream);
+/* raw device memory helpers for hosts without a CUDA binding (ctypes tests) */
+bt_status bt_device_alloc(bt_context* ctx, size_t bytes, void** out);
+bt_status bt_device_free(bt_context* ctx, void* ptr);
+bt_status bt_memcpy_h2d(bt_context* ctx, void* dst_device, const void* src_host, size_t bytes, void* stream);
+bt_status bt_memcpy_d2h(bt_context* ctx, void* dst_host, const void* src_device, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVY_TERRAIN_B200_H */

@@ -1,0 +1,142 @@
+"""GPU parity: bt_preprocessor (split / downsample / stitch kernels) vs the oracle's restatement of
+src/shaders/preprocess/*.wgsl and the task graph of preprocessor.rs.  Byte-exact."""
+import numpy as np
+import pytest
+
+from bevy_terrain_b200 import _ffi as F
+from tests import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _config(api, kind, lod_count, T, B, fmt):
+    model = api.TerrainModel.sphere((0, 0, 0), 1.0, 0.0, 1.0) if kind == F.BT_KIND_SPHERICAL else api.TerrainModel.planar((0, 0, 0), 1.0, 0.0, 1.0)
+    cfg = api.TerrainConfig(lod_count=lod_count, model=model)
+    cfg.add_attachment(api.AttachmentConfig(name="a", texture_size=T, border_size=B,
+                                            format=api.AttachmentFormat.R16 if fmt == F.BT_FORMAT_R16 else api.AttachmentFormat.Rgba8))
+    return cfg
+
+
+def _compare(pre, pyr, attachment=0):
+    got_tiles = {tuple(int(v) for v in t) for t in pre.tiles(attachment)}
+    exp_tiles = {tuple(int(v) for v in t) for t in pyr.tiles()}
+    assert got_tiles == exp_tiles
+    for tc in sorted(exp_tiles):
+        g, e = pre.get_tile(attachment, tc), pyr.tile(*tc)
+        if not np.array_equal(g, e):
+            bad = np.argwhere(g != e)
+            raise AssertionError(f"tile {tc}: {len(bad)} texels differ, first at {bad[0]}: got {g[tuple(bad[0])]} expected {e[tuple(bad[0])]}")
+    return len(exp_tiles)
+
+
+@pytest.mark.parametrize("fmt", [F.BT_FORMAT_R16, F.BT_FORMAT_RGBA8])
+@pytest.mark.parametrize("holes", [False, True])
+def test_preprocess_planar_full_pyramid(ctx, fmt, holes):
+    from bevy_terrain_b200 import api
+    T, B, L = 64, 2, 4
+    src = O.synth_source(fmt, 300, 280, seed=0x5EED0001 if fmt == F.BT_FORMAT_R16 else 0x5EED0002, holes=holes)
+    pyr = O.Pyramid(F.BT_KIND_SPHERICAL, fmt, T, B, L)   # Q7: preprocess_planar.rs runs with the default sphere model
+    pyr.add_datasets([O.make_dataset(src, lod_range=(0, L))])
+    pyr.run()
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_SPHERICAL, L, T, B, fmt))
+    try:
+        pre.preprocess_tile(api.PreprocessDataset(pixels=src, lod_range=range(0, L))).run()
+        assert _compare(pre, pyr) == 85
+    finally:
+        pre.close()
+
+
+def test_preprocess_planar_model_equals_sphere_model_for_one_face(ctx):
+    """Q7: for side-0-only data the planar and the spherical neighbour rules give the same pyramid"""
+    from bevy_terrain_b200 import api
+    T, B, L = 32, 2, 3
+    src = O.synth_source(F.BT_FORMAT_R16, 128, 128)
+    a = api.Preprocessor(ctx, _config(api, F.BT_KIND_SPHERICAL, L, T, B, F.BT_FORMAT_R16))
+    b = api.Preprocessor(ctx, _config(api, F.BT_KIND_PLANAR, L, T, B, F.BT_FORMAT_R16))
+    try:
+        a.preprocess_tile(api.PreprocessDataset(pixels=src, lod_range=range(0, L))).run()
+        b.preprocess_tile(api.PreprocessDataset(pixels=src, lod_range=range(0, L))).run()
+        for tc in a.tiles():
+            assert np.array_equal(a.get_tile(0, tc), b.get_tile(0, tc))
+    finally:
+        a.close(); b.close()
+
+
+def test_preprocess_partial_dataset_and_overlay(ctx):
+    """a dataset covering part of the face (ragged tile ranges, missing children) overlaid by a second one"""
+    from bevy_terrain_b200 import api
+    T, B, L = 32, 2, 4
+    src1 = O.synth_source(F.BT_FORMAT_R16, 200, 200, seed=11, holes=True)
+    src2 = O.synth_source(F.BT_FORMAT_R16, 90, 70, seed=12)
+    kw1 = dict(top_left=(0.1, 0.2), bottom_right=(0.8, 0.9), lod_range=(1, L))
+    kw2 = dict(top_left=(0.3, 0.3), bottom_right=(0.55, 0.6), lod_range=(0, L))
+    pyr = O.Pyramid(F.BT_KIND_PLANAR, F.BT_FORMAT_R16, T, B, L)
+    pyr.add_datasets([O.make_dataset(src1, **kw1)])
+    pyr.add_datasets([O.make_dataset(src2, **kw2)])
+    pyr.run()
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_PLANAR, L, T, B, F.BT_FORMAT_R16))
+    try:
+        pre.preprocess_tile(api.PreprocessDataset(pixels=src1, top_left=kw1["top_left"], bottom_right=kw1["bottom_right"], lod_range=range(*kw1["lod_range"])))
+        pre.preprocess_tile(api.PreprocessDataset(pixels=src2, top_left=kw2["top_left"], bottom_right=kw2["bottom_right"], lod_range=range(*kw2["lod_range"])))
+        pre.run()
+        _compare(pre, pyr)
+    finally:
+        pre.close()
+
+
+def test_preprocess_spherical_cross_face_stitch(ctx):
+    from bevy_terrain_b200 import api
+    T, B, L = 32, 2, 3
+    faces = [O.synth_source(F.BT_FORMAT_R16, 96, 96, seed=100 + s, holes=(s == 2)) for s in range(6)]
+    pyr = O.Pyramid(F.BT_KIND_SPHERICAL, F.BT_FORMAT_R16, T, B, L)
+    pyr.add_datasets([O.make_dataset(faces[s], side=s, lod_range=(0, L)) for s in range(6)])
+    pyr.run()
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_SPHERICAL, L, T, B, F.BT_FORMAT_R16))
+    try:
+        pre.preprocess_spherical(api.SphericalDataset(faces=faces, lod_range=range(0, L))).run()
+        assert _compare(pre, pyr) == 6 * 21
+    finally:
+        pre.close()
+
+
+def test_preprocess_odd_sizes(ctx):
+    """texture sizes that break the 16-byte row alignment take the scalar store path"""
+    from bevy_terrain_b200 import api
+    T, B, L = 36, 1, 3
+    src = O.synth_source(F.BT_FORMAT_R16, 77, 131, seed=5)
+    pyr = O.Pyramid(F.BT_KIND_PLANAR, F.BT_FORMAT_R16, T, B, L)
+    pyr.add_datasets([O.make_dataset(src, lod_range=(0, L))])
+    pyr.run()
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_PLANAR, L, T, B, F.BT_FORMAT_R16))
+    try:
+        pre.preprocess_tile(api.PreprocessDataset(pixels=src, lod_range=range(0, L))).run()
+        _compare(pre, pyr)
+    finally:
+        pre.close()
+
+
+def test_synth_source_matches_oracle(ctx):
+    for fmt, dt, shape in ((F.BT_FORMAT_R16, np.uint16, (97, 211)), (F.BT_FORMAT_RGBA8, np.uint8, (97, 211, 4))):
+        for holes in (False, True):
+            ptr = ctx.synth_source(fmt, 211, 97, x0=1000, y0=77, seed=42, holes=holes)
+            got = np.empty(shape, dtype=dt)
+            ctx.d2h(got, ptr)
+            ctx.free(ptr)
+            assert np.array_equal(got, O.synth_source(fmt, 211, 97, x0=1000, y0=77, seed=42, holes=holes))
+
+
+def test_mipmaps_match_oracle(ctx):
+    import ctypes as C
+    for fmt, dt, px in ((F.BT_FORMAT_R16, np.uint16, 1), (F.BT_FORMAT_RGBA8, np.uint8, 4)):
+        T, levels = 64, 4
+        src = O.synth_source(fmt, T, T, seed=9, holes=True)
+        n_out = sum((T >> l) ** 2 for l in range(1, levels)) * px
+        exp = np.zeros(n_out, dtype=dt)
+        O.lib().bto_generate_mipmaps(fmt, T, levels, src.ctypes.data, exp.ctypes.data)
+        d_in, d_out = ctx.alloc(src.nbytes), ctx.alloc(exp.nbytes)
+        ctx.h2d(d_in, src)
+        ctx.check(ctx.lib.bt_generate_mipmaps(ctx._h, fmt, T, levels, C.c_void_p(d_in), C.c_void_p(d_out), None))
+        got = np.empty_like(exp)
+        ctx.d2h(got, d_out)
+        ctx.free(d_in); ctx.free(d_out)
+        assert np.array_equal(got, exp)
