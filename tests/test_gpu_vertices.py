@@ -110,8 +110,9 @@ def test_vertices_structure_properties(ctx):
     vpt, vpr, g = scene.vc.vertices_per_tile, scene.vc.vertices_per_row, 16
     v = verts.reshape(len(tiles), g, vpr)
     # first/last index of every column strip is duplicated (degenerate triangles)
-    assert np.array_equal(v[:, :, 0].view(np.uint8), v[:, :, 1].view(np.uint8))
-    assert np.array_equal(v[:, :, -1].view(np.uint8), v[:, :, -2].view(np.uint8))
+    raw = np.ascontiguousarray(v).view(np.uint8).reshape(len(tiles), g, vpr, 40)
+    assert np.array_equal(raw[:, :, 0], raw[:, :, 1])
+    assert np.array_equal(raw[:, :, -1], raw[:, :, -2])
     # column c's right vertices are column c+1's left vertices
     right = v[:, :-1, 2::2][:, :, :g + 1]
     left = v[:, 1:, 1::2][:, :, :g + 1]

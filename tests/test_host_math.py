@@ -1,0 +1,110 @@
+"""The product's C++ f64 host math (host_math.cpp, reached through the C ABI; no GPU needed) against
+the oracle's independent C restatement and the Python clipmap reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bevy_terrain_b200 import _ffi as F
+from tests import oracle as O
+from tests.clipmap_ref import ClipmapRef
+from tests.scene import planar_view_positions, spherical_view_positions
+
+
+def _models():
+    from bevy_terrain_b200 import api
+    return [(api.TerrainModel.planar((0.0, -100.0, 0.0), 2000.0, 0.0, 500.0), O.terrain_model(F.BT_KIND_PLANAR, (0.0, -100.0, 0.0), 2000.0, 0.0, 500.0), planar_view_positions(6)),
+            (api.TerrainModel.sphere((0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0), O.terrain_model(F.BT_KIND_SPHERICAL, (0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0), spherical_view_positions())]
+
+
+def test_constructors_and_uniforms_match():
+    lib = F.load_library()
+    for prod, orc, _ in _models():
+        assert bytes(prod.c) == bytes(orc)
+        assert prod.scale() == O.model_scale(orc)
+        assert bytes(prod.mesh_transform()) == bytes(O.mesh_transform(orc))
+        for g in (16, 64):
+            cfg = O.default_view_config(grid_size=g)
+            u = F.ViewConfigUniform()
+            lib.bt_view_config_uniform_from(C.byref(cfg), C.byref(prod.c), C.byref(u))
+            assert bytes(u) == bytes(O.view_config_uniform(cfg, orc))
+    d = F.TerrainViewConfig()
+    lib.bt_terrain_view_config_default(C.byref(d))
+    assert bytes(d) == bytes(O.default_view_config())
+
+
+def test_model_approximation_matches_oracle_bitwise():
+    lib = F.load_library()
+    for prod, orc, positions in _models():
+        for pos in positions:
+            a = F.ModelApproximation()
+            assert lib.bt_model_approximation_compute(C.byref(prod.c), (F.f64 * 3)(*pos), 10, 123.5, C.byref(a)) == F.BT_OK
+            assert bytes(a) == bytes(O.model_approximation(orc, pos, 10, 123.5))
+
+
+def test_taylor_approximation_reproduces_f64_positions():
+    """the 2nd-order series (terrain_model.rs:263-360) evaluated like compute_relative_position must agree with
+    the exact f64 position near the view: validates the derivative algebra, not just its transcription"""
+    L = O.lib()
+    orc = O.terrain_model(F.BT_KIND_SPHERICAL, (0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0)
+    pos = (-(6371000.0 + 3000.0), 12345.0, -54321.0)
+    ap = O.model_approximation(orc, pos, 10, 0.0)
+    side = C.c_uint32(); uv = (C.c_double * 2)()
+    L.bto_coordinate_from_world_position(C.byref(orc), (C.c_double * 3)(*pos), C.byref(side), uv)
+    sp = ap.sides[side.value]
+    for ds, dt in ((1e-4, 0.0), (0.0, -2e-4), (3e-4, 2e-4)):
+        s, t = ds, dt
+        rel = [sp.c[k] + sp.c_s[k] * s + sp.c_t[k] * t + sp.c_ss[k] * s * s + sp.c_st[k] * s * t + sp.c_tt[k] * t * t for k in range(3)]
+        exact = (C.c_double * 3)()
+        L.bto_coordinate_world_position(C.byref(orc), side.value, (C.c_double * 2)(uv[0] + ds, uv[1] + dt), 0.0, exact)
+        err = np.linalg.norm(np.array(rel) - (np.array(exact[:]) - np.array(pos)))
+        assert err < 0.5, err   # metres, on a 6371 km sphere, ~2 km from the view
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_tile_tree_matches_python_reference_over_a_camera_path(which):
+    lib = F.load_library()
+    prod, orc, positions = _models()[which]
+    lod_count, atlas_size = 5, 400
+    cfg = O.default_view_config()
+    sides = 6 if which else 1
+    existing = [(s, l, x, y) for s in range(sides) for l in range(lod_count) for x in range(1 << l) for y in range(1 << l)
+                if not (l == 4 and (x + y) % 7 == 0)]   # some tiles missing on disk
+    ref = ClipmapRef(orc, cfg, lod_count, atlas_size, existing)
+    tt = C.c_void_p()
+    assert lib.bt_tile_tree_create(C.byref(prod.c), C.byref(cfg), lod_count, atlas_size, C.byref(tt)) == F.BT_OK
+    ex = np.array(existing, dtype=np.uint32)
+    assert lib.bt_tile_tree_add_existing(tt, ex.ctypes.data_as(C.POINTER(F.Tile)), len(ex)) == F.BT_OK
+    n_entries = sides * lod_count * cfg.tree_size ** 2
+    try:
+        for i, pos in enumerate(positions + positions[::-1]):
+            exp_loads = ref.update(pos)
+            buf = (F.TileLoad * atlas_size)(); n = F.u32()
+            assert lib.bt_tile_tree_update(tt, (F.f64 * 3)(*pos), buf, atlas_size, C.byref(n)) == F.BT_OK
+            got = [((l.tile.side, l.tile.lod, l.tile.x, l.tile.y), l.atlas_index) for l in buf[: n.value]]
+            assert got == exp_loads, f"frame {i}"
+            for j, (tc, _) in enumerate(exp_loads):
+                if j % 5 != 4:   # leave some tiles "still loading": best-tile lookup must fall back to parents
+                    ref.mark_loaded(tc)
+                    assert lib.bt_tile_tree_mark_loaded(tt, C.byref(F.Tile(*tc))) == F.BT_OK
+            ent = (F.TileTreeEntry * n_entries)(); org = (F.u32 * (2 * sides * lod_count))()
+            assert lib.bt_tile_tree_entries(tt, ent, n_entries, org, len(org)) == F.BT_OK
+            assert np.array_equal(np.frombuffer(ent, dtype=np.uint32).reshape(-1, 2), ref.entries())
+            assert np.array_equal(np.frombuffer(org, dtype=np.uint32), ref.origins.reshape(-1))
+    finally:
+        lib.bt_tile_tree_destroy(tt)
+
+
+def test_from_world_position_round_trip():
+    L = O.lib()
+    orc = O.terrain_model(F.BT_KIND_SPHERICAL, (10.0, -5.0, 3.0), 1000.0, 0.0, 1.0)
+    rng = np.random.default_rng(6)
+    for _ in range(200):
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        p = np.array([10.0, -5.0, 3.0]) + 1000.0 * d
+        side = C.c_uint32(); uv = (C.c_double * 2)()
+        L.bto_coordinate_from_world_position(C.byref(orc), (C.c_double * 3)(*p), C.byref(side), uv)
+        back = (C.c_double * 3)()
+        L.bto_coordinate_world_position(C.byref(orc), side.value, uv, 0.0, back)
+        assert np.allclose(back[:], p, atol=1e-6)
+        assert 0.0 <= uv[0] <= 1.0 and 0.0 <= uv[1] <= 1.0
