@@ -117,7 +117,7 @@ class TileLoad(C.Structure):
 class Dataset(C.Structure):  # preprocessor.rs:36-55
     _fields_ = [("attachment_index", u32), ("side", u32), ("top_left", f32 * 2), ("bottom_right", f32 * 2),
                 ("lod_begin", u32), ("lod_end", u32), ("width", u32), ("height", u32),
-                ("pixels_on_device", u32), ("_pad", u32), ("pixels", C.c_void_p)]
+                ("pixels_on_device", u32), ("row_begin", u32), ("row_count", u32), ("_pad", u32), ("pixels", C.c_void_p)]
 
 
 class Shard(C.Structure):

@@ -338,6 +338,8 @@ class PreprocessDataset:  # preprocessor.rs:36-55 — `pixels` replaces `path` (
     top_left: tuple = (0.0, 0.0)
     bottom_right: tuple = (1.0, 1.0)
     lod_range: range = range(0, 1)
+    row_begin: int = 0                    # row window of a sharded source (device_pixels points at row_begin)
+    row_count: int = 0
 
     def to_c(self) -> F.Dataset:
         d = F.Dataset()
@@ -352,6 +354,7 @@ class PreprocessDataset:  # preprocessor.rs:36-55 — `pixels` replaces `path` (
         else:
             d.height, d.width = self.height, self.width
             d.pixels_on_device, d.pixels = 1, self.device_pixels
+            d.row_begin, d.row_count = self.row_begin, self.row_count
         return d
 
 

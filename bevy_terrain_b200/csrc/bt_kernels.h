@@ -41,10 +41,10 @@ struct RowCopy {
 };
 
 struct DatasetDevice {
-    const void* pixels;     // device pointer, row-major
-    uint32_t width, height;
+    const void* pixels;     // device pointer to source row `row_begin`, row-major
+    uint32_t width, height; // of the WHOLE image
     float top_left[2], bottom_right[2];
-    uint32_t _pad[2];
+    uint32_t row_begin, row_count;  // rows present behind `pixels` (row_count == height for a whole image)
 };
 
 }  // namespace btd

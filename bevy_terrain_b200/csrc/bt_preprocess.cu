@@ -254,6 +254,8 @@ struct bt_preprocessor {
                 x.width = d.width; x.height = d.height;
                 x.top_left[0] = d.top_left[0]; x.top_left[1] = d.top_left[1];
                 x.bottom_right[0] = d.bottom_right[0]; x.bottom_right[1] = d.bottom_right[1];
+                x.row_begin = d.row_count ? d.row_begin : 0;
+                x.row_count = d.row_count ? d.row_count : d.height;
                 dd.push_back(x);
                 if (d.lod_end > d.lod_begin) collect(ji, d, di, d.lod_end - 1, tasks);
             }
@@ -414,6 +416,19 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
             return BT_ERR_INVALID_ARG;
         }
         if (!(d.bottom_right[0] > d.top_left[0]) || !(d.bottom_right[1] > d.top_left[1])) { ctx->set_error("add_datasets: empty extent"); return BT_ERR_INVALID_ARG; }
+        if (d.row_count && (uint64_t)d.row_begin + d.row_count > d.height) { ctx->set_error("add_datasets: row window exceeds the image"); return BT_ERR_INVALID_ARG; }
+        if (d.row_count && d.row_count < d.height) {
+            // the band's deepest-LOD tiles may only sample rows inside the window (bilinear footprint: +-1 row)
+            if (p->shard.world == 1) { ctx->set_error("add_datasets: a row window needs a sharded preprocessor"); return BT_ERR_INVALID_ARG; }
+            const uint32_t n = 1u << (d.lod_end - 1);
+            const double rows_per_tile = (double)d.height / n;
+            const double first = std::floor((double)((uint64_t)p->shard.rank * n / p->shard.world) * rows_per_tile) - 1.0;
+            const double last = std::ceil((double)((uint64_t)(p->shard.rank + 1) * n / p->shard.world) * rows_per_tile);
+            if ((double)d.row_begin > std::fmax(first, 0.0) || (double)(d.row_begin + d.row_count) < std::fmin(last, (double)d.height)) {
+                ctx->set_error("add_datasets: row window [%u,%u) does not cover rows [%.0f,%.0f) needed by rank %u", d.row_begin, d.row_begin + d.row_count, std::fmax(first, 0.0), std::fmin(last, (double)d.height), p->shard.rank);
+                return BT_ERR_INVALID_ARG;
+            }
+        }
         if (count > 1 && (side_mask & (1u << d.side))) { ctx->set_error("add_datasets: datasets of one job must lie on distinct sides"); return BT_ERR_INVALID_ARG; }
         side_mask |= 1u << d.side;
         if (p->shard.world > 1) {
@@ -429,7 +444,7 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
         bt_dataset d = datasets[i];
         if (!d.pixels_on_device) {  // stage the host image on the device (the reference uploads the Image asset, preprocessor.rs:241-246)
             void* dev = nullptr;
-            const size_t bytes = (size_t)d.width * d.height * s.px;
+            const size_t bytes = (size_t)d.width * (d.row_count ? d.row_count : d.height) * s.px;
             BT_CUDA(ctx, cudaMalloc(&dev, bytes));
             cudaError_t e = cudaMemcpy(dev, d.pixels, bytes, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { cudaFree(dev); BT_CUDA(ctx, e); }

@@ -81,7 +81,10 @@ __device__ __forceinline__ Px4 source_texel(const DatasetDevice& d, int x, int y
     using F = Fmt<FORMAT>;
     x = min(max(x, 0), (int)d.width - 1);   // clamp-to-edge (ImageSampler::linear, preprocessor.rs:408-409)
     y = min(max(y, 0), (int)d.height - 1);
-    return F::decode(__ldg(reinterpret_cast<const typename F::texel*>(d.pixels) + (size_t)y * d.width + (size_t)x));
+    // row window of a sharded source: rows outside the band are never needed by the band's tiles
+    // (bt_preprocess.cu validates the window); clamp so that a bad window cannot fault
+    const int ry = min(max(y - (int)d.row_begin, 0), (int)d.row_count - 1);
+    return F::decode(__ldg(reinterpret_cast<const typename F::texel*>(d.pixels) + (size_t)ry * d.width + (size_t)x));
 }
 
 template <int FORMAT>

@@ -346,6 +346,9 @@ typedef struct bt_dataset {
     uint32_t lod_begin, lod_end;     /* lod_range = lod_begin..lod_end (exclusive) */
     uint32_t width, height;          /* source image size in pixels */
     uint32_t pixels_on_device;
+    /* row window (sharded hosts hold only their band of a huge source): `pixels` points at source
+     * row `row_begin` and holds `row_count` rows; row_count == 0 means the whole image.          */
+    uint32_t row_begin, row_count;
     uint32_t _pad;
     const void* pixels;              /* R16: uint16, Rgba8: 4 x uint8; row-major */
 } bt_dataset;
