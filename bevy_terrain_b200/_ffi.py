@@ -209,6 +209,7 @@ def _declare(lib: C.CDLL) -> None:
         "bt_preprocessor_save": (i32, [vp, u32, C.c_char_p]),
         "bt_generate_mipmaps": (i32, [vp, u32, u32, u32, vp, vp, vp]),
         "bt_synth_source": (i32, [vp, u32, u32, u32, u32, u32, u32, u32, vp, vp]),
+        "bt_selftest_numerics": (i32, [vp, P(f32), P(f32), u32, P(u32)]),
         "bt_device_alloc": (i32, [vp, C.c_size_t, P(vp)]),
         "bt_device_free": (i32, [vp, vp]),
         "bt_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t, vp]),

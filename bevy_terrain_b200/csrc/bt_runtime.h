@@ -67,5 +67,6 @@ cudaError_t bt_launch_mipmaps(uint32_t format, uint32_t texture_size, uint32_t m
                               void* mips_out, cudaStream_t stream);
 cudaError_t bt_launch_synth(uint32_t format, uint32_t width, uint32_t height, uint32_t x0, uint32_t y0, uint32_t seed,
                             uint32_t holes, void* out, cudaStream_t stream);
+cudaError_t bt_launch_selftest(const float* x, float* log2_out, uint32_t n, uint32_t* mismatches, cudaStream_t stream);
 cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream);
 }

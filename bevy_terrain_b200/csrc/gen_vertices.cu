@@ -47,23 +47,59 @@ struct Record {  // one bt_vertex as five 8-byte words
     float2 w[5];
 };
 
+// Loop-invariant values of one launch, hoisted into registers once per thread.  Every entry is the
+// result of exactly the operations the per-vertex formula would perform, so hoisting is bit-neutral.
+struct FrameConsts {
+    float g, inv_g;            // grid_size and, when it is a power of two, its exact reciprocal
+    bool  g_pow2;
+    float Tf;                  // f32(texture_size)
+    int   T, Tm1;
+    float min_h, max_h;
+    float a_scale, a_offset;   // attachment_uv (attachments.wgsl:7-10)
+    float normal_offset;       // 0.5 / attachments[0].size (attachments.wgsl:85)
+    float side_length;         // attachments.wgsl:71,78
+    float size0;               // attachments[0].size
+    Vec3  planar_normal;       // normal_local_to_world for the planar model: a constant (functions.wgsl:14-24)
+    float lod_cap;             // f32(lod_count) - 0.00001 (functions.wgsl:52)
+};
+
+template <bool SPHERICAL>
+__device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) {
+    FrameConsts F;
+    F.g = U.view_config.grid_size;
+    const uint32_t gi = (uint32_t)F.g;
+    F.g_pow2 = ((float)gi == F.g) && gi != 0u && (gi & (gi - 1u)) == 0u;
+    F.inv_g = 1.0f / F.g;      // exact when g is a power of two: x * inv_g == x / g bit for bit
+    F.T = (int)U.texture_size;
+    F.Tm1 = F.T - 1;
+    F.Tf = (float)U.texture_size;
+    F.min_h = U.terrain_config.min_height;
+    F.max_h = U.terrain_config.max_height;
+    F.a_scale = U.attachments[0].scale;
+    F.a_offset = U.attachments[0].offset;
+    F.size0 = U.attachments[0].size;
+    F.normal_offset = 0.5f / F.size0;
+    F.side_length = SPHERICAL ? (float)(3.14159265359 / 4.0) * U.terrain_config.scale : U.terrain_config.scale;
+    F.planar_normal = normal_local_to_world<false>(U.mesh, Vec3{0.0f, 0.0f, 0.0f});
+    F.lod_cap = (float)U.terrain_config.lod_count - 0.00001f;
+    return F;
+}
+
 // bilinear R16 fetch — exact f32 weights, texel centres at i+0.5, clamp-to-edge; operation order
 // of the CPU twin AttachmentData::sample (src/terrain_data/mod.rs:221-264): lerp y, then x
-__device__ __forceinline__ float sample_r16(const uint16_t* __restrict__ layer, uint32_t T, float u, float v) {
-    float Tf = (float)T;
-    float px = u * Tf - 0.5f, py = v * Tf - 0.5f;
+__device__ __forceinline__ float sample_r16(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
+    float px = u * F.Tf - 0.5f, py = v * F.Tf - 0.5f;
     float fx = floorf(px), fy = floorf(py);
     float rx = px - fx, ry = py - fy;
     int ix = (int)fx, iy = (int)fy;
-    int m = (int)T - 1;
-    int x0 = min(max(ix, 0), m), x1 = min(max(ix + 1, 0), m);
-    int y0 = min(max(iy, 0), m), y1 = min(max(iy + 1, 0), m);
-    const uint16_t* r0 = layer + (size_t)y0 * T;
-    const uint16_t* r1 = layer + (size_t)y1 * T;
-    float v00 = (float)__ldg(r0 + x0) / 65535.0f;
-    float v01 = (float)__ldg(r1 + x0) / 65535.0f;
-    float v10 = (float)__ldg(r0 + x1) / 65535.0f;
-    float v11 = (float)__ldg(r1 + x1) / 65535.0f;
+    int x0 = min(max(ix, 0), F.Tm1), x1 = min(max(ix + 1, 0), F.Tm1);
+    int y0 = min(max(iy, 0), F.Tm1), y1 = min(max(iy + 1, 0), F.Tm1);
+    const uint16_t* r0 = layer + y0 * F.T;
+    const uint16_t* r1 = layer + y1 * F.T;
+    float v00 = unorm16_to_float(__ldg(r0 + x0));
+    float v01 = unorm16_to_float(__ldg(r1 + x0));
+    float v10 = unorm16_to_float(__ldg(r0 + x1));
+    float v11 = unorm16_to_float(__ldg(r1 + x1));
     float a = v00 + (v01 - v00) * ry;
     float b = v10 + (v11 - v10) * ry;
     return a + (b - a) * rx;
@@ -86,24 +122,22 @@ __device__ __forceinline__ AtlasTile lookup_tile(const ViewUniforms& U, const bt
 }
 
 // sample_height — attachments.wgsl:7-24,45-49
-__device__ __forceinline__ float sample_height_uv(const ViewUniforms& U, const uint16_t* __restrict__ atlas, uint32_t index, float u, float v) {
-    const uint32_t T = U.texture_size;
-    const float s = sample_r16(atlas + (size_t)index * T * T, T, u, v);
-    return mix(U.terrain_config.min_height, U.terrain_config.max_height, s);
+__device__ __forceinline__ float sample_height_uv(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
+    const float s = sample_r16(F, layer, u, v);
+    return mix(F.min_h, F.max_h, s);
 }
 
 // sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch)
 template <bool SPHERICAL>
-__device__ __forceinline__ Vec3 sample_normal(const ViewUniforms& U, const uint16_t* __restrict__ atlas, const AtlasTile& t,
+__device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16_t* __restrict__ layer, const AtlasTile& t,
                                               float u, float v, Vec3 vertex_normal) {
-    const float side_length = SPHERICAL ? (float)(3.14159265359 / 4.0) * U.terrain_config.scale : U.terrain_config.scale;
-    const float pixels_per_side = U.attachments[0].size * tile_count(t.c.lod);
-    const float distance_between_samples = side_length / pixels_per_side;
-    const float offset = 0.5f / U.attachments[0].size;
-    const float left = sample_height_uv(U, atlas, t.index, u + -offset, v + 0.0f);
-    const float up = sample_height_uv(U, atlas, t.index, u + 0.0f, v + -offset);
-    const float right = sample_height_uv(U, atlas, t.index, u + offset, v + 0.0f);
-    const float down = sample_height_uv(U, atlas, t.index, u + 0.0f, v + offset);
+    const float pixels_per_side = F.size0 * tile_count(t.c.lod);
+    const float distance_between_samples = F.side_length / pixels_per_side;
+    const float offset = F.normal_offset;
+    const float left = sample_height_uv(F, layer, u + -offset, v + 0.0f);
+    const float up = sample_height_uv(F, layer, u + 0.0f, v + -offset);
+    const float right = sample_height_uv(F, layer, u + offset, v + 0.0f);
+    const float down = sample_height_uv(F, layer, u + 0.0f, v + offset);
     const Vec3 sn = normalize3(Vec3{left - right, down - up, distance_between_samples});
     Vec3 r;
     if (SPHERICAL) {
@@ -126,16 +160,19 @@ __device__ __forceinline__ Vec3 sample_normal(const ViewUniforms& U, const uint1
 
 // vertex_info + vertex + vertex_output — vertex.wgsl:30-98
 template <bool SPHERICAL>
-__device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const bt_tile_tree_entry* __restrict__ tile_tree,
+__device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const FrameConsts& F, const bt_tile_tree_entry* __restrict__ tile_tree,
                                                  const uint16_t* __restrict__ atlas, uint32_t flags, const bt_tile& tile,
                                                  uint32_t tile_index, uint32_t gx, uint32_t gy) {
     const bt_view_config_uniform& vc = U.view_config;
     const bt_model_approximation& ap = U.approximation;
-    const float g = vc.grid_size;
-    const Coord c0{tile.side, tile.lod, tile.x, tile.y, (float)gx / g, (float)gy / g};  // compute_tile_uv
+    const float g = F.g;
+    // compute_tile_uv — functions.wgsl:64-71 (x / g == x * (1/g) exactly when g is a power of two)
+    const float u0 = F.g_pow2 ? (float)gx * F.inv_g : (float)gx / g;
+    const float v0 = F.g_pow2 ? (float)gy * F.inv_g : (float)gy / g;
+    const Coord c0{tile.side, tile.lod, tile.x, tile.y, u0, v0};
     Vec3 lp = local_position<SPHERICAL>(c0);
     Vec3 wp = position_local_to_world(U.mesh, lp);
-    Vec3 wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+    Vec3 wn = SPHERICAL ? normal_local_to_world<SPHERICAL>(U.mesh, lp) : F.planar_normal;
     const float h0 = ap.approximate_height;
     const float* e = U.view_world_position;
     float d = length3(Vec3{(wp.x + h0 * wn.x) - e[0], (wp.y + h0 * wn.y) - e[1], (wp.z + h0 * wn.z) - e[2]});
@@ -157,30 +194,33 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const bt
     if (high_precision) {
         const Vec3 rel = relative_position(ap, c);
         wp = Vec3{e[0] + rel.x, e[1] + rel.y, e[2] + rel.z};
-    } else {
+    } else if (flags & BT_FLAG_MORPH) {
+        // without MORPH the coordinate is unchanged and the recomputation would reproduce lp/wp/wn bit for bit
         lp = local_position<SPHERICAL>(c);
         wp = position_local_to_world(U.mesh, lp);
-        wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+        if (SPHERICAL) wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
     }
     // compute_blend — functions.wgsl:51-62
-    const float target_lod = fminf(log2_det(vc.blend_distance / d), (float)U.terrain_config.lod_count - 0.00001f);
+    const float target_lod = fminf(log2_det(vc.blend_distance / d), F.lod_cap);
     const uint32_t blend_lod = f2u(target_lod);
     float blend_ratio = 0.0f;
     if ((flags & BT_FLAG_BLEND) && blend_lod != 0u)
         blend_ratio = inverse_mix((float)blend_lod + vc.blend_range, (float)blend_lod, target_lod);
 
-    const float a_scale = U.attachments[0].scale, a_offset = U.attachments[0].offset;
+    const int tile_texels = F.T * F.T;
     const AtlasTile ta = lookup_tile(U, tile_tree, c, blend_lod);
-    const float ua = ta.c.u * a_scale + a_offset, va = ta.c.v * a_scale + a_offset;  // attachment_uv
-    float height = sample_height_uv(U, atlas, ta.index, ua, va);
+    const uint16_t* layer_a = atlas + (size_t)ta.index * tile_texels;
+    const float ua = ta.c.u * F.a_scale + F.a_offset, va = ta.c.v * F.a_scale + F.a_offset;  // attachment_uv
+    float height = sample_height_uv(F, layer_a, ua, va);
     Vec3 nrm = wn;
-    if (flags & BT_FLAG_NORMALS) nrm = sample_normal<SPHERICAL>(U, atlas, ta, ua, va, wn);
+    if (flags & BT_FLAG_NORMALS) nrm = sample_normal<SPHERICAL>(F, layer_a, ta, ua, va, wn);
     if (blend_ratio > 0.0f) {
         const AtlasTile tb = lookup_tile(U, tile_tree, c, blend_lod - 1u);
-        const float ub = tb.c.u * a_scale + a_offset, vb = tb.c.v * a_scale + a_offset;
-        height = mix(height, sample_height_uv(U, atlas, tb.index, ub, vb), blend_ratio);
+        const uint16_t* layer_b = atlas + (size_t)tb.index * tile_texels;
+        const float ub = tb.c.u * F.a_scale + F.a_offset, vb = tb.c.v * F.a_scale + F.a_offset;
+        height = mix(height, sample_height_uv(F, layer_b, ub, vb), blend_ratio);
         if (flags & BT_FLAG_NORMALS) {  // fragment.wgsl:103-107
-            const Vec3 n2 = sample_normal<SPHERICAL>(U, atlas, tb, ub, vb, wn);
+            const Vec3 n2 = sample_normal<SPHERICAL>(F, layer_b, tb, ub, vb, wn);
             nrm = Vec3{mix(nrm.x, n2.x, blend_ratio), mix(nrm.y, n2.y, blend_ratio), mix(nrm.z, n2.z, blend_ratio)};
         }
     }
@@ -221,8 +261,9 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         mbar_expect_tx(&H.bar, (uint32_t)sizeof(ViewUniforms));
         bulk_load(&H.U, P.uniforms, (uint32_t)sizeof(ViewUniforms), &H.bar);
     }
-    mbar_wait(&H.bar, 0);
+    mbar_wait_cta(&H.bar, 0);
     const ViewUniforms& U = H.U;
+    const FrameConsts F = make_frame_consts<SPHERICAL>(U);
 
     const uint32_t g = P.grid_size;
     const uint32_t vpr = U.view_config.vertices_per_row, vpt = U.view_config.vertices_per_tile;
@@ -260,7 +301,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         const uint32_t n_verts = n_cols * n_rows;
         for (uint32_t i = tid; i < n_verts; i += GEN_THREADS) {
             const uint32_t gy = i / n_cols, lx = i - gy * n_cols;  // lanes walk along texel rows
-            const Record r = compute_vertex<SPHERICAL>(U, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
+            const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
             // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
             if (lx < n_strips) {
                 store_record(image, strip_stride, lx, 2u * gy + 1u, r);

@@ -31,7 +31,7 @@ template <int FORMAT> struct Fmt;
 template <> struct Fmt<BT_FORMAT_R16> {
     using texel = uint16_t;
     static constexpr int PX_PER_THREAD = 8;
-    static __device__ __forceinline__ Px4 decode(uint16_t t) { return Px4{{(float)t / 65535.0f, 0.0f, 0.0f, 1.0f}}; }
+    static __device__ __forceinline__ Px4 decode(uint16_t t) { return Px4{{unorm16_to_float(t), 0.0f, 0.0f, 1.0f}}; }  // == (float)t / 65535.0f
     static __device__ __forceinline__ uint16_t zero() { return 0; }
     static __device__ __forceinline__ uint16_t pack(const Px4& p) {  // pack2x16unorm — preprocessing.wgsl:85-88
         float c = fminf(fmaxf(p.v[0], 0.0f), 1.0f);
@@ -42,7 +42,7 @@ template <> struct Fmt<BT_FORMAT_RGBA8> {
     using texel = uchar4;
     static constexpr int PX_PER_THREAD = 4;
     static __device__ __forceinline__ Px4 decode(uchar4 t) {
-        return Px4{{(float)t.x / 255.0f, (float)t.y / 255.0f, (float)t.z / 255.0f, (float)t.w / 255.0f}};
+        return Px4{{unorm8_to_float(t.x), unorm8_to_float(t.y), unorm8_to_float(t.z), unorm8_to_float(t.w)}};  // == (float)c / 255.0f
     }
     static __device__ __forceinline__ uchar4 zero() { return make_uchar4(0, 0, 0, 0); }
     static __device__ __forceinline__ uchar4 pack(const Px4& p) {  // pack4x8unorm — preprocessing.wgsl:81-84
@@ -101,27 +101,39 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
     const uint32_t y = pid / packets_per_row, x0 = (pid - y * packets_per_row) * N;
     texel* row = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes) + (size_t)y * L.T;
     const bool aligned = ((L.T * sizeof(texel)) % 16 == 0) && (L.tile_bytes % 16 == 0);
-    const float tile_scale = tile_count(task.tile.lod);
+    const float inv_tile_scale = exp2i(-(int)(task.tile.lod & 31u));  // x / tile_count(lod) == x * 2^-lod exactly
     const float Cf = (float)L.C;
+    // inverse_mix with top_left = 0, bottom_right = 1 is (x - 0) / (1 - 0) = x exactly: skip the division
+    const bool full_x = d.top_left[0] == 0.0f && d.bottom_right[0] == 1.0f;
+    const bool full_y = d.top_left[1] == 0.0f && d.bottom_right[1] == 1.0f;
+    const float range_x = d.bottom_right[0] - d.top_left[0], range_y = d.bottom_right[1] - d.top_left[1];
+    // the y terms are shared by the packet
+    const float tcy = (float)(y - L.B) / Cf;
+    float sy = ((float)task.tile.y + tcy) * inv_tile_scale;
+    if (!full_y) sy = (sy - d.top_left[1]) / range_y;
+    const float py = sy * (float)d.height - 0.5f;
+    const float fy = floorf(py);
+    const float ry = py - fy;
+    const int iy = (int)fy;
+    const bool inside_y = tcy >= 0.0f && tcy <= 1.0f;
+    const float Wf = (float)d.width;
     Packet<texel, N> out;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t x = x0 + i;
         if (x >= L.T) { out.t[i] = F::zero(); continue; }
         if (is_border(L, x, y)) { out.t[i] = F::zero(); continue; }
-        const float tcx = (float)(x - L.B) / Cf, tcy = (float)(y - L.B) / Cf;
-        float sx = ((float)task.tile.x + tcx) / tile_scale;
-        float sy = ((float)task.tile.y + tcy) / tile_scale;
-        sx = (sx - d.top_left[0]) / (d.bottom_right[0] - d.top_left[0]);   // inverse_mix — preprocessing.wgsl:44-46
-        sy = (sy - d.top_left[1]) / (d.bottom_right[1] - d.top_left[1]);
-        const float px = sx * (float)d.width - 0.5f, py = sy * (float)d.height - 0.5f;
-        const float fx = floorf(px), fy = floorf(py);
-        const float rx = px - fx, ry = py - fy;
-        const int ix = (int)fx, iy = (int)fy;
+        const float tcx = (float)(x - L.B) / Cf;
+        float sx = ((float)task.tile.x + tcx) * inv_tile_scale;
+        if (!full_x) sx = (sx - d.top_left[0]) / range_x;   // inverse_mix — preprocessing.wgsl:44-46
+        const float px = sx * Wf - 0.5f;
+        const float fx = floorf(px);
+        const float rx = px - fx;
+        const int ix = (int)fx;
         const Px4 v00 = source_texel<FORMAT>(d, ix, iy), v10 = source_texel<FORMAT>(d, ix + 1, iy);
         const Px4 v01 = source_texel<FORMAT>(d, ix, iy + 1), v11 = source_texel<FORMAT>(d, ix + 1, iy + 1);
         const bool is_valid = v00.v[0] != 0.0f && v10.v[0] != 0.0f && v01.v[0] != 0.0f && v11.v[0] != 0.0f;  // textureGather(0,..)
-        const bool is_inside = (tcx >= 0.0f && tcx <= 1.0f) && (tcy >= 0.0f && tcy <= 1.0f);                    // inside_square
+        const bool is_inside = (tcx >= 0.0f && tcx <= 1.0f) && inside_y;                                        // inside_square
         if (is_valid && is_inside) {
             Px4 value;
 #pragma unroll
@@ -178,8 +190,15 @@ __global__ void __launch_bounds__(PYR_THREADS) downsample_kernel(PyramidLayout L
             }
         }
         if (count != 0.0f) {
+            // value / count: division by 1, 2, 4 is an exact scaling (bit-identical to the IEEE quotient)
+            if (count == 3.0f) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sum.v[k] = sum.v[k] / count;
+                for (int k = 0; k < 4; ++k) sum.v[k] = sum.v[k] / 3.0f;
+            } else {
+                const float scale = count == 4.0f ? 0.25f : (count == 2.0f ? 0.5f : 1.0f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sum.v[k] = sum.v[k] * scale;
+            }
             out.t[i] = F::pack(sum);
         }
     }
@@ -414,6 +433,28 @@ extern "C" cudaError_t bt_launch_synth(uint32_t format, uint32_t width, uint32_t
     const uint64_t n = (uint64_t)width * height;
     if (n == 0) return cudaSuccess;
     synth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(format, width, height, x0, y0, seed, holes, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// numerics self-test: the exact-decode shortcuts against the IEEE divisions they replace, and
+// log2_det evaluated on caller-provided inputs (compared with the oracle's bto_log2f by the tests)
+// ------------------------------------------------------------------------------------------------
+namespace btd {
+__global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__ log2_out, uint32_t n, uint32_t* __restrict__ mismatches) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536u) {
+        volatile float m16 = 65535.0f, m8 = 255.0f;   // volatile: keep the reference form a true IEEE division
+        if (unorm16_to_float(i) != (float)i / m16) atomicAdd(&mismatches[0], 1u);
+        if (i < 256u && unorm8_to_float(i) != (float)i / m8) atomicAdd(&mismatches[1], 1u);
+    }
+    if (i < n) log2_out[i] = log2_det(x[i]);
+}
+}  // namespace btd
+
+extern "C" cudaError_t bt_launch_selftest(const float* x, float* log2_out, uint32_t n, uint32_t* mismatches, cudaStream_t stream) {
+    const uint32_t threads = n > 65536u ? n : 65536u;
+    btd::selftest_kernel<<<(threads + 255) / 256, 256, 0, stream>>>(x, log2_out, n, mismatches);
     return cudaGetLastError();
 }
 

@@ -77,8 +77,7 @@ select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restri
     // prepare_root — prepare_prepass.wgsl:4-23 (overlaps the bulk copy)
     const uint32_t n_roots = SPHERICAL ? 6u : 1u;
     if (tid < (int)n_roots) S.frontier[0][tid] = bt_tile{(uint32_t)tid, 0u, 0u, 0u};
-    mbar_wait(&S.bar, 0);
-    __syncthreads();
+    mbar_wait_cta(&S.bar, 0);
 
     const ViewUniforms& U = S.U;
     const uint32_t refinement_count = U.view_config.refinement_count;
