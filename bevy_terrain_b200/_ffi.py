@@ -120,6 +120,10 @@ class Dataset(C.Structure):  # preprocessor.rs:36-55
                 ("pixels_on_device", u32), ("row_begin", u32), ("row_count", u32), ("_pad", u32), ("pixels", C.c_void_p)]
 
 
+class ExchangeCopy(C.Structure):
+    _fields_ = [("tile", Tile), ("tile_row", u32), ("tile_col", u32), ("pixels", u32), ("src_rank", u32), ("buffer_offset", u64)]
+
+
 class Shard(C.Structure):
     _fields_ = [("rank", u32), ("world", u32)]
 
@@ -196,6 +200,9 @@ def _declare(lib: C.CDLL) -> None:
         "bt_preprocessor_run_split_downsample": (i32, [vp, vp]),
         "bt_preprocessor_run_stitch": (i32, [vp, vp]),
         "bt_preprocessor_run": (i32, [vp, vp]),
+        "bt_preprocessor_plan": (i32, [vp]),
+        "bt_preprocessor_plan_tiles": (i32, [vp, u32, P(Tile), P(u32), u32, P(u32)]),
+        "bt_preprocessor_plan_exchange": (i32, [vp, u32, u32, P(ExchangeCopy), u32, P(u32)]),
         "bt_preprocessor_halo_bytes": (i32, [vp, P(u64)]),
         "bt_preprocessor_halo_pack": (i32, [vp, vp, vp]),
         "bt_preprocessor_halo_unpack": (i32, [vp, vp, vp]),

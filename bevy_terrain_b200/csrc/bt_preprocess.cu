@@ -25,6 +25,8 @@ using btd::DatasetDevice;
 using btd::PyramidTask;
 using btd::RowCopy;
 
+#define BT_SET_ERROR(ctx_, ...) do { if (ctx_) (ctx_)->set_error(__VA_ARGS__); } while (0)
+
 namespace {
 
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
@@ -112,6 +114,7 @@ struct bt_preprocessor {
     RowCopy* d_copies = nullptr; size_t d_copies_cap = 0;
 
     bool spherical() const { return kind == BT_KIND_SPHERICAL; }
+    bool plan_only() const { return ctx == nullptr; }  // created without a context: host-side planning only
 
     // PreprocessDataset::overlapping_tiles — preprocessor.rs:58-66 (f32), intersected with the rows
     // this rank owns (world == 1: everything)
@@ -162,7 +165,7 @@ struct bt_preprocessor {
             unsigned char* bigger = nullptr;
             cudaError_t e = cudaMalloc((void**)&bigger, (size_t)need * s.tile_bytes);
             if (e != cudaSuccess) {
-                ctx->set_error("preprocessor: pyramid store of %u tiles (%zu bytes) does not fit: %s", need, (size_t)need * s.tile_bytes, cudaGetErrorString(e));
+                BT_SET_ERROR(ctx, "preprocessor: pyramid store of %u tiles (%zu bytes) does not fit: %s", need, (size_t)need * s.tile_bytes, cudaGetErrorString(e));
                 (void)cudaGetLastError();
                 return BT_ERR_OUT_OF_MEMORY;
             }
@@ -358,14 +361,14 @@ extern "C" {
 
 bt_status bt_preprocessor_create(bt_context* ctx, uint32_t kind, const bt_attachment_config* attachments, uint32_t attachment_count,
                                  uint32_t lod_count, bt_shard shard, bt_preprocessor** out) {
-    if (!ctx || !attachments || !out || attachment_count == 0 || attachment_count > 8 || lod_count == 0 || lod_count > 24) return BT_ERR_INVALID_ARG;
+    if (!attachments || !out || attachment_count == 0 || attachment_count > 8 || lod_count == 0 || lod_count > 24) return BT_ERR_INVALID_ARG;
     if (kind != BT_KIND_PLANAR && kind != BT_KIND_SPHERICAL) return BT_ERR_INVALID_ARG;
     if (shard.world == 0 || shard.rank >= shard.world || (shard.world & (shard.world - 1)) != 0) {
-        ctx->set_error("bt_preprocessor_create: shard world must be a power of two and rank < world");
+        BT_SET_ERROR(ctx, "bt_preprocessor_create: shard world must be a power of two and rank < world");
         return BT_ERR_INVALID_ARG;
     }
     if (shard.world > 1 && kind == BT_KIND_SPHERICAL) {
-        ctx->set_error("bt_preprocessor_create: sharding a spherical (cross-face stitched) pyramid is not supported yet");
+        BT_SET_ERROR(ctx, "bt_preprocessor_create: sharding a spherical (cross-face stitched) pyramid is not supported yet");
         return BT_ERR_INVALID_ARG;
     }
     bt_preprocessor* p = new bt_preprocessor();
@@ -377,7 +380,7 @@ bt_status bt_preprocessor_create(bt_context* ctx, uint32_t kind, const bt_attach
     for (uint32_t i = 0; i < attachment_count; ++i) {
         const bt_attachment_config& a = attachments[i];
         if ((a.format != BT_FORMAT_R16 && a.format != BT_FORMAT_RGBA8) || a.texture_size <= 2 * a.border_size) {
-            ctx->set_error("bt_preprocessor_create: attachment %u: unsupported format %u (only R16/Rgba8 have shader paths in the reference) or texture_size <= 2*border", i, a.format);
+            BT_SET_ERROR(ctx, "bt_preprocessor_create: attachment %u: unsupported format %u (only R16/Rgba8 have shader paths in the reference) or texture_size <= 2*border", i, a.format);
             delete p;
             return BT_ERR_INVALID_ARG;
         }
@@ -393,6 +396,7 @@ bt_status bt_preprocessor_create(bt_context* ctx, uint32_t kind, const bt_attach
 
 void bt_preprocessor_destroy(bt_preprocessor* p) {
     if (!p) return;
+    if (p->plan_only()) { delete p; return; }
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (Store& s : p->stores) if (s.arena) cudaFree(s.arena);
@@ -406,43 +410,43 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
     bt_context* ctx = p->ctx;
     Job j;
     j.attachment = datasets[0].attachment_index;
-    if (j.attachment >= p->stores.size()) { ctx->set_error("add_datasets: attachment_index %u out of range", j.attachment); return BT_ERR_INVALID_ARG; }
-    if (p->shard.world > 1 && count != 1) { ctx->set_error("add_datasets: sharded preprocessing takes one dataset per job"); return BT_ERR_INVALID_ARG; }
+    if (j.attachment >= p->stores.size()) { BT_SET_ERROR(ctx, "add_datasets: attachment_index %u out of range", j.attachment); return BT_ERR_INVALID_ARG; }
+    if (p->shard.world > 1 && count != 1) { BT_SET_ERROR(ctx, "add_datasets: sharded preprocessing takes one dataset per job"); return BT_ERR_INVALID_ARG; }
     uint32_t side_mask = 0;
     for (uint32_t i = 0; i < count; ++i) {
         const bt_dataset& d = datasets[i];
-        if (d.attachment_index != j.attachment || d.side >= 6 || d.lod_begin >= d.lod_end || d.lod_end > p->lod_count || !d.pixels || d.width == 0 || d.height == 0) {
-            ctx->set_error("add_datasets: dataset %u invalid (attachment/side/lod_range %u..%u of %u/pixels)", i, d.lod_begin, d.lod_end, p->lod_count);
+        if (d.attachment_index != j.attachment || d.side >= 6 || d.lod_begin >= d.lod_end || d.lod_end > p->lod_count || (!d.pixels && !p->plan_only()) || d.width == 0 || d.height == 0) {
+            BT_SET_ERROR(ctx, "add_datasets: dataset %u invalid (attachment/side/lod_range %u..%u of %u/pixels)", i, d.lod_begin, d.lod_end, p->lod_count);
             return BT_ERR_INVALID_ARG;
         }
-        if (!(d.bottom_right[0] > d.top_left[0]) || !(d.bottom_right[1] > d.top_left[1])) { ctx->set_error("add_datasets: empty extent"); return BT_ERR_INVALID_ARG; }
-        if (d.row_count && (uint64_t)d.row_begin + d.row_count > d.height) { ctx->set_error("add_datasets: row window exceeds the image"); return BT_ERR_INVALID_ARG; }
+        if (!(d.bottom_right[0] > d.top_left[0]) || !(d.bottom_right[1] > d.top_left[1])) { BT_SET_ERROR(ctx, "add_datasets: empty extent"); return BT_ERR_INVALID_ARG; }
+        if (d.row_count && (uint64_t)d.row_begin + d.row_count > d.height) { BT_SET_ERROR(ctx, "add_datasets: row window exceeds the image"); return BT_ERR_INVALID_ARG; }
         if (d.row_count && d.row_count < d.height) {
             // the band's deepest-LOD tiles may only sample rows inside the window (bilinear footprint: +-1 row)
-            if (p->shard.world == 1) { ctx->set_error("add_datasets: a row window needs a sharded preprocessor"); return BT_ERR_INVALID_ARG; }
+            if (p->shard.world == 1) { BT_SET_ERROR(ctx, "add_datasets: a row window needs a sharded preprocessor"); return BT_ERR_INVALID_ARG; }
             const uint32_t n = 1u << (d.lod_end - 1);
             const double rows_per_tile = (double)d.height / n;
             const double first = std::floor((double)((uint64_t)p->shard.rank * n / p->shard.world) * rows_per_tile) - 1.0;
             const double last = std::ceil((double)((uint64_t)(p->shard.rank + 1) * n / p->shard.world) * rows_per_tile);
             if ((double)d.row_begin > std::fmax(first, 0.0) || (double)(d.row_begin + d.row_count) < std::fmin(last, (double)d.height)) {
-                ctx->set_error("add_datasets: row window [%u,%u) does not cover rows [%.0f,%.0f) needed by rank %u", d.row_begin, d.row_begin + d.row_count, std::fmax(first, 0.0), std::fmin(last, (double)d.height), p->shard.rank);
+                BT_SET_ERROR(ctx, "add_datasets: row window [%u,%u) does not cover rows [%.0f,%.0f) needed by rank %u", d.row_begin, d.row_begin + d.row_count, std::fmax(first, 0.0), std::fmin(last, (double)d.height), p->shard.rank);
                 return BT_ERR_INVALID_ARG;
             }
         }
-        if (count > 1 && (side_mask & (1u << d.side))) { ctx->set_error("add_datasets: datasets of one job must lie on distinct sides"); return BT_ERR_INVALID_ARG; }
+        if (count > 1 && (side_mask & (1u << d.side))) { BT_SET_ERROR(ctx, "add_datasets: datasets of one job must lie on distinct sides"); return BT_ERR_INVALID_ARG; }
         side_mask |= 1u << d.side;
         if (p->shard.world > 1) {
             if (d.top_left[0] != 0.0f || d.top_left[1] != 0.0f || d.bottom_right[0] != 1.0f || d.bottom_right[1] != 1.0f || d.lod_end - 1 < p->root_lod) {
-                ctx->set_error("add_datasets: sharded preprocessing needs a full-coverage dataset whose deepest LOD has >= world tile rows");
+                BT_SET_ERROR(ctx, "add_datasets: sharded preprocessing needs a full-coverage dataset whose deepest LOD has >= world tile rows");
                 return BT_ERR_INVALID_ARG;
             }
         }
     }
-    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->plan_only()) BT_CUDA(ctx, cudaSetDevice(ctx->device));
     const Store& s = p->stores[j.attachment];
     for (uint32_t i = 0; i < count; ++i) {
         bt_dataset d = datasets[i];
-        if (!d.pixels_on_device) {  // stage the host image on the device (the reference uploads the Image asset, preprocessor.rs:241-246)
+        if (!d.pixels_on_device && !p->plan_only()) {  // stage the host image on the device (the reference uploads the Image asset, preprocessor.rs:241-246)
             void* dev = nullptr;
             const size_t bytes = (size_t)d.width * (d.row_count ? d.row_count : d.height) * s.px;
             BT_CUDA(ctx, cudaMalloc(&dev, bytes));
@@ -459,8 +463,8 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
 }
 
 bt_status bt_preprocessor_run(bt_preprocessor* p, void* stream) {
-    if (!p) return BT_ERR_INVALID_ARG;
-    if (p->shard.world != 1) { p->ctx->set_error("bt_preprocessor_run: sharded runs use the phase API (split_downsample / roots / halo / stitch)"); return BT_ERR_INVALID_ARG; }
+    if (!p || p->plan_only()) return BT_ERR_INVALID_ARG;
+    if (p->shard.world != 1) { BT_SET_ERROR(p->ctx, "bt_preprocessor_run: sharded runs use the phase API (split_downsample / roots / halo / stitch)"); return BT_ERR_INVALID_ARG; }
     BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
     for (int ji; (ji = p->pending_job()) >= 0;) {
         bt_status st = p->run_split_downsample_job((uint32_t)ji, (cudaStream_t)stream);
@@ -471,91 +475,48 @@ bt_status bt_preprocessor_run(bt_preprocessor* p, void* stream) {
 }
 
 bt_status bt_preprocessor_run_split_downsample(bt_preprocessor* p, void* stream) {
-    if (!p) return BT_ERR_INVALID_ARG;
+    if (!p || p->plan_only()) return BT_ERR_INVALID_ARG;
     const int ji = p->pending_job();
-    if (ji < 0 || p->jobs[ji].split_done) { p->ctx->set_error("run_split_downsample: no pending job"); return BT_ERR_INVALID_ARG; }
+    if (ji < 0 || p->jobs[ji].split_done) { BT_SET_ERROR(p->ctx, "run_split_downsample: no pending job"); return BT_ERR_INVALID_ARG; }
     BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
     return p->run_split_downsample_job((uint32_t)ji, (cudaStream_t)stream);
 }
 
 bt_status bt_preprocessor_run_stitch(bt_preprocessor* p, void* stream) {
-    if (!p) return BT_ERR_INVALID_ARG;
+    if (!p || p->plan_only()) return BT_ERR_INVALID_ARG;
     const int ji = p->pending_job();
-    if (ji < 0 || !p->jobs[ji].split_done) { p->ctx->set_error("run_stitch: run_split_downsample has not run"); return BT_ERR_INVALID_ARG; }
+    if (ji < 0 || !p->jobs[ji].split_done) { BT_SET_ERROR(p->ctx, "run_stitch: run_split_downsample has not run"); return BT_ERR_INVALID_ARG; }
     const Job& j = p->jobs[ji];
     if (p->shard.world > 1 && ((p->roots_bytes(j) && !j.roots_done) || (p->halo_bytes(j) && !j.halo_done))) {
-        p->ctx->set_error("run_stitch: the sub-root gather / halo exchange has not been completed on this rank");
+        BT_SET_ERROR(p->ctx, "run_stitch: the sub-root gather / halo exchange has not been completed on this rank");
         return BT_ERR_INVALID_ARG;
     }
     BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
     return p->run_stitch_job((uint32_t)ji, (cudaStream_t)stream);
 }
 
-// ---- multi-GPU: sub-root gather --------------------------------------------------------------------
-bt_status bt_preprocessor_roots_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank) {
-    if (!p || !send_bytes_per_rank) return BT_ERR_INVALID_ARG;
-    const int ji = p->pending_job();
-    *send_bytes_per_rank = ji < 0 ? 0 : p->roots_bytes(p->jobs[ji]);
-    return BT_OK;
-}
-
-bt_status bt_preprocessor_roots_pack(bt_preprocessor* p, void* device_send, void* stream) {
-    if (!p) return BT_ERR_INVALID_ARG;
-    const int ji = p->pending_job();
-    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
-    const Job& j = p->jobs[ji];
-    if (p->roots_bytes(j) == 0) return BT_OK;
-    if (!device_send) return BT_ERR_INVALID_ARG;
-    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
-    Store& s = p->stores[j.attachment];
-    const uint32_t n = 1u << p->root_lod;
-    for (uint32_t x = 0; x < n; ++x) {  // my single owned row of the root level, x-major
-        const uint32_t slot = s.slot_of.at(TileKey{j.datasets[0].side, p->root_lod, x, p->shard.rank});
-        BT_CUDA(p->ctx, cudaMemcpyAsync(static_cast<unsigned char*>(device_send) + (size_t)x * s.tile_bytes, s.arena + (size_t)slot * s.tile_bytes,
-                                        s.tile_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    }
-    return BT_OK;
-}
-
-bt_status bt_preprocessor_roots_unpack_and_finish(bt_preprocessor* p, const void* device_gathered, void* stream) {
-    if (!p) return BT_ERR_INVALID_ARG;
-    const int ji = p->pending_job();
-    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
-    Job& j = p->jobs[ji];
-    if (p->roots_bytes(j) == 0) { j.roots_done = true; return BT_OK; }
-    if (!device_gathered) return BT_ERR_INVALID_ARG;
-    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
-    Store& s = p->stores[j.attachment];
-    const uint32_t n = 1u << p->root_lod;
-    const uint64_t per_rank = p->roots_bytes(j);
-    for (uint32_t r = 0; r < p->shard.world; ++r) {
-        if (r == p->shard.rank) continue;
-        for (uint32_t x = 0; x < n; ++x) {
-            const uint32_t slot = s.slot_of.at(TileKey{j.datasets[0].side, p->root_lod, x, r});
-            BT_CUDA(p->ctx, cudaMemcpyAsync(s.arena + (size_t)slot * s.tile_bytes,
-                                            static_cast<const unsigned char*>(device_gathered) + (size_t)r * per_rank + (size_t)x * s.tile_bytes,
-                                            s.tile_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-        }
-    }
-    // the levels above the shard boundary: every rank computes them (21 tiles at world = 8)
-    bt_status st = p->run_levels((uint32_t)ji, p->root_lod, j.datasets[0].lod_begin, false, (cudaStream_t)stream);
-    if (st == BT_OK) j.roots_done = true;
-    return st;
-}
-
-// ---- multi-GPU: halo strips -----------------------------------------------------------------------
-bt_status bt_preprocessor_halo_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank) {
-    if (!p || !send_bytes_per_rank) return BT_ERR_INVALID_ARG;
-    const int ji = p->pending_job();
-    *send_bytes_per_rank = ji < 0 ? 0 : p->halo_bytes(p->jobs[ji]);
-    return BT_OK;
-}
-
-static bt_status halo_copies(bt_preprocessor* p, const Job& j, unsigned char* buffer, bool pack, std::vector<RowCopy>& out) {
-    Store& s = p->stores[j.attachment];
+// ---- multi-GPU exchange: ONE host-side plan drives both the CUDA pack/unpack and the CPU (gloo) tests -----
+// kind 0 = halo strips, 1 = sub-root tiles.  pack: my tiles -> my send buffer (offsets relative to it);
+// unpack: gathered buffer [world][bytes_per_rank] -> my ghost / replica tiles (absolute offsets).
+static void exchange_plan(const bt_preprocessor* p, const Job& j, uint32_t kind, bool unpack, std::vector<bt_exchange_copy>& out) {
+    const Store& s = p->stores[j.attachment];
     const bt_dataset& d = j.datasets[0];
     const uint32_t T = s.cfg.texture_size, B = s.cfg.border_size, C = T - 2 * B;
+    const uint32_t rank = p->shard.rank, world = p->shard.world;
+    if (kind == 1) {  // one row of the root level per rank, tiles x-major
+        const uint64_t per_rank = p->roots_bytes(j);
+        if (per_rank == 0) return;
+        const uint32_t n = 1u << p->root_lod;
+        for (uint32_t r = 0; r < world; ++r) {
+            if (unpack ? r == rank : r != rank) continue;
+            for (uint32_t x = 0; x < n; ++x)
+                out.push_back(bt_exchange_copy{bt_tile{d.side, p->root_lod, x, r}, 0u, 0u, T * T, r,
+                                               (unpack ? (uint64_t)r * per_rank : 0ull) + (uint64_t)x * s.tile_bytes});
+        }
+        return;
+    }
     const uint64_t per_rank = p->halo_bytes(j);
+    if (per_rank == 0) return;
     const uint64_t row_bytes = (uint64_t)C * s.px;
     uint64_t offset = 0;
     for (uint32_t lod = std::max(d.lod_begin, p->root_lod + 1); lod < d.lod_end; ++lod) {
@@ -563,63 +524,119 @@ static bt_status halo_copies(bt_preprocessor* p, const Job& j, unsigned char* bu
         uint32_t y0, y1;
         p->owned_rows(lod, &y0, &y1);
         const uint64_t strip = (uint64_t)B * row_bytes, half = (uint64_t)n * strip;
-        for (uint32_t x = 0; x < n; ++x) {
+        for (uint32_t x = 0; x < n; ++x)
             for (uint32_t b = 0; b < B; ++b) {
-                if (pack) {
-                    // top strip: first B centre rows of my first row; bottom strip: last B centre rows of my last row
-                    const unsigned char* top = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y0}) * s.tile_bytes + ((size_t)(B + b) * T + B) * s.px;
-                    const unsigned char* bot = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y1 - 1}) * s.tile_bytes + ((size_t)(B + C - B + b) * T + B) * s.px;
-                    out.push_back(RowCopy{top, buffer + offset + (uint64_t)x * strip + (uint64_t)b * row_bytes, row_bytes});
-                    out.push_back(RowCopy{bot, buffer + offset + half + (uint64_t)x * strip + (uint64_t)b * row_bytes, row_bytes});
+                const uint64_t in_strip = (uint64_t)x * strip + (uint64_t)b * row_bytes;
+                if (!unpack) {
+                    // top strip = first B centre rows of my first row; bottom strip = last B centre rows of my last row
+                    out.push_back(bt_exchange_copy{bt_tile{d.side, lod, x, y0}, B + b, B, C, rank, offset + in_strip});
+                    out.push_back(bt_exchange_copy{bt_tile{d.side, lod, x, y1 - 1}, C + b, B, C, rank, offset + half + in_strip});
                 } else {
-                    if (y0 > 0) {  // ghost row above me <- bottom strip of rank-1
-                        unsigned char* dst = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y0 - 1}) * s.tile_bytes + ((size_t)(B + C - B + b) * T + B) * s.px;
-                        out.push_back(RowCopy{buffer + (uint64_t)(p->shard.rank - 1) * per_rank + offset + half + (uint64_t)x * strip + (uint64_t)b * row_bytes, dst, row_bytes});
-                    }
-                    if (y1 < n) {  // ghost row below me <- top strip of rank+1
-                        unsigned char* dst = s.arena + (size_t)s.slot_of.at(TileKey{d.side, lod, x, y1}) * s.tile_bytes + ((size_t)(B + b) * T + B) * s.px;
-                        out.push_back(RowCopy{buffer + (uint64_t)(p->shard.rank + 1) * per_rank + offset + (uint64_t)x * strip + (uint64_t)b * row_bytes, dst, row_bytes});
-                    }
+                    if (y0 > 0)   // ghost row above me <- bottom strip of rank-1 (its last centre rows)
+                        out.push_back(bt_exchange_copy{bt_tile{d.side, lod, x, y0 - 1}, C + b, B, C, rank - 1, (uint64_t)(rank - 1) * per_rank + offset + half + in_strip});
+                    if (y1 < n)   // ghost row below me <- top strip of rank+1 (its first centre rows)
+                        out.push_back(bt_exchange_copy{bt_tile{d.side, lod, x, y1}, B + b, B, C, rank + 1, (uint64_t)(rank + 1) * per_rank + offset + in_strip});
                 }
             }
-        }
         offset += 2 * half;
     }
-    return BT_OK;
 }
 
-bt_status bt_preprocessor_halo_pack(bt_preprocessor* p, void* device_send, void* stream) {
-    if (!p) return BT_ERR_INVALID_ARG;
-    const int ji = p->pending_job();
-    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
-    const Job& j = p->jobs[ji];
-    if (p->halo_bytes(j) == 0) return BT_OK;
-    if (!device_send) return BT_ERR_INVALID_ARG;
-    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+static bt_status run_exchange(bt_preprocessor* p, const Job& j, uint32_t kind, bool unpack, unsigned char* buffer, cudaStream_t stream) {
+    Store& s = p->stores[j.attachment];
+    std::vector<bt_exchange_copy> plan;
+    exchange_plan(p, j, kind, unpack, plan);
     std::vector<RowCopy> copies;
-    halo_copies(p, j, static_cast<unsigned char*>(device_send), true, copies);
-    bt_status st = p->upload(&p->d_copies, &p->d_copies_cap, copies, (cudaStream_t)stream);
+    copies.reserve(plan.size());
+    for (const bt_exchange_copy& c : plan) {
+        unsigned char* tile = s.arena + (size_t)s.slot_of.at(TileKey{c.tile.side, c.tile.lod, c.tile.x, c.tile.y}) * s.tile_bytes +
+                              ((size_t)c.tile_row * s.cfg.texture_size + c.tile_col) * s.px;
+        unsigned char* buf = buffer + c.buffer_offset;
+        const uint64_t bytes = (uint64_t)c.pixels * s.px;
+        copies.push_back(unpack ? RowCopy{buf, tile, bytes} : RowCopy{tile, buf, bytes});
+    }
+    BT_CUDA(p->ctx, cudaStreamSynchronize(stream));  // an earlier launch may still read d_copies
+    bt_status st = p->upload(&p->d_copies, &p->d_copies_cap, copies, stream);
     if (st != BT_OK) return st;
-    BT_CUDA(p->ctx, bt_launch_row_copy(p->d_copies, (uint32_t)copies.size(), (cudaStream_t)stream));
+    BT_CUDA(p->ctx, bt_launch_row_copy(p->d_copies, (uint32_t)copies.size(), stream));
     return BT_OK;
 }
 
-bt_status bt_preprocessor_halo_unpack(bt_preprocessor* p, const void* device_gathered, void* stream) {
+// host-side planning entry points (work on a plan-only preprocessor too)
+bt_status bt_preprocessor_plan(bt_preprocessor* p) {
     if (!p) return BT_ERR_INVALID_ARG;
     const int ji = p->pending_job();
-    if (ji < 0 || !p->jobs[ji].split_done) return BT_ERR_INVALID_ARG;
+    if (ji < 0) return BT_ERR_INVALID_ARG;
+    p->allocate_job_tiles((uint32_t)ji);
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_plan_tiles(bt_preprocessor* p, uint32_t attachment, bt_tile* tiles, uint32_t* kinds, uint32_t cap, uint32_t* count) {
+    if (!p || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    const Store& s = p->stores[attachment];
+    for (uint32_t i = 0; i < s.keys.size() && i < cap; ++i) {
+        if (tiles) tiles[i] = bt_tile{s.keys[i].side, s.keys[i].lod, s.keys[i].x, s.keys[i].y};
+        if (kinds) kinds[i] = s.kind[i];
+    }
+    if (count) *count = (uint32_t)s.keys.size();
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_plan_exchange(bt_preprocessor* p, uint32_t kind, uint32_t unpack, bt_exchange_copy* out, uint32_t cap, uint32_t* count) {
+    if (!p || kind > 1) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0) return BT_ERR_INVALID_ARG;
+    std::vector<bt_exchange_copy> plan;
+    exchange_plan(p, p->jobs[ji], kind, unpack != 0, plan);
+    if (out) for (size_t i = 0; i < plan.size() && i < cap; ++i) out[i] = plan[i];
+    if (count) *count = (uint32_t)plan.size();
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_roots_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank) {
+    if (!p || !send_bytes_per_rank) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    *send_bytes_per_rank = ji < 0 ? 0 : p->roots_bytes(p->jobs[ji]);
+    return BT_OK;
+}
+
+bt_status bt_preprocessor_halo_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank) {
+    if (!p || !send_bytes_per_rank) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    *send_bytes_per_rank = ji < 0 ? 0 : p->halo_bytes(p->jobs[ji]);
+    return BT_OK;
+}
+
+static bt_status exchange_entry(bt_preprocessor* p, uint32_t kind, bool unpack, void* buffer, void* stream) {
+    if (!p || p->plan_only()) return BT_ERR_INVALID_ARG;
+    const int ji = p->pending_job();
+    if (ji < 0 || !p->jobs[ji].split_done) { BT_SET_ERROR(p->ctx, "exchange: run_split_downsample has not run"); return BT_ERR_INVALID_ARG; }
     Job& j = p->jobs[ji];
-    if (p->halo_bytes(j) == 0) { j.halo_done = true; return BT_OK; }
-    if (!device_gathered) return BT_ERR_INVALID_ARG;
-    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
-    std::vector<RowCopy> copies;
-    halo_copies(p, j, const_cast<unsigned char*>(static_cast<const unsigned char*>(device_gathered)), false, copies);
-    BT_CUDA(p->ctx, cudaStreamSynchronize((cudaStream_t)stream));  // the pack launch may still read d_copies
-    bt_status st = p->upload(&p->d_copies, &p->d_copies_cap, copies, (cudaStream_t)stream);
-    if (st != BT_OK) return st;
-    BT_CUDA(p->ctx, bt_launch_row_copy(p->d_copies, (uint32_t)copies.size(), (cudaStream_t)stream));
-    j.halo_done = true;
+    const uint64_t bytes = kind == 1 ? p->roots_bytes(j) : p->halo_bytes(j);
+    if (bytes) {
+        if (!buffer) return BT_ERR_INVALID_ARG;
+        BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+        bt_status st = run_exchange(p, j, kind, unpack, static_cast<unsigned char*>(buffer), (cudaStream_t)stream);
+        if (st != BT_OK) return st;
+    }
+    if (unpack && kind == 1) {
+        if (bytes) {  // the levels above the shard boundary: every rank computes them (21 tiles at world = 8)
+            bt_status st = p->run_levels((uint32_t)ji, p->root_lod, j.datasets[0].lod_begin, false, (cudaStream_t)stream);
+            if (st != BT_OK) return st;
+        }
+        j.roots_done = true;
+    }
+    if (unpack && kind == 0) j.halo_done = true;
     return BT_OK;
+}
+
+bt_status bt_preprocessor_roots_pack(bt_preprocessor* p, void* device_send, void* stream) { return exchange_entry(p, 1, false, device_send, stream); }
+bt_status bt_preprocessor_roots_unpack_and_finish(bt_preprocessor* p, const void* device_gathered, void* stream) {
+    return exchange_entry(p, 1, true, const_cast<void*>(device_gathered), stream);
+}
+bt_status bt_preprocessor_halo_pack(bt_preprocessor* p, void* device_send, void* stream) { return exchange_entry(p, 0, false, device_send, stream); }
+bt_status bt_preprocessor_halo_unpack(bt_preprocessor* p, const void* device_gathered, void* stream) {
+    return exchange_entry(p, 0, true, const_cast<void*>(device_gathered), stream);
 }
 
 // ---- results --------------------------------------------------------------------------------------
@@ -658,10 +675,10 @@ bt_status bt_preprocessor_tile_device_ptr(bt_preprocessor* p, uint32_t attachmen
 
 bt_status bt_preprocessor_get_tile(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void* host_out, size_t bytes) {
     void* dev = nullptr;
-    if (!host_out) return BT_ERR_INVALID_ARG;
+    if (!host_out || !p || p->plan_only()) return BT_ERR_INVALID_ARG;
     bt_status st = bt_preprocessor_tile_device_ptr(p, attachment, tile, &dev);
     if (st != BT_OK) return st;
-    if (bytes != p->stores[attachment].tile_bytes) { p->ctx->set_error("get_tile: expected %zu bytes", p->stores[attachment].tile_bytes); return BT_ERR_INVALID_ARG; }
+    if (bytes != p->stores[attachment].tile_bytes) { BT_SET_ERROR(p->ctx, "get_tile: expected %zu bytes", p->stores[attachment].tile_bytes); return BT_ERR_INVALID_ARG; }
     BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
     BT_CUDA(p->ctx, cudaMemcpy(host_out, dev, bytes, cudaMemcpyDeviceToHost));
     return BT_OK;
@@ -678,7 +695,7 @@ static void put_varint(std::vector<unsigned char>& out, uint64_t v) {
 // Save tasks + save_tile_config (tile_atlas.rs:77-116,605-613): raw mip-0 texels per tile and the
 // bincode tile list.  Files go to <directory>/<side>_<lod>_<x>_<y>.bin and <directory>/config.tc.
 bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const char* directory) {
-    if (!p || !directory || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    if (!p || p->plan_only() || !directory || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
     bt_context* ctx = p->ctx;
     const Store& s = p->stores[attachment];
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -695,7 +712,7 @@ bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const ch
         FILE* f = std::fopen(path.c_str(), "wb");
         if (!f || std::fwrite(host.data(), 1, host.size(), f) != host.size()) {
             if (f) std::fclose(f);
-            ctx->set_error("bt_preprocessor_save: cannot write %s", path.c_str());
+            BT_SET_ERROR(ctx, "bt_preprocessor_save: cannot write %s", path.c_str());
             return BT_ERR_IO;
         }
         std::fclose(f);
@@ -705,7 +722,7 @@ bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const ch
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f || std::fwrite(tc.data(), 1, tc.size(), f) != tc.size()) {
         if (f) std::fclose(f);
-        ctx->set_error("bt_preprocessor_save: cannot write %s", path.c_str());
+        BT_SET_ERROR(ctx, "bt_preprocessor_save: cannot write %s", path.c_str());
         return BT_ERR_IO;
     }
     std::fclose(f);

@@ -372,6 +372,21 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
 bt_status bt_preprocessor_run_split_downsample(bt_preprocessor* p, void* stream);
 bt_status bt_preprocessor_run_stitch(bt_preprocessor* p, void* stream);
 bt_status bt_preprocessor_run(bt_preprocessor* p, void* stream);          /* both, world == 1 */
+/* Host-side plan of the pending job's exchange (no GPU needed: `ctx` may be NULL at creation for a
+ * plan-only preprocessor, which is how the world_size-2 gloo tests exercise this logic on CPU).
+ * One descriptor = `pixels` contiguous texels starting at (tile_row, tile_col) of `tile`
+ * <-> `buffer_offset` bytes into the send buffer (pack) or the gathered [world][bytes] buffer (unpack). */
+typedef struct bt_exchange_copy {
+    bt_tile  tile;
+    uint32_t tile_row, tile_col, pixels;
+    uint32_t src_rank;             /* rank whose data this segment carries */
+    uint64_t buffer_offset;
+} bt_exchange_copy;
+bt_status bt_preprocessor_plan(bt_preprocessor* p);   /* allocate the pending job's tile table (implicit in run_*) */
+/* every slot incl. ghosts/replicas; kinds: 0 = owned output, 1 = ghost (halo receiver), 2 = replica */
+bt_status bt_preprocessor_plan_tiles(bt_preprocessor* p, uint32_t attachment, bt_tile* tiles, uint32_t* kinds, uint32_t cap, uint32_t* count);
+/* kind: 0 = halo strips, 1 = sub-root tiles; unpack: 0 = pack plan, 1 = unpack plan */
+bt_status bt_preprocessor_plan_exchange(bt_preprocessor* p, uint32_t kind, uint32_t unpack, bt_exchange_copy* out, uint32_t cap, uint32_t* count);
 /* multi-GPU hooks: sub-root gather + halo strips (see DESIGN.md "multi-GPU") */
 bt_status bt_preprocessor_halo_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank);
 bt_status bt_preprocessor_halo_pack(bt_preprocessor* p, void* device_send, void* stream);

@@ -72,6 +72,10 @@ void     bto_pyramid_add_dataset(bto_pyramid* p, const bt_dataset* dataset);
 void     bto_pyramid_add_datasets(bto_pyramid* p, const bt_dataset* datasets, uint32_t n);
 /* runs split -> downsample -> stitch for all recorded datasets, reference task order */
 void     bto_pyramid_run(bto_pyramid* p, int threads);
+void     bto_pyramid_run_phases(bto_pyramid* p, int threads, int phases); /* bit0 split+downsample, bit1 stitch */
+void     bto_stitch_tile_raw(uint32_t format, uint32_t T, uint32_t B, const bt_tile* tile, void* data,
+                             const bt_tile nb_tiles[8], void* const nb[8]);
+void     bto_downsample_tile_raw(uint32_t format, uint32_t T, uint32_t B, void* data, void* const child[4]);
 uint32_t bto_pyramid_tile_count(const bto_pyramid* p);
 uint32_t bto_pyramid_list_tiles(const bto_pyramid* p, bt_tile* out, uint32_t cap);
 /* returns NULL when the tile does not exist */

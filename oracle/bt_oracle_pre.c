@@ -387,7 +387,28 @@ static task* collect(bto_pyramid* p, const bt_dataset* d, uint32_t lod, uint32_t
     return t;
 }
 
-void bto_pyramid_run(bto_pyramid* p, int threads) {
+static void pyramid_run_phases(bto_pyramid* p, int threads, int phases);
+void bto_pyramid_run(bto_pyramid* p, int threads) { pyramid_run_phases(p, threads, 3); }
+/* phases: bit 0 = split + downsample, bit 1 = stitch (tests of the sharded exchange stop after bit 0) */
+void bto_pyramid_run_phases(bto_pyramid* p, int threads, int phases) { pyramid_run_phases(p, threads, phases); }
+
+/* raw per-tile entry points (no pyramid store): used by the world_size-2 gloo test to stitch / downsample
+ * rank-local tiles whose neighbours come from halo exchanges */
+void bto_stitch_tile_raw(uint32_t format, uint32_t T, uint32_t B, const bt_tile* tile, void* data,
+                         const bt_tile nb_tiles[8], void* const nb[8]) {
+    bto_pyramid tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    tmp.format = format; tmp.T = T; tmp.B = B; tmp.C = T - 2 * B; tmp.pixel_size = (format == BT_FORMAT_R16) ? 2 : 4;
+    stitch_tile(&tmp, tile, data, nb_tiles, nb);
+}
+void bto_downsample_tile_raw(uint32_t format, uint32_t T, uint32_t B, void* data, void* const child[4]) {
+    bto_pyramid tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    tmp.format = format; tmp.T = T; tmp.B = B; tmp.C = T - 2 * B; tmp.pixel_size = (format == BT_FORMAT_R16) ? 2 : 4;
+    downsample_tile(&tmp, data, child);
+}
+
+static void pyramid_run_phases(bto_pyramid* p, int threads, int phases) {
     (void)threads;
 #ifdef _OPENMP
     if (threads <= 0) threads = omp_get_max_threads();
@@ -403,7 +424,7 @@ void bto_pyramid_run(bto_pyramid* p, int threads) {
             for (uint32_t lod = d->lod_begin; lod < d->lod_end; ++lod) { size_t n; free(collect(p, d, lod, ji, &n)); }
         }
         /* split_and_downsample — preprocessor.rs:234-269 */
-        for (uint32_t di = 0; di < j->count; ++di) {
+        for (uint32_t di = 0; (phases & 1) && di < j->count; ++di) {
             const bt_dataset* d = &j->datasets[di];
             if (d->lod_end <= d->lod_begin) continue;
             size_t n; task* t = collect(p, d, d->lod_end - 1u, ji, &n);
@@ -432,7 +453,7 @@ void bto_pyramid_run(bto_pyramid* p, int threads) {
             if (j->datasets[di].lod_begin < lod_begin) lod_begin = j->datasets[di].lod_begin;
             if (j->datasets[di].lod_end > lod_end) lod_end = j->datasets[di].lod_end;
         }
-        for (uint32_t lod = lod_begin; lod < lod_end; ++lod) for (uint32_t di = 0; di < j->count; ++di) {
+        for (uint32_t lod = lod_begin; (phases & 2) && lod < lod_end; ++lod) for (uint32_t di = 0; di < j->count; ++di) {
             const bt_dataset* d = &j->datasets[di];
             if (lod < d->lod_begin || lod >= d->lod_end) continue;
             size_t n; task* t = collect(p, d, lod, ji, &n);

@@ -61,6 +61,9 @@ def lib() -> C.CDLL:
         "bto_pyramid_add_dataset": (None, [vp, P(F.Dataset)]),
         "bto_pyramid_add_datasets": (None, [vp, P(F.Dataset), u32]),
         "bto_pyramid_run": (None, [vp, i32]),
+        "bto_pyramid_run_phases": (None, [vp, i32, i32]),
+        "bto_stitch_tile_raw": (None, [u32, u32, u32, P(F.Tile), vp, P(F.Tile), P(vp)]),
+        "bto_downsample_tile_raw": (None, [u32, u32, u32, vp, P(vp)]),
         "bto_pyramid_tile_count": (u32, [vp]),
         "bto_pyramid_list_tiles": (u32, [vp, P(F.Tile), u32]),
         "bto_pyramid_tile": (vp, [vp, P(F.Tile)]),
@@ -204,8 +207,8 @@ class Pyramid:
         self._keep.append((arr, datasets))
         lib().bto_pyramid_add_datasets(self._p, arr, len(datasets))
 
-    def run(self, threads: int = 0) -> None:
-        lib().bto_pyramid_run(self._p, threads)
+    def run(self, threads: int = 0, phases: int = 3) -> None:
+        lib().bto_pyramid_run_phases(self._p, threads, phases)
 
     def tiles(self) -> np.ndarray:
         n = lib().bto_pyramid_tile_count(self._p)
