@@ -6,14 +6,14 @@
 // blended as src/shaders/render/fragment.wgsl:99-107).
 //
 // Design (B200):
-//   * persistent CTAs (one per SM) stride over work items = (tile, block of CB column strips)
+//   * persistent CTAs (two per SM) stride over work items = (tile, block of CB column strips)
 //   * the reference's triangle-strip index stream visits every grid vertex ~2x (8448 strip
 //     vertices for 65x65 = 4225 unique ones at grid 64, compute_tile_uv functions.wgsl:64-71);
 //     each unique vertex is computed ONCE and scattered to its 2-3 strip positions in a
 //     shared-memory image of the output block — bit-identical to recomputation because the
 //     vertex is a pure function of (tile, column, row)
 //   * the image is written to HBM with TMA 1-D bulk stores (cp.async.bulk.global.shared::cta,
-//     one per strip), double-buffered so the stores of item i overlap the compute of item i+1;
+//     one per strip); while one CTA's stores drain, the SM's other CTA computes its next item;
 //     HBM sees only full-line, fully coalesced writes of the 40-B interleaved records
 //   * the uniform block is staged into shared memory with one TMA bulk load + mbarrier
 //   * height texels are gathered with read-only (ld.global.nc) 16-bit loads; lanes walk along
@@ -24,7 +24,9 @@
 
 namespace btd {
 
-constexpr int GEN_THREADS = 576;       // 18 warps: 2 rounds cover the 17x65 = 1105 vertices of a g=64 work item
+constexpr int GEN_THREADS = 384;       // 12 warps: 3 rounds cover the 17x65 = 1105 vertices of a g=64 work item (96 % lane use)
+constexpr int GEN_CTAS_PER_SM = 2;     // two resident CTAs: one computes while the other waits at a barrier / on its bulk store
+constexpr int GEN_BUFFERS = 1;         // output images per CTA (the second CTA of the SM provides the overlap)
 constexpr uint32_t STRIP_PAD = 16;     // bytes between strips in the smem image (bank spreading; keeps 16-B alignment)
 
 struct GenParams {
@@ -127,17 +129,72 @@ __device__ __forceinline__ float sample_height_uv(const FrameConsts& F, const ui
     return mix(F.min_h, F.max_h, s);
 }
 
-// sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch)
+// The five taps of sample_height + sample_normal (centre, left, up, right, down) land in a "plus" of at most
+// 12 distinct texels: rows iy..iy+1 x columns ix-1..ix+2 and rows iy-1..iy+2 x columns ix..ix+1.  This routine
+// loads and decodes each texel once and evaluates every tap with exactly the per-tap arithmetic of sample_r16
+// (same operands, same order), so it is bit-identical to five independent taps.  `v + 0.0f == v` and
+// `u + 0.0f == u` hold bit for bit because attachment_uv yields values >= +0.
+struct FiveTaps { float centre, left, up, right, down; bool ok; };
+
+__device__ __forceinline__ float lerp2(float v00, float v01, float v10, float v11, float rx, float ry) {
+    const float a = v00 + (v01 - v00) * ry;
+    const float b = v10 + (v11 - v10) * ry;
+    return a + (b - a) * rx;
+}
+
+__device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
+    const float o = F.normal_offset;
+    const float pxc = u * F.Tf - 0.5f, pyc = v * F.Tf - 0.5f;
+    const float pxl = (u + -o) * F.Tf - 0.5f, pxr = (u + o) * F.Tf - 0.5f;
+    const float pyu = (v + -o) * F.Tf - 0.5f, pyd = (v + o) * F.Tf - 0.5f;
+    const float fxc = floorf(pxc), fyc = floorf(pyc), fxl = floorf(pxl), fxr = floorf(pxr), fyu = floorf(pyu), fyd = floorf(pyd);
+    const float rxc = pxc - fxc, ryc = pyc - fyc, rxl = pxl - fxl, rxr = pxr - fxr, ryu = pyu - fyu, ryd = pyd - fyd;
+    const int ix = (int)fxc, iy = (int)fyc;
+    const uint32_t jl = (uint32_t)((int)fxl - ix + 1), jr = (uint32_t)((int)fxr - ix);  // expected jl in {0,1}, jr in {0,1}
+    const uint32_t ju = (uint32_t)((int)fyu - iy + 1), jd = (uint32_t)((int)fyd - iy);
+    FiveTaps out;
+    out.ok = (jl | jr | ju | jd) <= 1u;   // offsets of 0.5/size texture units = ~0.5 texel: always true; guarded anyway
+    const int c0 = min(max(ix - 1, 0), F.Tm1), c1 = min(max(ix, 0), F.Tm1), c2 = min(max(ix + 1, 0), F.Tm1), c3 = min(max(ix + 2, 0), F.Tm1);
+    const uint16_t* q0 = layer + min(max(iy - 1, 0), F.Tm1) * F.T;
+    const uint16_t* q1 = layer + min(max(iy, 0), F.Tm1) * F.T;
+    const uint16_t* q2 = layer + min(max(iy + 1, 0), F.Tm1) * F.T;
+    const uint16_t* q3 = layer + min(max(iy + 2, 0), F.Tm1) * F.T;
+    // texel t<row><col>
+    const float t10 = unorm16_to_float(__ldg(q1 + c0)), t11 = unorm16_to_float(__ldg(q1 + c1));
+    const float t12 = unorm16_to_float(__ldg(q1 + c2)), t13 = unorm16_to_float(__ldg(q1 + c3));
+    const float t20 = unorm16_to_float(__ldg(q2 + c0)), t21 = unorm16_to_float(__ldg(q2 + c1));
+    const float t22 = unorm16_to_float(__ldg(q2 + c2)), t23 = unorm16_to_float(__ldg(q2 + c3));
+    const float t01 = unorm16_to_float(__ldg(q0 + c1)), t02 = unorm16_to_float(__ldg(q0 + c2));
+    const float t31 = unorm16_to_float(__ldg(q3 + c1)), t32 = unorm16_to_float(__ldg(q3 + c2));
+    out.centre = lerp2(t11, t21, t12, t22, rxc, ryc);
+    // left: columns (ix-1+jl, ix+jl); right: columns (ix+jr, ix+1+jr); rows iy, iy+1 (py == centre's)
+    out.left = jl ? lerp2(t11, t21, t12, t22, rxl, ryc) : lerp2(t10, t20, t11, t21, rxl, ryc);
+    out.right = jr ? lerp2(t12, t22, t13, t23, rxr, ryc) : lerp2(t11, t21, t12, t22, rxr, ryc);
+    // up: rows (iy-1+ju, iy+ju); down: rows (iy+jd, iy+1+jd); columns ix, ix+1 (px == centre's)
+    out.up = ju ? lerp2(t11, t21, t12, t22, rxc, ryu) : lerp2(t01, t11, t02, t12, rxc, ryu);
+    out.down = jd ? lerp2(t21, t31, t22, t32, rxc, ryd) : lerp2(t11, t21, t12, t22, rxc, ryd);
+    return out;
+}
+
+// sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch); `pre` carries the shared taps
 template <bool SPHERICAL>
 __device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16_t* __restrict__ layer, const AtlasTile& t,
-                                              float u, float v, Vec3 vertex_normal) {
+                                              float u, float v, Vec3 vertex_normal, const FiveTaps* pre = nullptr) {
     const float pixels_per_side = F.size0 * tile_count(t.c.lod);
-    const float distance_between_samples = F.side_length / pixels_per_side;
+    const float distance_between_samples = div_rn(F.side_length, pixels_per_side);
     const float offset = F.normal_offset;
-    const float left = sample_height_uv(F, layer, u + -offset, v + 0.0f);
-    const float up = sample_height_uv(F, layer, u + 0.0f, v + -offset);
-    const float right = sample_height_uv(F, layer, u + offset, v + 0.0f);
-    const float down = sample_height_uv(F, layer, u + 0.0f, v + offset);
+    float left, up, right, down;
+    if (pre && pre->ok) {
+        left = mix(F.min_h, F.max_h, pre->left);
+        up = mix(F.min_h, F.max_h, pre->up);
+        right = mix(F.min_h, F.max_h, pre->right);
+        down = mix(F.min_h, F.max_h, pre->down);
+    } else {
+        left = sample_height_uv(F, layer, u + -offset, v + 0.0f);
+        up = sample_height_uv(F, layer, u + 0.0f, v + -offset);
+        right = sample_height_uv(F, layer, u + offset, v + 0.0f);
+        down = sample_height_uv(F, layer, u + 0.0f, v + offset);
+    }
     const Vec3 sn = normalize3(Vec3{left - right, down - up, distance_between_samples});
     Vec3 r;
     if (SPHERICAL) {
@@ -184,10 +241,10 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     // compute_morph — functions.wgsl:35-49
     Coord c = c0;
     if (flags & BT_FLAG_MORPH) {
-        const float target_lod = log2_det(2.0f * vc.morph_distance / d);
-        const float ratio = (c0.lod == 0u) ? 0.0f : inverse_mix((float)c0.lod + vc.morph_range, (float)c0.lod, target_lod);
-        const float even_u = (float)(f2u(c0.u * g) & ~1u) / g;
-        const float even_v = (float)(f2u(c0.v * g) & ~1u) / g;
+        const float target_lod = log2_det(div_rn(2.0f * vc.morph_distance, d));
+        const float ratio = (c0.lod == 0u) ? 0.0f : inverse_mix_rn((float)c0.lod + vc.morph_range, (float)c0.lod, target_lod);
+        const float even_u = F.g_pow2 ? (float)(f2u(c0.u * g) & ~1u) * F.inv_g : (float)(f2u(c0.u * g) & ~1u) / g;
+        const float even_v = F.g_pow2 ? (float)(f2u(c0.v * g) & ~1u) * F.inv_g : (float)(f2u(c0.v * g) & ~1u) / g;
         c.u = mix(c0.u, even_u, ratio);
         c.v = mix(c0.v, even_v, ratio);
     }
@@ -201,27 +258,37 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
         if (SPHERICAL) wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
     }
     // compute_blend — functions.wgsl:51-62
-    const float target_lod = fminf(log2_det(vc.blend_distance / d), F.lod_cap);
+    const float target_lod = fminf(log2_det(div_rn(vc.blend_distance, d)), F.lod_cap);
     const uint32_t blend_lod = f2u(target_lod);
     float blend_ratio = 0.0f;
     if ((flags & BT_FLAG_BLEND) && blend_lod != 0u)
-        blend_ratio = inverse_mix((float)blend_lod + vc.blend_range, (float)blend_lod, target_lod);
+        blend_ratio = inverse_mix_rn((float)blend_lod + vc.blend_range, (float)blend_lod, target_lod);
 
     const int tile_texels = F.T * F.T;
+    const bool normals = (flags & BT_FLAG_NORMALS) != 0u;
     const AtlasTile ta = lookup_tile(U, tile_tree, c, blend_lod);
     const uint16_t* layer_a = atlas + (size_t)ta.index * tile_texels;
     const float ua = ta.c.u * F.a_scale + F.a_offset, va = ta.c.v * F.a_scale + F.a_offset;  // attachment_uv
-    float height = sample_height_uv(F, layer_a, ua, va);
+    float height;
     Vec3 nrm = wn;
-    if (flags & BT_FLAG_NORMALS) nrm = sample_normal<SPHERICAL>(F, layer_a, ta, ua, va, wn);
+    if (normals) {
+        const FiveTaps taps = sample_five(F, layer_a, ua, va);
+        height = mix(F.min_h, F.max_h, taps.centre);
+        nrm = sample_normal<SPHERICAL>(F, layer_a, ta, ua, va, wn, &taps);
+    } else {
+        height = sample_height_uv(F, layer_a, ua, va);
+    }
     if (blend_ratio > 0.0f) {
         const AtlasTile tb = lookup_tile(U, tile_tree, c, blend_lod - 1u);
         const uint16_t* layer_b = atlas + (size_t)tb.index * tile_texels;
         const float ub = tb.c.u * F.a_scale + F.a_offset, vb = tb.c.v * F.a_scale + F.a_offset;
-        height = mix(height, sample_height_uv(F, layer_b, ub, vb), blend_ratio);
-        if (flags & BT_FLAG_NORMALS) {  // fragment.wgsl:103-107
-            const Vec3 n2 = sample_normal<SPHERICAL>(F, layer_b, tb, ub, vb, wn);
+        if (normals) {  // fragment.wgsl:103-107
+            const FiveTaps taps = sample_five(F, layer_b, ub, vb);
+            height = mix(height, mix(F.min_h, F.max_h, taps.centre), blend_ratio);
+            const Vec3 n2 = sample_normal<SPHERICAL>(F, layer_b, tb, ub, vb, wn, &taps);
             nrm = Vec3{mix(nrm.x, n2.x, blend_ratio), mix(nrm.y, n2.y, blend_ratio), mix(nrm.z, n2.z, blend_ratio)};
+        } else {
+            height = mix(height, sample_height_uv(F, layer_b, ub, vb), blend_ratio);
         }
     }
     Record r;  // vertex_output — vertex.wgsl:73-83
@@ -246,7 +313,7 @@ struct GenSmemHeader {
 };
 
 template <bool SPHERICAL>
-__global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenParams P) {
+__global__ void __launch_bounds__(GEN_THREADS, GEN_CTAS_PER_SM) gen_vertices_kernel(const GenParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     GenSmemHeader& H = *reinterpret_cast<GenSmemHeader*>(smem_raw);
     unsigned char* images = smem_raw + ((sizeof(GenSmemHeader) + 127) & ~size_t(127));
@@ -290,10 +357,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
         const uint32_t n_strips = min(P.strips_per_item, g - c0);
         const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
-        unsigned char* image = images + (size_t)(it & 1u) * P.image_bytes;
+        unsigned char* image = images + (size_t)(it % GEN_BUFFERS) * P.image_bytes;
 
-        // the bulk stores issued from this buffer two items ago must have finished READING it
-        if (tid == 0) bulk_wait_read<1>();
+        // the bulk stores last issued from this buffer must have finished READING it
+        if (tid == 0) bulk_wait_read<GEN_BUFFERS - 1>();
         __syncthreads();
 
         const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
@@ -337,11 +404,11 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     if (grid_size == 0) return cudaErrorInvalidValue;
     const uint32_t strip_stride = 2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex) + STRIP_PAD;
     const size_t header = (sizeof(GenSmemHeader) + 127) & ~size_t(127);
-    const size_t budget = 200 * 1024 - header;  // leave L1 some room out of the 227 KiB
-    uint32_t cb = (uint32_t)(budget / (2ull * strip_stride));
+    const size_t budget = (200 * 1024) / GEN_CTAS_PER_SM - header - 1024;  // per CTA; leaves L1 some room out of the 227 KiB
+    uint32_t cb = (uint32_t)(budget / ((size_t)GEN_BUFFERS * strip_stride));
     if (cb > 16u) cb = 16u;
     if (cb > grid_size) cb = grid_size;
-    if (cb == 0) return cudaErrorInvalidValue;  // grid_size too large for a double-buffered strip
+    if (cb == 0) return cudaErrorInvalidValue;  // grid_size too large for one strip per CTA
     GenParams P;
     P.uniforms = static_cast<const ViewUniforms*>(uniforms);
     P.tiles = final_tiles;
@@ -356,11 +423,11 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     P.strips_per_item = cb;
     P.items_per_tile = (grid_size + cb - 1u) / cb;
     P.image_bytes = cb * strip_stride;
-    const size_t smem = header + 2ull * P.image_bytes;
+    const size_t smem = header + (size_t)GEN_BUFFERS * P.image_bytes;
     cudaError_t e = cudaFuncSetAttribute(spherical ? gen_vertices_kernel<true> : gen_vertices_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = sm_count > 0 ? sm_count : 148;
+    const int grid = (sm_count > 0 ? sm_count : 148) * GEN_CTAS_PER_SM;
     if (spherical) gen_vertices_kernel<true><<<grid, GEN_THREADS, smem, stream>>>(P);
     else gen_vertices_kernel<false><<<grid, GEN_THREADS, smem, stream>>>(P);
     return cudaGetLastError();

@@ -448,7 +448,15 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
         if (unorm16_to_float(i) != (float)i / m16) atomicAdd(&mismatches[0], 1u);
         if (i < 256u && unorm8_to_float(i) != (float)i / m8) atomicAdd(&mismatches[1], 1u);
     }
-    if (i < n) log2_out[i] = log2_det(x[i]);
+    if (i < n) {
+        log2_out[i] = log2_det(x[i]);
+        // div_rn (no range check / slow path) against the IEEE division, on pairs drawn from x
+        volatile float a = x[i], b = x[(uint32_t)(((uint64_t)i * 7919u + 13u) % n)];
+        const float q = a / b;
+        const bool ordinary = fabsf(b) >= 1.17549435e-38f && fabsf(b) < 1e37f && fabsf(a) < 1e37f &&
+                              (q == 0.0f ? a == 0.0f : (fabsf(q) >= 1.17549435e-38f && fabsf(q) < 1e37f));
+        if (ordinary && div_rn(a, b) != q) atomicAdd(&mismatches[2], 1u);
+    }
 }
 }  // namespace btd
 
