@@ -318,7 +318,7 @@ def run_b200(args):
             "frame": frame_state,
             "preprocess": preprocess,
         }
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -513,11 +513,23 @@ def run_reference(args):
                        "source": f"{args.source}^2", "lods": args.lods, "attachments": "height R16 only"},
         "setup_s": setup_s,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) went to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # anything a library prints to fd 1 from here on lands on stderr
     if args.impl == "reference":
         run_reference(args)
     else:
