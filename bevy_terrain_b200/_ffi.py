@@ -197,6 +197,7 @@ def _declare(lib: C.CDLL) -> None:
         "bt_preprocessor_create": (i32, [vp, u32, P(AttachmentConfig), u32, u32, Shard, P(vp)]),
         "bt_preprocessor_destroy": (None, [vp]),
         "bt_preprocessor_add_datasets": (i32, [vp, P(Dataset), u32]),
+        "bt_preprocessor_reserve": (i32, [vp, vp]),
         "bt_preprocessor_run_split_downsample": (i32, [vp, vp]),
         "bt_preprocessor_run_stitch": (i32, [vp, vp]),
         "bt_preprocessor_run": (i32, [vp, vp]),

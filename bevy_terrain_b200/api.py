@@ -399,6 +399,11 @@ class Preprocessor:
         self.ctx.check(self.ctx.lib.bt_preprocessor_add_datasets(self._h, arr, 6))
         return self
 
+    def reserve(self, stream: int = 0) -> "Preprocessor":
+        """allocate the device pyramid store up front (keeps cudaMalloc out of run)"""
+        self.ctx.check(self.ctx.lib.bt_preprocessor_reserve(self._h, C.c_void_p(stream)))
+        return self
+
     def run(self, stream: int = 0) -> "Preprocessor":
         self.ctx.check(self.ctx.lib.bt_preprocessor_run(self._h, C.c_void_p(stream)))
         return self

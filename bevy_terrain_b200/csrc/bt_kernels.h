@@ -24,13 +24,16 @@ struct GenStatus {
 
 // one preprocess task = one output tile of one phase (SplitData / DownsampleData / StitchData,
 // src/preprocess/gpu_preprocessor.rs:31-50); slots index the device pyramid store
+constexpr uint32_t kTaskFresh = 1u;
+
 struct PyramidTask {
     bt_tile  tile;
     uint32_t slot;          // output tile slot
     uint32_t dataset;       // split: index into the dataset table
     uint32_t dep[8];        // downsample: 4 child slots; stitch: 8 neighbour slots; 0xFFFFFFFF = invalid
     uint32_t dep_side[8];   // stitch: neighbour side (for project_to_side)
-    uint32_t _pad[2];
+    uint32_t flags;         // kTaskFresh: the output slot has never been written (reads as the zeroed atlas)
+    uint32_t _pad;
 };
 
 // one contiguous row copy of the halo / root exchange (multi-GPU preprocess)

@@ -54,8 +54,9 @@ struct Store {  // one attachment's device-resident tile pyramid
     std::vector<uint32_t> exists_from_job;
     std::vector<uint8_t> kind;
     unsigned char* arena = nullptr;
+    std::vector<uint8_t> written;  // slot has been produced by a kernel (else its content is "the zero-initialised atlas texture")
     uint32_t arena_slots = 0;    // slots the arena can hold
-    uint32_t zeroed_slots = 0;   // slots already zero-initialised
+    uint32_t cleared_slots = 0;  // slots whose first-use handling (ghost zeroing) has been done
 };
 
 struct Job {
@@ -149,6 +150,7 @@ struct bt_preprocessor {
         s.keys.push_back(k);
         s.exists_from_job.push_back(job);
         s.kind.push_back(kind_);
+        s.written.push_back(0);
         return slot;
     }
     // TileAtlasState::get_tile — tile_atlas.rs:369-381, evaluated at queue-build time of `job`
@@ -170,17 +172,20 @@ struct bt_preprocessor {
                 return BT_ERR_OUT_OF_MEMORY;
             }
             if (s.arena) {
-                BT_CUDA(ctx, cudaMemcpyAsync(bigger, s.arena, (size_t)s.zeroed_slots * s.tile_bytes, cudaMemcpyDeviceToDevice, stream));
+                BT_CUDA(ctx, cudaMemcpyAsync(bigger, s.arena, (size_t)s.arena_slots * s.tile_bytes, cudaMemcpyDeviceToDevice, stream));
                 BT_CUDA(ctx, cudaStreamSynchronize(stream));
                 BT_CUDA(ctx, cudaFree(s.arena));
             }
             s.arena = bigger;
             s.arena_slots = need;
         }
-        if (need > s.zeroed_slots) {  // atlas textures start zeroed (wgpu); split falls through to that content
-            BT_CUDA(ctx, cudaMemsetAsync(s.arena + (size_t)s.zeroed_slots * s.tile_bytes, 0, (size_t)(need - s.zeroed_slots) * s.tile_bytes, stream));
-            s.zeroed_slots = need;
-        }
+        // The reference's atlas textures start zeroed (wgpu) and split falls through to that content.  Instead of
+        // clearing the whole store (32 GiB for config 5), split tasks on never-written slots carry a "fresh" flag and
+        // substitute zero for the read; downsample overwrites every texel; only ghost tiles (written strip-wise by
+        // the halo unpack) are cleared here.
+        for (uint32_t i = s.cleared_slots; i < need; ++i)
+            if (s.kind[i] == kGhost) BT_CUDA(ctx, cudaMemsetAsync(s.arena + (size_t)i * s.tile_bytes, 0, s.tile_bytes, stream));
+        s.cleared_slots = need;
         return BT_OK;
     }
 
@@ -239,6 +244,7 @@ struct bt_preprocessor {
                 t.tile = bt_tile{d.side, lod, x, y};
                 t.slot = s.slot_of.at(TileKey{d.side, lod, x, y});
                 t.dataset = di;
+                t.flags = s.written[t.slot] ? 0u : btd::kTaskFresh;
                 out.push_back(t);
             }
     }
@@ -267,6 +273,7 @@ struct bt_preprocessor {
             st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
             if (st != BT_OK) return st;
             BT_CUDA(ctx, bt_launch_split(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), d_datasets, stream));
+            for (const PyramidTask& t : tasks) s.written[t.slot] = 1;
         }
         for (int32_t lod = (int32_t)lod_hi_exclusive - 1; lod >= (int32_t)lod_lo; --lod) {
             tasks.clear();
@@ -284,6 +291,7 @@ struct bt_preprocessor {
             bt_status st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
             if (st != BT_OK) return st;
             BT_CUDA(ctx, bt_launch_downsample(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), stream));
+            for (const PyramidTask& t : tasks) s.written[t.slot] = 1;
         }
         return BT_OK;
     }
@@ -459,6 +467,28 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
         j.datasets.push_back(d);
     }
     p->jobs.push_back(std::move(j));
+    return BT_OK;
+}
+
+// Allocates (and first-use-initialises) the device pyramid store for every pending job, so that a subsequent
+// run contains no cudaMalloc.  Optional: run_* do the same lazily.
+bt_status bt_preprocessor_reserve(bt_preprocessor* p, void* stream) {
+    if (!p || p->plan_only()) return BT_ERR_INVALID_ARG;
+    BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    for (size_t ji = 0; ji < p->jobs.size(); ++ji) if (!p->jobs[ji].stitched) p->allocate_job_tiles((uint32_t)ji);
+    for (Store& s : p->stores) {
+        bt_status st = p->ensure_arena(s, (cudaStream_t)stream);
+        if (st != BT_OK) return st;
+    }
+    // task / dataset scratch sized for the largest level
+    size_t most = 0;
+    for (const Store& s : p->stores) most = std::max(most, s.keys.size());
+    if (most > p->d_tasks_cap) {
+        if (p->d_tasks) BT_CUDA(p->ctx, cudaFree(p->d_tasks));
+        p->d_tasks = nullptr;
+        BT_CUDA(p->ctx, cudaMalloc((void**)&p->d_tasks, most * sizeof(PyramidTask)));
+        p->d_tasks_cap = most;
+    }
     return BT_OK;
 }
 
@@ -668,7 +698,7 @@ bt_status bt_preprocessor_tile_device_ptr(bt_preprocessor* p, uint32_t attachmen
     if (!p || !tile || !out || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
     const Store& s = p->stores[attachment];
     auto it = s.slot_of.find(TileKey{tile->side, tile->lod, tile->x, tile->y});
-    if (it == s.slot_of.end() || !s.arena || it->second >= s.zeroed_slots) return BT_ERR_NOT_FOUND;
+    if (it == s.slot_of.end() || !s.arena || it->second >= s.arena_slots) return BT_ERR_NOT_FOUND;
     *out = s.arena + (size_t)it->second * s.tile_bytes;
     return BT_OK;
 }

@@ -63,6 +63,7 @@ struct FrameConsts {
     float size0;               // attachments[0].size
     Vec3  planar_normal;       // normal_local_to_world for the planar model: a constant (functions.wgsl:14-24)
     float lod_cap;             // f32(lod_count) - 0.00001 (functions.wgsl:52)
+    uint32_t tree_size, tree_mask, lod_count;  // tree_mask = tree_size - 1 when tree_size is a power of two, else 0
 };
 
 template <bool SPHERICAL>
@@ -84,6 +85,9 @@ __device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) 
     F.side_length = SPHERICAL ? (float)(3.14159265359 / 4.0) * U.terrain_config.scale : U.terrain_config.scale;
     F.planar_normal = normal_local_to_world<false>(U.mesh, Vec3{0.0f, 0.0f, 0.0f});
     F.lod_cap = (float)U.terrain_config.lod_count - 0.00001f;
+    F.tree_size = U.view_config.tree_size;
+    F.tree_mask = (F.tree_size & (F.tree_size - 1u)) == 0u ? F.tree_size - 1u : 0u;
+    F.lod_count = U.terrain_config.lod_count;
     return F;
 }
 
@@ -113,11 +117,13 @@ struct AtlasTile {
 };
 
 // lookup_tile (default variant) — functions.wgsl:232-246,198-206
-__device__ __forceinline__ AtlasTile lookup_tile(const ViewUniforms& U, const bt_tile_tree_entry* __restrict__ tile_tree,
+__device__ __forceinline__ AtlasTile lookup_tile(const FrameConsts& F, const bt_tile_tree_entry* __restrict__ tile_tree,
                                                  Coord c, uint32_t lod) {
     change_lod(c, lod);
-    const uint32_t ts = U.view_config.tree_size;
-    const uint32_t idx = ((c.side * U.terrain_config.lod_count + c.lod) * ts + c.x % ts) * ts + c.y % ts;
+    const uint32_t ts = F.tree_size;
+    const uint32_t tx = F.tree_mask ? (c.x & F.tree_mask) : c.x % ts;   // xy % tree_size (functions.wgsl:199)
+    const uint32_t ty = F.tree_mask ? (c.y & F.tree_mask) : c.y % ts;
+    const uint32_t idx = ((c.side * F.lod_count + c.lod) * ts + tx) * ts + ty;
     const uint2 e = __ldg(reinterpret_cast<const uint2*>(tile_tree) + idx);
     change_lod(c, e.y);
     return AtlasTile{e.x, c};
@@ -266,7 +272,7 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
 
     const int tile_texels = F.T * F.T;
     const bool normals = (flags & BT_FLAG_NORMALS) != 0u;
-    const AtlasTile ta = lookup_tile(U, tile_tree, c, blend_lod);
+    const AtlasTile ta = lookup_tile(F, tile_tree, c, blend_lod);
     const uint16_t* layer_a = atlas + (size_t)ta.index * tile_texels;
     const float ua = ta.c.u * F.a_scale + F.a_offset, va = ta.c.v * F.a_scale + F.a_offset;  // attachment_uv
     float height;
@@ -279,7 +285,7 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
         height = sample_height_uv(F, layer_a, ua, va);
     }
     if (blend_ratio > 0.0f) {
-        const AtlasTile tb = lookup_tile(U, tile_tree, c, blend_lod - 1u);
+        const AtlasTile tb = lookup_tile(F, tile_tree, c, blend_lod - 1u);
         const uint16_t* layer_b = atlas + (size_t)tb.index * tile_texels;
         const float ub = tb.c.u * F.a_scale + F.a_offset, vb = tb.c.v * F.a_scale + F.a_offset;
         if (normals) {  // fragment.wgsl:103-107
@@ -366,8 +372,9 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_CTAS_PER_SM) gen_vertices_ker
         const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
         const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
         const uint32_t n_verts = n_cols * n_rows;
+        const uint32_t magic = 0xFFFFFFFFu / n_cols + 1u;   // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32
         for (uint32_t i = tid; i < n_verts; i += GEN_THREADS) {
-            const uint32_t gy = i / n_cols, lx = i - gy * n_cols;  // lanes walk along texel rows
+            const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
             const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
             // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
             if (lx < n_strips) {

@@ -87,19 +87,30 @@ __device__ __forceinline__ Px4 source_texel(const DatasetDevice& d, int x, int y
     return F::decode(__ldg(reinterpret_cast<const typename F::texel*>(d.pixels) + (size_t)ry * d.width + (size_t)x));
 }
 
+// Each thread owns a strip of N pixels x SPLIT_ROWS rows.  Per pixel column the x terms (tile coordinate,
+// source coordinate, bilinear weight, clamped texel columns) are computed once; per source row the horizontal
+// lerp  h(row) = mix(texel(row, x0), texel(row, x1), rx)  and its validity bit are cached in registers, so at the
+// native 1:1 ratio every output row fetches ONE new source row (2 texels per pixel instead of 4) and vertically
+// adjacent outputs share h(row).  value = mix(h(y0), h(y1), ry) is exactly the shader's
+// mix(mix(v00,v10,rx), mix(v01,v11,rx), ry): same operands, same order, bit-identical.
+constexpr int SPLIT_ROWS = 8;
+constexpr int SPLIT_CH_R16 = 1, SPLIT_CH_RGBA8 = 4;
+
 template <int FORMAT>
 __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks,
                                                             const DatasetDevice* __restrict__ datasets) {
     using F = Fmt<FORMAT>;
     using texel = typename F::texel;
     constexpr int N = F::PX_PER_THREAD;
+    constexpr int CH = FORMAT == BT_FORMAT_R16 ? SPLIT_CH_R16 : SPLIT_CH_RGBA8;  // R16 packs only .x (preprocessing.wgsl:85-88)
     const PyramidTask& task = tasks[blockIdx.y];
     const DatasetDevice d = datasets[task.dataset];
     const uint32_t packets_per_row = (L.T + N - 1) / N;
+    const uint32_t row_groups = (L.T + SPLIT_ROWS - 1) / SPLIT_ROWS;
     const uint32_t pid = blockIdx.x * PYR_THREADS + threadIdx.x;
-    if (pid >= packets_per_row * L.T) return;
-    const uint32_t y = pid / packets_per_row, x0 = (pid - y * packets_per_row) * N;
-    texel* row = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes) + (size_t)y * L.T;
+    if (pid >= packets_per_row * row_groups) return;
+    const uint32_t yg = pid / packets_per_row, x0 = (pid - yg * packets_per_row) * N;
+    texel* tile = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes);
     const bool aligned = ((L.T * sizeof(texel)) % 16 == 0) && (L.tile_bytes % 16 == 0);
     const float inv_tile_scale = exp2i(-(int)(task.tile.lod & 31u));  // x / tile_count(lod) == x * 2^-lod exactly
     const float Cf = (float)L.C;
@@ -107,43 +118,110 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
     const bool full_x = d.top_left[0] == 0.0f && d.bottom_right[0] == 1.0f;
     const bool full_y = d.top_left[1] == 0.0f && d.bottom_right[1] == 1.0f;
     const float range_x = d.bottom_right[0] - d.top_left[0], range_y = d.bottom_right[1] - d.top_left[1];
-    // the y terms are shared by the packet
-    const float tcy = (float)(y - L.B) / Cf;
-    float sy = ((float)task.tile.y + tcy) * inv_tile_scale;
-    if (!full_y) sy = (sy - d.top_left[1]) / range_y;
-    const float py = sy * (float)d.height - 0.5f;
-    const float fy = floorf(py);
-    const float ry = py - fy;
-    const int iy = (int)fy;
-    const bool inside_y = tcy >= 0.0f && tcy <= 1.0f;
-    const float Wf = (float)d.width;
-    Packet<texel, N> out;
+    const float Wf = (float)d.width, Hf = (float)d.height;
+    const int wm1 = (int)d.width - 1, hm1 = (int)d.height - 1;
+    const texel* __restrict__ src = reinterpret_cast<const texel*>(d.pixels);
+
+    // ---- per-column terms ----
+    float rx[N];
+    int cx0[N], cx1[N];
+    uint32_t col_ok = 0, col_inside = 0;  // bit i: pixel column lies in the tile centre / passes inside_square in x
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t x = x0 + i;
-        if (x >= L.T) { out.t[i] = F::zero(); continue; }
-        if (is_border(L, x, y)) { out.t[i] = F::zero(); continue; }
+        rx[i] = 0.0f; cx0[i] = 0; cx1[i] = 0;
+        if (x >= L.T || x < L.B || x >= L.B + L.C) continue;
         const float tcx = (float)(x - L.B) / Cf;
         float sx = ((float)task.tile.x + tcx) * inv_tile_scale;
         if (!full_x) sx = (sx - d.top_left[0]) / range_x;   // inverse_mix — preprocessing.wgsl:44-46
         const float px = sx * Wf - 0.5f;
         const float fx = floorf(px);
-        const float rx = px - fx;
+        rx[i] = px - fx;
         const int ix = (int)fx;
-        const Px4 v00 = source_texel<FORMAT>(d, ix, iy), v10 = source_texel<FORMAT>(d, ix + 1, iy);
-        const Px4 v01 = source_texel<FORMAT>(d, ix, iy + 1), v11 = source_texel<FORMAT>(d, ix + 1, iy + 1);
-        const bool is_valid = v00.v[0] != 0.0f && v10.v[0] != 0.0f && v01.v[0] != 0.0f && v11.v[0] != 0.0f;  // textureGather(0,..)
-        const bool is_inside = (tcx >= 0.0f && tcx <= 1.0f) && inside_y;                                        // inside_square
-        if (is_valid && is_inside) {
-            Px4 value;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) value.v[k] = mix(mix(v00.v[k], v10.v[k], rx), mix(v01.v[k], v11.v[k], rx), ry);
-            out.t[i] = F::pack(value);
-        } else {
-            out.t[i] = row[x];  // textureLoad(atlas, coords, atlas_index): keep what earlier datasets wrote
-        }
+        cx0[i] = min(max(ix, 0), wm1);       // clamp-to-edge (ImageSampler::linear, preprocessor.rs:408-409)
+        cx1[i] = min(max(ix + 1, 0), wm1);
+        col_ok |= 1u << i;
+        if (tcx >= 0.0f && tcx <= 1.0f) col_inside |= 1u << i;   // inside_square, x part
     }
-    store_packet<texel, N>(row, x0, L.T, out, aligned);
+
+    // ---- cached horizontal lerps of two source rows ----
+    float hA[N][CH], hB[N][CH];
+    uint32_t vA = 0, vB = 0;       // bit i: both texels of the row have red != 0 (textureGather(0, ..) validity)
+    int rowA = -1, rowB = -1;      // clamped source row held in A / B
+    auto load_row = [&](float (&h)[N][CH], uint32_t& valid, int y) {
+        // row window of a sharded source (bt_preprocess.cu validates it); clamp so a bad window cannot fault
+        const int ry_ = min(max(y - (int)d.row_begin, 0), (int)d.row_count - 1);
+        const texel* __restrict__ r = src + (size_t)ry_ * d.width;
+        valid = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (!(col_ok >> i & 1u)) continue;
+            const Px4 t0 = F::decode(__ldg(r + cx0[i])), t1 = F::decode(__ldg(r + cx1[i]));
+#pragma unroll
+            for (int k = 0; k < CH; ++k) h[i][k] = mix(t0.v[k], t1.v[k], rx[i]);
+            if (t0.v[0] != 0.0f && t1.v[0] != 0.0f) valid |= 1u << i;
+        }
+    };
+
+#pragma unroll 1
+    for (int r = 0; r < SPLIT_ROWS; ++r) {
+        const uint32_t y = yg * SPLIT_ROWS + r;
+        if (y >= L.T) break;
+        texel* row = tile + (size_t)y * L.T;
+        Packet<texel, N> out;
+#pragma unroll
+        for (int i = 0; i < N; ++i) out.t[i] = F::zero();
+        if (y >= L.B && y < L.B + L.C && col_ok != 0u) {   // border rows stay zero (split.wgsl:19-21)
+            const float tcy = (float)(y - L.B) / Cf;
+            float sy = ((float)task.tile.y + tcy) * inv_tile_scale;
+            if (!full_y) sy = (sy - d.top_left[1]) / range_y;
+            const float py = sy * Hf - 0.5f;
+            const float fy = floorf(py);
+            const float ry = py - fy;
+            const int iy = (int)fy;
+            const bool inside_y = tcy >= 0.0f && tcy <= 1.0f;
+            const int ya = min(max(iy, 0), hm1), yb = min(max(iy + 1, 0), hm1);
+            if (ya != rowA) {
+                if (ya == rowB) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i)
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) hA[i][k] = hB[i][k];
+                    vA = vB;
+                } else {
+                    load_row(hA, vA, ya);
+                }
+                rowA = ya;
+            }
+            if (yb != rowB) {
+                if (yb == rowA) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i)
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) hB[i][k] = hA[i][k];
+                    vB = vA;
+                } else {
+                    load_row(hB, vB, yb);
+                }
+                rowB = yb;
+            }
+            const uint32_t write_mask = inside_y ? (col_inside & vA & vB) : 0u;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (!(col_ok >> i & 1u)) continue;
+                if (write_mask >> i & 1u) {
+                    Px4 value{{0.0f, 0.0f, 0.0f, 0.0f}};
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) value.v[k] = mix(hA[i][k], hB[i][k], ry);
+                    out.t[i] = F::pack(value);
+                } else {
+                    // textureLoad(atlas, coords, atlas_index): keep what earlier datasets wrote (zero on a fresh slot)
+                    out.t[i] = (task.flags & kTaskFresh) ? F::zero() : row[x0 + i];
+                }
+            }
+        }
+        store_packet<texel, N>(row, x0, L.T, out, aligned);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,11 +448,12 @@ extern "C" cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_
     PyramidLayout L{static_cast<unsigned char*>(arena), tile_bytes, T, B, T - 2u * B, format};
     for (uint32_t first = 0; first < n_tasks; first += 65535u) {  // gridDim.y limit
         const uint32_t n = (n_tasks - first) < 65535u ? (n_tasks - first) : 65535u;
+        const uint32_t row_groups = (T + SPLIT_ROWS - 1) / SPLIT_ROWS;
         if (format == BT_FORMAT_R16) {
-            const uint32_t packets = ((T + 7) / 8) * T;
+            const uint32_t packets = ((T + 7) / 8) * row_groups;
             split_kernel<BT_FORMAT_R16><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
         } else {
-            const uint32_t packets = ((T + 3) / 4) * T;
+            const uint32_t packets = ((T + 3) / 4) * row_groups;
             split_kernel<BT_FORMAT_RGBA8><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
         }
     }

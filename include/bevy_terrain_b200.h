@@ -367,6 +367,8 @@ void      bt_preprocessor_destroy(bt_preprocessor* p);
  * (:314-343) — split/downsample ALL datasets, barrier, then per LOD per dataset stitch, so that
  * cross-face neighbours exist when the stitch tasks resolve them.                             */
 bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* datasets, uint32_t count);
+/* optional: allocate the device pyramid store of all pending jobs now (keeps cudaMalloc out of run_*) */
+bt_status bt_preprocessor_reserve(bt_preprocessor* p, void* stream);
 /* Runs split -> downsample (per level) -> [halo exchange hook] -> stitch on `stream`.
  * Phases are exposed separately so that a multi-GPU host can run the collective between them. */
 bt_status bt_preprocessor_run_split_downsample(bt_preprocessor* p, void* stream);
