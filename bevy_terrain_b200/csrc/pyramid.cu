@@ -57,6 +57,8 @@ template <> struct Fmt<BT_FORMAT_RGBA8> {
 
 template <typename texel, int N>
 struct alignas(16) Packet { texel t[N]; };
+template <typename texel, int N>
+struct alignas(8) Packet8 { texel t[N]; };
 
 // is_border — preprocessing.wgsl:55-57
 __device__ __forceinline__ bool is_border(const PyramidLayout& L, uint32_t x, uint32_t y) {
@@ -87,22 +89,25 @@ __device__ __forceinline__ Px4 source_texel(const DatasetDevice& d, int x, int y
     return F::decode(__ldg(reinterpret_cast<const typename F::texel*>(d.pixels) + (size_t)ry * d.width + (size_t)x));
 }
 
-// Each thread owns a strip of N pixels x SPLIT_ROWS rows.  Per pixel column the x terms (tile coordinate,
-// source coordinate, bilinear weight, clamped texel columns) are computed once; per source row the horizontal
-// lerp  h(row) = mix(texel(row, x0), texel(row, x1), rx)  and its validity bit are cached in registers, so at the
-// native 1:1 ratio every output row fetches ONE new source row (2 texels per pixel instead of 4) and vertically
-// adjacent outputs share h(row).  value = mix(h(y0), h(y1), ry) is exactly the shader's
-// mix(mix(v00,v10,rx), mix(v01,v11,rx), ry): same operands, same order, bit-identical.
-constexpr int SPLIT_ROWS = 8;
-constexpr int SPLIT_CH_R16 = 1, SPLIT_CH_RGBA8 = 4;
+// Each thread owns a strip of N pixels x SPLIT_ROWS rows (N * sizeof(texel) = 8 bytes: one 64-bit store per row).
+// Per pixel column the x terms (tile coordinate, source coordinate, bilinear weight, clamped texel column) are
+// computed once; per source row the horizontal lerp  h(row) = mix(texel(row, x0), texel(row, x1), rx)  and its
+// validity bit are cached in registers, so at the native 1:1 ratio every output row fetches ONE new source row
+// (2 texels per pixel instead of 4) and vertically adjacent outputs share h(row).  value = mix(h(y0), h(y1), ry)
+// is exactly the shader's mix(mix(v00,v10,rx), mix(v01,v11,rx), ry): same operands, same order, bit-identical.
+// The code is branch-free per pixel (clamped coordinates make every load legal; masks select at the end).
+constexpr int SPLIT_ROWS = 16;
+
+template <int FORMAT> struct SplitCfg;
+template <> struct SplitCfg<BT_FORMAT_R16> { static constexpr int N = 4, CH = 1; };    // R16 packs only .x (preprocessing.wgsl:85-88)
+template <> struct SplitCfg<BT_FORMAT_RGBA8> { static constexpr int N = 2, CH = 4; };
 
 template <int FORMAT>
-__global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks,
-                                                            const DatasetDevice* __restrict__ datasets) {
+__global__ void __launch_bounds__(PYR_THREADS, 4) split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks,
+                                                               const DatasetDevice* __restrict__ datasets) {
     using F = Fmt<FORMAT>;
     using texel = typename F::texel;
-    constexpr int N = F::PX_PER_THREAD;
-    constexpr int CH = FORMAT == BT_FORMAT_R16 ? SPLIT_CH_R16 : SPLIT_CH_RGBA8;  // R16 packs only .x (preprocessing.wgsl:85-88)
+    constexpr int N = SplitCfg<FORMAT>::N, CH = SplitCfg<FORMAT>::CH;
     const PyramidTask& task = tasks[blockIdx.y];
     const DatasetDevice d = datasets[task.dataset];
     const uint32_t packets_per_row = (L.T + N - 1) / N;
@@ -111,7 +116,8 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
     if (pid >= packets_per_row * row_groups) return;
     const uint32_t yg = pid / packets_per_row, x0 = (pid - yg * packets_per_row) * N;
     texel* tile = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes);
-    const bool aligned = ((L.T * sizeof(texel)) % 16 == 0) && (L.tile_bytes % 16 == 0);
+    const bool aligned = ((L.T * sizeof(texel)) % 8 == 0) && (L.tile_bytes % 8 == 0) && x0 + N <= L.T;
+    const bool fresh = (task.flags & kTaskFresh) != 0u;
     const float inv_tile_scale = exp2i(-(int)(task.tile.lod & 31u));  // x / tile_count(lod) == x * 2^-lod exactly
     const float Cf = (float)L.C;
     // inverse_mix with top_left = 0, bottom_right = 1 is (x - 0) / (1 - 0) = x exactly: skip the division
@@ -122,25 +128,22 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
     const int wm1 = (int)d.width - 1, hm1 = (int)d.height - 1;
     const texel* __restrict__ src = reinterpret_cast<const texel*>(d.pixels);
 
-    // ---- per-column terms ----
+    // ---- per-column terms (computed for every lane, masked at the end) ----
     float rx[N];
-    int cx0[N], cx1[N];
-    uint32_t col_ok = 0, col_inside = 0;  // bit i: pixel column lies in the tile centre / passes inside_square in x
+    uint32_t cx0[N];
+    uint32_t col_centre = 0, col_inside = 0;  // bit i: pixel column lies in the tile centre / passes inside_square in x
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t x = x0 + i;
-        rx[i] = 0.0f; cx0[i] = 0; cx1[i] = 0;
-        if (x >= L.T || x < L.B || x >= L.B + L.C) continue;
-        const float tcx = (float)(x - L.B) / Cf;
+        const float tcx = (float)((int)x - (int)L.B) / Cf;
         float sx = ((float)task.tile.x + tcx) * inv_tile_scale;
         if (!full_x) sx = (sx - d.top_left[0]) / range_x;   // inverse_mix — preprocessing.wgsl:44-46
         const float px = sx * Wf - 0.5f;
         const float fx = floorf(px);
         rx[i] = px - fx;
         const int ix = (int)fx;
-        cx0[i] = min(max(ix, 0), wm1);       // clamp-to-edge (ImageSampler::linear, preprocessor.rs:408-409)
-        cx1[i] = min(max(ix + 1, 0), wm1);
-        col_ok |= 1u << i;
+        cx0[i] = (uint32_t)min(max(ix, 0), wm1) | ((uint32_t)(min(max(ix + 1, 0), wm1) - min(max(ix, 0), wm1)) << 31);  // clamp-to-edge; bit 31 = step to x1
+        if (x < L.T && x >= L.B && x < L.B + L.C) col_centre |= 1u << i;
         if (tcx >= 0.0f && tcx <= 1.0f) col_inside |= 1u << i;   // inside_square, x part
     }
 
@@ -155,11 +158,11 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
         valid = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (!(col_ok >> i & 1u)) continue;
-            const Px4 t0 = F::decode(__ldg(r + cx0[i])), t1 = F::decode(__ldg(r + cx1[i]));
+            const uint32_t c0 = cx0[i] & 0x7FFFFFFFu, c1 = c0 + (cx0[i] >> 31);
+            const Px4 t0 = F::decode(__ldg(r + c0)), t1 = F::decode(__ldg(r + c1));
 #pragma unroll
             for (int k = 0; k < CH; ++k) h[i][k] = mix(t0.v[k], t1.v[k], rx[i]);
-            if (t0.v[0] != 0.0f && t1.v[0] != 0.0f) valid |= 1u << i;
+            valid |= (uint32_t)(t0.v[0] != 0.0f && t1.v[0] != 0.0f) << i;
         }
     };
 
@@ -168,10 +171,10 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
         const uint32_t y = yg * SPLIT_ROWS + r;
         if (y >= L.T) break;
         texel* row = tile + (size_t)y * L.T;
-        Packet<texel, N> out;
+        Packet8<texel, N> out;
 #pragma unroll
         for (int i = 0; i < N; ++i) out.t[i] = F::zero();
-        if (y >= L.B && y < L.B + L.C && col_ok != 0u) {   // border rows stay zero (split.wgsl:19-21)
+        if (y >= L.B && y < L.B + L.C && col_centre != 0u) {   // border rows stay zero (split.wgsl:19-21); warp-uniform in y
             const float tcy = (float)(y - L.B) / Cf;
             float sy = ((float)task.tile.y + tcy) * inv_tile_scale;
             if (!full_y) sy = (sy - d.top_left[1]) / range_y;
@@ -205,22 +208,26 @@ __global__ void __launch_bounds__(PYR_THREADS) split_kernel(PyramidLayout L, con
                 }
                 rowB = yb;
             }
-            const uint32_t write_mask = inside_y ? (col_inside & vA & vB) : 0u;
+            const uint32_t write_mask = inside_y ? (col_centre & col_inside & vA & vB) : 0u;
+            const uint32_t keep_mask = col_centre & ~write_mask;   // textureLoad(atlas, coords): keep earlier datasets' texels
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                if (!(col_ok >> i & 1u)) continue;
-                if (write_mask >> i & 1u) {
-                    Px4 value{{0.0f, 0.0f, 0.0f, 0.0f}};
+                Px4 value{{0.0f, 0.0f, 0.0f, 0.0f}};
 #pragma unroll
-                    for (int k = 0; k < CH; ++k) value.v[k] = mix(hA[i][k], hB[i][k], ry);
-                    out.t[i] = F::pack(value);
-                } else {
-                    // textureLoad(atlas, coords, atlas_index): keep what earlier datasets wrote (zero on a fresh slot)
-                    out.t[i] = (task.flags & kTaskFresh) ? F::zero() : row[x0 + i];
-                }
+                for (int k = 0; k < CH; ++k) value.v[k] = mix(hA[i][k], hB[i][k], ry);
+                if (write_mask >> i & 1u) out.t[i] = F::pack(value);
+            }
+            if (keep_mask != 0u && !fresh) {
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    if (keep_mask >> i & 1u) out.t[i] = row[x0 + i];
             }
         }
-        store_packet<texel, N>(row, x0, L.T, out, aligned);
+        if (aligned) {
+            *reinterpret_cast<uint2*>(row + x0) = *reinterpret_cast<const uint2*>(&out);
+        } else {
+            for (int i = 0; i < N; ++i) if (x0 + i < L.T) row[x0 + i] = out.t[i];
+        }
     }
 }
 
@@ -247,8 +254,10 @@ __global__ void __launch_bounds__(PYR_THREADS) downsample_kernel(PyramidLayout L
         out.t[i] = F::zero();
         if (x >= L.T || is_border(L, x, y)) continue;
         const uint32_t tx = x - L.B, ty = y - L.B;
-        const uint32_t cx = 2u * (tx % child_size) + L.B, cy = 2u * (ty % child_size) + L.B;
-        uint32_t child_index = tx / child_size + 2u * (ty / child_size);
+        // tx / child_size and tx % child_size without an integer division: tx < C <= 2*child_size + 1
+        const uint32_t qx = (tx >= child_size) + (tx >= 2u * child_size), qy = (ty >= child_size) + (ty >= 2u * child_size);
+        const uint32_t cx = 2u * (tx - qx * child_size) + L.B, cy = 2u * (ty - qy * child_size) + L.B;
+        uint32_t child_index = qx + 2u * qy;
         if (child_index > 3u) child_index = 3u;
         const uint32_t child_slot = task.dep[child_index];
         if (child_slot == INVALID_SLOT) continue;  // invalid layer reads as zero -> count == 0 -> 0 (Q3)
@@ -450,10 +459,10 @@ extern "C" cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_
         const uint32_t n = (n_tasks - first) < 65535u ? (n_tasks - first) : 65535u;
         const uint32_t row_groups = (T + SPLIT_ROWS - 1) / SPLIT_ROWS;
         if (format == BT_FORMAT_R16) {
-            const uint32_t packets = ((T + 7) / 8) * row_groups;
+            const uint32_t packets = ((T + SplitCfg<BT_FORMAT_R16>::N - 1) / SplitCfg<BT_FORMAT_R16>::N) * row_groups;
             split_kernel<BT_FORMAT_R16><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
         } else {
-            const uint32_t packets = ((T + 3) / 4) * row_groups;
+            const uint32_t packets = ((T + SplitCfg<BT_FORMAT_RGBA8>::N - 1) / SplitCfg<BT_FORMAT_RGBA8>::N) * row_groups;
             split_kernel<BT_FORMAT_RGBA8><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
         }
     }
