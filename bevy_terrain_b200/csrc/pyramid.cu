@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PYR_THREADS, 4) split_kernel(PyramidLayout L, 
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t x = x0 + i;
-        const float tcx = (float)((int)x - (int)L.B) / Cf;
+        const float tcx = div_rn((float)((int)x - (int)L.B), Cf);   // == IEEE quotient (bt_device.cuh)
         float sx = ((float)task.tile.x + tcx) * inv_tile_scale;
         if (!full_x) sx = (sx - d.top_left[0]) / range_x;   // inverse_mix — preprocessing.wgsl:44-46
         const float px = sx * Wf - 0.5f;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(PYR_THREADS, 4) split_kernel(PyramidLayout L, 
 #pragma unroll
         for (int i = 0; i < N; ++i) out.t[i] = F::zero();
         if (y >= L.B && y < L.B + L.C && col_centre != 0u) {   // border rows stay zero (split.wgsl:19-21); warp-uniform in y
-            const float tcy = (float)(y - L.B) / Cf;
+            const float tcy = div_rn((float)(y - L.B), Cf);
             float sy = ((float)task.tile.y + tcy) * inv_tile_scale;
             if (!full_y) sy = (sy - d.top_left[1]) / range_y;
             const float py = sy * Hf - 0.5f;
@@ -248,6 +248,64 @@ __global__ void __launch_bounds__(PYR_THREADS) downsample_kernel(PyramidLayout L
     const bool aligned = ((L.T * sizeof(texel)) % 16 == 0) && (L.tile_bytes % 16 == 0);
     const uint32_t child_size = L.C / 2u;
     Packet<texel, N> out;
+    // ---- fast path: the whole packet lies in the centre, inside ONE child, and the child texel pairs are 4-byte
+    // (R16) / 8-byte (Rgba8) aligned: vector loads, no per-pixel indexing.  Same operands in the same order as the
+    // general path below (sum over OFFSETS (0,0),(0,1),(1,0),(1,1); adding an invalid R16 texel adds exactly +0).
+    if (aligned && (L.B % 2u) == 0u && (L.C % 2u) == 0u && y >= L.B && y < L.B + L.C && x0 >= L.B && x0 + N <= L.B + L.C) {
+        const uint32_t tx0 = x0 - L.B, txl = tx0 + N - 1u, ty = y - L.B;
+        const uint32_t qx = tx0 >= child_size, qy = ty >= child_size;
+        if (qx == (uint32_t)(txl >= child_size)) {
+            const uint32_t child_slot = task.dep[qx + 2u * qy];
+            const uint32_t cx = 2u * (tx0 - qx * child_size) + L.B, cy = 2u * (ty - qy * child_size) + L.B;
+            if (child_slot == INVALID_SLOT) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) out.t[i] = F::zero();
+            } else {
+                const texel* r0 = reinterpret_cast<const texel*>(L.arena + (size_t)child_slot * L.tile_bytes) + (size_t)cy * L.T + cx;
+                const texel* r1 = r0 + L.T;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    texel a, b, c, e;  // (cx,cy) (cx+1,cy) (cx,cy+1) (cx+1,cy+1)
+                    if constexpr (FORMAT == BT_FORMAT_R16) {
+                        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(r0) + i), w1 = __ldg(reinterpret_cast<const uint32_t*>(r1) + i);
+                        a = (uint16_t)(w0 & 0xFFFFu); b = (uint16_t)(w0 >> 16); c = (uint16_t)(w1 & 0xFFFFu); e = (uint16_t)(w1 >> 16);
+                        const float count = (float)((a != 0) + (c != 0) + (b != 0) + (e != 0));
+                        // invalid texels are exactly 0.0: adding them leaves the sum unchanged, as skipping them does
+                        float sum = ((unorm16_to_float(a) + unorm16_to_float(c)) + unorm16_to_float(b)) + unorm16_to_float(e);
+                        if (count == 3.0f) sum = sum / 3.0f;
+                        else sum = sum * (count == 4.0f ? 0.25f : (count == 2.0f ? 0.5f : 1.0f));
+                        out.t[i] = count != 0.0f ? F::pack(Px4{{sum, 0.0f, 0.0f, 0.0f}}) : F::zero();
+                    } else {
+                        const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(r0) + i), w1 = __ldg(reinterpret_cast<const uint2*>(r1) + i);
+                        a = *reinterpret_cast<const uchar4*>(&w0.x); b = *reinterpret_cast<const uchar4*>(&w0.y);
+                        c = *reinterpret_cast<const uchar4*>(&w1.x); e = *reinterpret_cast<const uchar4*>(&w1.y);
+                        const texel order[4] = {a, c, b, e};
+                        Px4 sum{{0.0f, 0.0f, 0.0f, 0.0f}};
+                        float count = 0.0f;
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            const bool is_valid = (order[o].x | order[o].y | order[o].z) != 0;   // any(xyz != 0)
+                            const Px4 cv = F::decode(order[o]);
+                            // rgb of an invalid texel are exactly 0.0 (adding them is a no-op); alpha must be skipped
+                            sum.v[0] += cv.v[0]; sum.v[1] += cv.v[1]; sum.v[2] += cv.v[2];
+                            if (is_valid) { sum.v[3] += cv.v[3]; count += 1.0f; }
+                        }
+                        if (count == 3.0f) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) sum.v[k] = sum.v[k] / 3.0f;
+                        } else {
+                            const float scale = count == 4.0f ? 0.25f : (count == 2.0f ? 0.5f : 1.0f);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) sum.v[k] = sum.v[k] * scale;
+                        }
+                        out.t[i] = count != 0.0f ? F::pack(sum) : F::zero();
+                    }
+                }
+            }
+            store_packet<texel, N>(row, x0, L.T, out, aligned);
+            return;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const uint32_t x = x0 + i;
