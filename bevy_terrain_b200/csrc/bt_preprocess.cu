@@ -54,16 +54,29 @@ struct Store {  // one attachment's device-resident tile pyramid
     std::vector<uint32_t> exists_from_job;
     std::vector<uint8_t> kind;
     unsigned char* arena = nullptr;
+    std::vector<uint8_t> planned;  // slot is the target of an already planned (earlier) job
     std::vector<uint8_t> written;  // slot has been produced by a kernel (else its content is "the zero-initialised atlas texture")
     uint32_t arena_slots = 0;    // slots the arena can hold
     uint32_t cleared_slots = 0;  // slots whose first-use handling (ghost zeroing) has been done
+};
+
+struct Range { uint32_t begin = 0, count = 0; };
+struct Level { uint32_t lod; Range range; };
+struct JobPlan {  // all task tables of one job, concatenated: [split | downsample levels (deepest first) | stitch]
+    std::vector<PyramidTask> tasks;
+    std::vector<DatasetDevice> datasets;
+    Range split, stitch;
+    std::vector<Level> levels;
+    PyramidTask* d_tasks = nullptr;
+    DatasetDevice* d_datasets = nullptr;
 };
 
 struct Job {
     uint32_t attachment = 0;
     std::vector<bt_dataset> datasets;
     std::vector<void*> owned_pixels;  // device copies of host-provided sources
-    bool split_done = false, roots_done = false, halo_done = false, stitched = false;
+    JobPlan plan;
+    bool prepared = false, split_done = false, roots_done = false, halo_done = false, stitched = false;
 };
 
 // NEIGHBOURING_SIDES / SideInfo — src/math/coordinate.rs:9-53
@@ -244,63 +257,113 @@ struct bt_preprocessor {
                 t.tile = bt_tile{d.side, lod, x, y};
                 t.slot = s.slot_of.at(TileKey{d.side, lod, x, y});
                 t.dataset = di;
-                t.flags = s.written[t.slot] ? 0u : btd::kTaskFresh;
+                t.flags = 0u;
                 out.push_back(t);
             }
     }
 
-    bt_status run_levels(uint32_t ji, uint32_t lod_hi_exclusive, uint32_t lod_lo, bool with_split, cudaStream_t stream) {
-        // downsample levels lod_hi_exclusive-1 ... lod_lo (and the split of the deepest level if asked)
+    // ---- job plan: every task table of a job is built once, uploaded with ONE copy, and the kernels are then
+    // launched back to back without host synchronisation (the reference rebuilds a uniform buffer + bind group
+    // per task per frame, gpu_preprocessor.rs:120-223)
+    bt_status prepare_job(uint32_t ji, cudaStream_t stream) {
         Job& j = jobs[ji];
+        if (j.prepared) return BT_OK;
         Store& s = stores[j.attachment];
-        std::vector<PyramidTask> tasks;
-        if (with_split) {
-            std::vector<DatasetDevice> dd;
-            for (uint32_t di = 0; di < j.datasets.size(); ++di) {
-                const bt_dataset& d = j.datasets[di];
-                DatasetDevice x{};
-                x.pixels = d.pixels;
-                x.width = d.width; x.height = d.height;
-                x.top_left[0] = d.top_left[0]; x.top_left[1] = d.top_left[1];
-                x.bottom_right[0] = d.bottom_right[0]; x.bottom_right[1] = d.bottom_right[1];
-                x.row_begin = d.row_count ? d.row_begin : 0;
-                x.row_count = d.row_count ? d.row_count : d.height;
-                dd.push_back(x);
-                if (d.lod_end > d.lod_begin) collect(ji, d, di, d.lod_end - 1, tasks);
-            }
-            bt_status st = upload(&d_datasets, &d_datasets_cap, dd, stream);
-            if (st != BT_OK) return st;
-            st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
-            if (st != BT_OK) return st;
-            BT_CUDA(ctx, bt_launch_split(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), d_datasets, stream));
-            for (const PyramidTask& t : tasks) s.written[t.slot] = 1;
+        allocate_job_tiles(ji);
+        if (s.planned.size() < s.keys.size()) s.planned.resize(s.keys.size(), 0);
+        uint32_t lod_end = 0, lod_begin = kInvalid;
+        for (const bt_dataset& d : j.datasets) { lod_end = std::max(lod_end, d.lod_end); lod_begin = std::min(lod_begin, d.lod_begin); }
+        JobPlan& P = j.plan;
+        std::vector<PyramidTask>& tasks = P.tasks;
+        tasks.clear();
+        P.datasets.clear();
+        // split of the deepest level of every dataset
+        for (uint32_t di = 0; di < j.datasets.size(); ++di) {
+            const bt_dataset& d = j.datasets[di];
+            DatasetDevice x{};
+            x.pixels = d.pixels;
+            x.width = d.width; x.height = d.height;
+            x.top_left[0] = d.top_left[0]; x.top_left[1] = d.top_left[1];
+            x.bottom_right[0] = d.bottom_right[0]; x.bottom_right[1] = d.bottom_right[1];
+            x.row_begin = d.row_count ? d.row_begin : 0;
+            x.row_count = d.row_count ? d.row_count : d.height;
+            P.datasets.push_back(x);
+            collect(ji, d, di, d.lod_end - 1, tasks);
         }
-        for (int32_t lod = (int32_t)lod_hi_exclusive - 1; lod >= (int32_t)lod_lo; --lod) {
-            tasks.clear();
+        P.split = Range{0u, (uint32_t)tasks.size()};
+        for (uint32_t i = P.split.begin; i < P.split.begin + P.split.count; ++i) {
+            tasks[i].flags = (s.written[tasks[i].slot] || s.planned[tasks[i].slot]) ? 0u : btd::kTaskFresh;
+            s.planned[tasks[i].slot] = 1;
+        }
+        // downsample levels, deepest first; sharded: levels below the root level run after the sub-root gather
+        P.levels.clear();
+        for (int32_t lod = (int32_t)lod_end - 2; lod >= (int32_t)lod_begin; --lod) {
+            const uint32_t first = (uint32_t)tasks.size();
             for (uint32_t di = 0; di < j.datasets.size(); ++di) {
                 const bt_dataset& d = j.datasets[di];
                 if ((uint32_t)lod + 1 >= d.lod_end || (uint32_t)lod < d.lod_begin) continue;  // the deepest level is split, not downsampled
-                const size_t first = tasks.size();
+                const size_t f = tasks.size();
                 collect(ji, d, di, (uint32_t)lod, tasks);
-                for (size_t i = first; i < tasks.size(); ++i)  // TileCoordinate::children — coordinate.rs:197-206
+                for (size_t i = f; i < tasks.size(); ++i) {  // TileCoordinate::children — coordinate.rs:197-206
                     for (uint32_t c = 0; c < 4; ++c)
                         tasks[i].dep[c] = get_tile(s, TileKey{d.side, (uint32_t)lod + 1, (tasks[i].tile.x << 1) + c % 2, (tasks[i].tile.y << 1) + c / 2}, ji);
+                    s.planned[tasks[i].slot] = 1;
+                }
             }
-            if (tasks.empty()) continue;
-            // the previous launch may still read d_tasks: stream order makes the upload wait (same stream)
-            bt_status st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
-            if (st != BT_OK) return st;
-            BT_CUDA(ctx, bt_launch_downsample(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), stream));
-            for (const PyramidTask& t : tasks) s.written[t.slot] = 1;
+            if (tasks.size() > first) P.levels.push_back(Level{(uint32_t)lod, Range{first, (uint32_t)tasks.size() - first}});
+        }
+        // stitch: every LOD in one launch (reads only neighbour CENTRES, all final after the downsample phase)
+        static const int32_t kOffsets[8][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};  // coordinate.rs:209-218
+        const uint32_t stitch_first = (uint32_t)tasks.size();
+        for (uint32_t di = 0; di < j.datasets.size(); ++di) {
+            const bt_dataset& d = j.datasets[di];
+            for (uint32_t lod = d.lod_begin; lod < d.lod_end; ++lod) {
+                const size_t f = tasks.size();
+                collect(ji, d, di, lod, tasks);
+                for (size_t i = f; i < tasks.size(); ++i) {
+                    const TileKey self{tasks[i].tile.side, tasks[i].tile.lod, tasks[i].tile.x, tasks[i].tile.y};
+                    for (int k = 0; k < 8; ++k) {  // TileCoordinate::neighbours — coordinate.rs:208-225
+                        const TileKey nb = neighbour_coordinate(self, (int32_t)self.x + kOffsets[k][0], (int32_t)self.y + kOffsets[k][1], spherical());
+                        tasks[i].dep[k] = get_tile(s, nb, ji);
+                        tasks[i].dep_side[k] = nb.side;
+                    }
+                }
+            }
+        }
+        P.stitch = Range{stitch_first, (uint32_t)tasks.size() - stitch_first};
+        j.prepared = true;
+        if (plan_only()) return BT_OK;
+        // device copies (one allocation + one copy per job)
+        bt_status st = ensure_arena(s, stream);
+        if (st != BT_OK) return st;
+        BT_CUDA(ctx, cudaMalloc((void**)&P.d_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(PyramidTask)));
+        BT_CUDA(ctx, cudaMalloc((void**)&P.d_datasets, std::max<size_t>(P.datasets.size(), 1) * sizeof(DatasetDevice)));
+        BT_CUDA(ctx, cudaMemcpyAsync(P.d_tasks, tasks.data(), tasks.size() * sizeof(PyramidTask), cudaMemcpyHostToDevice, stream));
+        BT_CUDA(ctx, cudaMemcpyAsync(P.d_datasets, P.datasets.data(), P.datasets.size() * sizeof(DatasetDevice), cudaMemcpyHostToDevice, stream));
+        BT_CUDA(ctx, cudaStreamSynchronize(stream));  // pageable sources: the copies are complete when this returns
+        return BT_OK;
+    }
+
+    bt_status run_levels(uint32_t ji, uint32_t lod_hi_exclusive, uint32_t lod_lo, bool with_split, cudaStream_t stream) {
+        // downsample levels lod_hi_exclusive-1 ... lod_lo (and the split of the deepest level if asked); launches only
+        Job& j = jobs[ji];
+        Store& s = stores[j.attachment];
+        const JobPlan& P = j.plan;
+        if (with_split) {
+            BT_CUDA(ctx, bt_launch_split(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + P.split.begin, P.split.count, P.d_datasets, stream));
+            for (uint32_t i = P.split.begin; i < P.split.begin + P.split.count; ++i) s.written[P.tasks[i].slot] = 1;
+        }
+        for (const Level& lv : P.levels) {
+            if (lv.lod >= lod_hi_exclusive || lv.lod < lod_lo) continue;
+            BT_CUDA(ctx, bt_launch_downsample(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + lv.range.begin, lv.range.count, stream));
+            for (uint32_t i = lv.range.begin; i < lv.range.begin + lv.range.count; ++i) s.written[P.tasks[i].slot] = 1;
         }
         return BT_OK;
     }
 
     bt_status run_split_downsample_job(uint32_t ji, cudaStream_t stream) {
         Job& j = jobs[ji];
-        Store& s = stores[j.attachment];
-        allocate_job_tiles(ji);
-        bt_status st = ensure_arena(s, stream);
+        bt_status st = prepare_job(ji, stream);
         if (st != BT_OK) return st;
         uint32_t lod_end = 0, lod_begin = kInvalid;
         for (const bt_dataset& d : j.datasets) { lod_end = std::max(lod_end, d.lod_end); lod_begin = std::min(lod_begin, d.lod_begin); }
@@ -314,27 +377,8 @@ struct bt_preprocessor {
     bt_status run_stitch_job(uint32_t ji, cudaStream_t stream) {
         Job& j = jobs[ji];
         Store& s = stores[j.attachment];
-        std::vector<PyramidTask> tasks;
-        static const int32_t kOffsets[8][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};  // coordinate.rs:209-218
-        for (uint32_t di = 0; di < j.datasets.size(); ++di) {
-            const bt_dataset& d = j.datasets[di];
-            for (uint32_t lod = d.lod_begin; lod < d.lod_end; ++lod) {
-                const size_t first = tasks.size();
-                collect(ji, d, di, lod, tasks);
-                for (size_t i = first; i < tasks.size(); ++i) {
-                    const TileKey self{tasks[i].tile.side, tasks[i].tile.lod, tasks[i].tile.x, tasks[i].tile.y};
-                    for (int k = 0; k < 8; ++k) {  // TileCoordinate::neighbours — coordinate.rs:208-225
-                        const TileKey nb = neighbour_coordinate(self, (int32_t)self.x + kOffsets[k][0], (int32_t)self.y + kOffsets[k][1], spherical());
-                        tasks[i].dep[k] = get_tile(s, nb, ji);
-                        tasks[i].dep_side[k] = nb.side;
-                    }
-                }
-            }
-        }
-        // stitch reads only neighbour CENTRES, all final after the downsample phase: one launch for every LOD
-        bt_status st = upload(&d_tasks, &d_tasks_cap, tasks, stream);
-        if (st != BT_OK) return st;
-        BT_CUDA(ctx, bt_launch_stitch(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, d_tasks, (uint32_t)tasks.size(), stream));
+        const JobPlan& P = j.plan;
+        BT_CUDA(ctx, bt_launch_stitch(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + P.stitch.begin, P.stitch.count, stream));
         j.stitched = true;
         return BT_OK;
     }
@@ -408,7 +452,7 @@ void bt_preprocessor_destroy(bt_preprocessor* p) {
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (Store& s : p->stores) if (s.arena) cudaFree(s.arena);
-    for (Job& j : p->jobs) for (void* px : j.owned_pixels) cudaFree(px);
+    for (Job& j : p->jobs) { for (void* px : j.owned_pixels) cudaFree(px); cudaFree(j.plan.d_tasks); cudaFree(j.plan.d_datasets); }
     cudaFree(p->d_tasks); cudaFree(p->d_datasets); cudaFree(p->d_copies);
     delete p;
 }
@@ -475,19 +519,11 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
 bt_status bt_preprocessor_reserve(bt_preprocessor* p, void* stream) {
     if (!p || p->plan_only()) return BT_ERR_INVALID_ARG;
     BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
-    for (size_t ji = 0; ji < p->jobs.size(); ++ji) if (!p->jobs[ji].stitched) p->allocate_job_tiles((uint32_t)ji);
-    for (Store& s : p->stores) {
-        bt_status st = p->ensure_arena(s, (cudaStream_t)stream);
+    for (size_t ji = 0; ji < p->jobs.size(); ++ji) p->allocate_job_tiles((uint32_t)ji);   // size every store for all jobs first
+    for (size_t ji = 0; ji < p->jobs.size(); ++ji) {
+        if (p->jobs[ji].stitched) continue;
+        bt_status st = p->prepare_job((uint32_t)ji, (cudaStream_t)stream);
         if (st != BT_OK) return st;
-    }
-    // task / dataset scratch sized for the largest level
-    size_t most = 0;
-    for (const Store& s : p->stores) most = std::max(most, s.keys.size());
-    if (most > p->d_tasks_cap) {
-        if (p->d_tasks) BT_CUDA(p->ctx, cudaFree(p->d_tasks));
-        p->d_tasks = nullptr;
-        BT_CUDA(p->ctx, cudaMalloc((void**)&p->d_tasks, most * sizeof(PyramidTask)));
-        p->d_tasks_cap = most;
     }
     return BT_OK;
 }
@@ -597,8 +633,7 @@ bt_status bt_preprocessor_plan(bt_preprocessor* p) {
     if (!p) return BT_ERR_INVALID_ARG;
     const int ji = p->pending_job();
     if (ji < 0) return BT_ERR_INVALID_ARG;
-    p->allocate_job_tiles((uint32_t)ji);
-    return BT_OK;
+    return p->prepare_job((uint32_t)ji, nullptr);
 }
 
 bt_status bt_preprocessor_plan_tiles(bt_preprocessor* p, uint32_t attachment, bt_tile* tiles, uint32_t* kinds, uint32_t cap, uint32_t* count) {
