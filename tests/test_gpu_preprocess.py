@@ -140,3 +140,57 @@ def test_mipmaps_match_oracle(ctx):
         ctx.d2h(got, d_out)
         ctx.free(d_in); ctx.free(d_out)
         assert np.array_equal(got, exp)
+
+
+def _read_varint(buf, pos):
+    b = buf[pos]
+    if b < 251:
+        return b, pos + 1
+    n = {251: 2, 252: 4, 253: 8}[b]
+    return int.from_bytes(buf[pos + 1:pos + 1 + n], "little"), pos + 1 + n
+
+
+def test_save_writes_reference_tile_files_and_config_tc(ctx, tmp_path):
+    """Save tasks + save_tile_config (tile_atlas.rs:77-116,605-613): raw mip-0 texels in <side>_<lod>_<x>_<y>.bin and a
+    bincode-standard (varint) Vec<TileCoordinate> in config.tc (formats/mod.rs:14-24)"""
+    from bevy_terrain_b200 import api
+    T, B, L = 32, 2, 3
+    src = O.synth_source(F.BT_FORMAT_R16, 600, 300, seed=21)   # > 250 forces multi-byte varints? (coordinates stay small; the count does not matter)
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_PLANAR, L, T, B, F.BT_FORMAT_R16))
+    try:
+        pre.preprocess_tile(api.PreprocessDataset(pixels=src, lod_range=range(0, L))).run()
+        pre.save(0, str(tmp_path))
+        tiles = {tuple(int(v) for v in t) for t in pre.tiles()}
+        for tc in tiles:
+            raw = np.fromfile(tmp_path / ("%d_%d_%d_%d.bin" % tc), dtype=np.uint16).reshape(T, T)
+            assert np.array_equal(raw, pre.get_tile(0, tc))
+        buf = (tmp_path / "config.tc").read_bytes()
+        n, pos = _read_varint(buf, 0)
+        listed = set()
+        for _ in range(n):
+            vals = []
+            for _ in range(4):
+                v, pos = _read_varint(buf, pos)
+                vals.append(v)
+            listed.add(tuple(vals))
+        assert pos == len(buf) and listed == tiles and n == 21
+    finally:
+        pre.close()
+
+
+def test_preprocess_errors_are_reported_not_fatal(ctx):
+    """reference behaviour: panics / silently nothing (Rgb8, Rg16 have no shader path); here: status codes"""
+    from bevy_terrain_b200 import api
+    import ctypes as C
+    att = (F.AttachmentConfig * 1)(F.AttachmentConfig(32, 2, 1, 5))       # Rgb8 id = 5 (terrain_data/mod.rs:52)
+    h = C.c_void_p()
+    assert ctx.lib.bt_preprocessor_create(ctx._h, F.BT_KIND_PLANAR, att, 1, 3, F.Shard(0, 1), C.byref(h)) == F.BT_ERR_INVALID_ARG
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_PLANAR, 3, 32, 2, F.BT_FORMAT_R16))
+    try:
+        with pytest.raises(F.BtError):   # lod_range beyond lod_count
+            pre.preprocess_tile(api.PreprocessDataset(pixels=np.ones((8, 8), np.uint16), lod_range=range(0, 9)))
+        with pytest.raises(F.BtError):   # empty extent
+            pre.preprocess_tile(api.PreprocessDataset(pixels=np.ones((8, 8), np.uint16), top_left=(0.5, 0.5), bottom_right=(0.5, 0.9), lod_range=range(0, 2)))
+        assert ctx.lib.bt_preprocessor_get_tile(pre._h, 0, C.byref(F.Tile(0, 0, 0, 0)), C.c_void_p(1), 32 * 32 * 2) == F.BT_ERR_NOT_FOUND
+    finally:
+        pre.close()
