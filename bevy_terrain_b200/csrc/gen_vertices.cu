@@ -6,14 +6,15 @@
 // blended as src/shaders/render/fragment.wgsl:99-107).
 //
 // Design (B200):
-//   * persistent CTAs (two per SM) stride over work items = (tile, block of CB column strips)
+//   * persistent CTAs (one per SM, warp-specialised: 23 compute warps + 1 TMA store warp) stride over work items
+//     = (tile, block of CB column strips); image hand-over by mbarriers, no CTA-wide barrier in steady state
 //   * the reference's triangle-strip index stream visits every grid vertex ~2x (8448 strip
 //     vertices for 65x65 = 4225 unique ones at grid 64, compute_tile_uv functions.wgsl:64-71);
 //     each unique vertex is computed ONCE and scattered to its 2-3 strip positions in a
 //     shared-memory image of the output block — bit-identical to recomputation because the
 //     vertex is a pure function of (tile, column, row)
 //   * the image is written to HBM with TMA 1-D bulk stores (cp.async.bulk.global.shared::cta,
-//     one per strip); while one CTA's stores drain, the SM's other CTA computes its next item;
+//     one per strip), double-buffered: the stores of item i drain while item i+1 is computed;
 //     HBM sees only full-line, fully coalesced writes of the 40-B interleaved records
 //   * the uniform block is staged into shared memory with one TMA bulk load + mbarrier
 //   * height texels are gathered with read-only (ld.global.nc) 16-bit loads; lanes walk along
@@ -24,9 +25,10 @@
 
 namespace btd {
 
-constexpr int GEN_THREADS = 384;       // 12 warps: 3 rounds cover the 17x65 = 1105 vertices of a g=64 work item (96 % lane use)
-constexpr int GEN_CTAS_PER_SM = 2;     // two resident CTAs: one computes while the other waits at a barrier / on its bulk store
-constexpr int GEN_BUFFERS = 1;         // output images per CTA (the second CTA of the SM provides the overlap)
+constexpr int GEN_COMPUTE_WARPS = 23;  // compute warps per CTA (+ 1 store warp): 24 warps, one CTA per SM
+constexpr int GEN_THREADS = (GEN_COMPUTE_WARPS + 1) * 32;
+constexpr int GEN_CTAS_PER_SM = 1;
+constexpr int GEN_BUFFERS = 2;         // output images per CTA: compute of item i+1 overlaps the TMA stores of item i
 constexpr uint32_t STRIP_PAD = 16;     // bytes between strips in the smem image (bank spreading; keeps 16-B alignment)
 
 struct GenParams {
@@ -314,19 +316,28 @@ __device__ __forceinline__ void store_record(unsigned char* image, uint32_t stri
 
 struct GenSmemHeader {
     ViewUniforms U;
-    uint64_t bar;
-    uint64_t _pad;
+    uint64_t bar;                   // uniform-block TMA load
+    uint64_t full[GEN_BUFFERS];     // image b completely written by the compute warps (count = compute warps)
+    uint64_t empty[GEN_BUFFERS];    // image b completely read by the TMA stores (count = 1, the store warp)
 };
 
+// Warp-specialised pipeline, one CTA per SM:
+//   * GEN_COMPUTE_WARPS warps compute vertices and scatter them into output image (it & 1); there is NO CTA-wide barrier
+//     on the steady-state path: a warp that has finished its chunks of item i arrives on full[b] and starts on its
+//     chunks of item i+1 in the other image, so the ragged last round of an item (1105 vertices = 34.5 warp-chunks) is
+//     filled with the next item's work
+//   * one store warp waits on full[b], issues the item's TMA bulk stores, waits until they have READ the image
+//     (cp.async.bulk.wait_group.read) and arrives on empty[b], which the compute warps wait on before reusing image b
 template <bool SPHERICAL>
-__global__ void __launch_bounds__(GEN_THREADS, GEN_CTAS_PER_SM) gen_vertices_kernel(const GenParams P) {
+__global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     GenSmemHeader& H = *reinterpret_cast<GenSmemHeader*>(smem_raw);
     unsigned char* images = smem_raw + ((sizeof(GenSmemHeader) + 127) & ~size_t(127));
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&H.bar, 1);
+        for (int b = 0; b < GEN_BUFFERS; ++b) { mbar_init(&H.full[b], GEN_COMPUTE_WARPS); mbar_init(&H.empty[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -336,7 +347,6 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_CTAS_PER_SM) gen_vertices_ker
     }
     mbar_wait_cta(&H.bar, 0);
     const ViewUniforms& U = H.U;
-    const FrameConsts F = make_frame_consts<SPHERICAL>(U);
 
     const uint32_t g = P.grid_size;
     const uint32_t vpr = U.view_config.vertices_per_row, vpt = U.view_config.vertices_per_tile;
@@ -357,47 +367,73 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_CTAS_PER_SM) gen_vertices_ker
     }
     const uint32_t n_items = n_tiles * P.items_per_tile;
 
+    if (warp == GEN_COMPUTE_WARPS) {
+        // ---------------- store warp ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+                const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
+                const uint32_t tile_index = w / P.items_per_tile;
+                const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
+                const uint32_t n_strips = min(P.strips_per_item, g - c0);
+                unsigned char* image = images + (size_t)b * P.image_bytes;
+                mbar_wait(&H.full[b], use & 1u);          // every compute warp has written (and proxy-fenced) its records
+                fence_proxy_async();
+                unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
+                                     ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
+                for (uint32_t s = 0; s < n_strips; ++s)
+                    bulk_store(out + (size_t)s * strip_bytes, image + (size_t)s * strip_stride, strip_bytes);
+                bulk_commit();
+                bulk_wait_read<0>();                      // the TMA has read the image: hand it back
+                mbar_arrive(&H.empty[b]);
+            }
+            bulk_wait<0>();                               // all global writes complete before the CTA exits
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const FrameConsts F = make_frame_consts<SPHERICAL>(U);
     uint32_t it = 0;
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
         const uint32_t tile_index = w / P.items_per_tile;
         const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
         const uint32_t n_strips = min(P.strips_per_item, g - c0);
         const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
-        unsigned char* image = images + (size_t)(it % GEN_BUFFERS) * P.image_bytes;
-
-        // the bulk stores last issued from this buffer must have finished READING it
-        if (tid == 0) bulk_wait_read<GEN_BUFFERS - 1>();
-        __syncthreads();
+        unsigned char* image = images + (size_t)b * P.image_bytes;
+        if (use > 0u) mbar_wait(&H.empty[b], (use - 1u) & 1u);   // the stores of the previous user of image b have read it
 
         const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
         const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
         const uint32_t n_verts = n_cols * n_rows;
+        const uint32_t n_chunks = (n_verts + 31u) >> 5;
         const uint32_t magic = 0xFFFFFFFFu / n_cols + 1u;   // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32
-        for (uint32_t i = tid; i < n_verts; i += GEN_THREADS) {
-            const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
-            const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
-            // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
-            if (lx < n_strips) {
-                store_record(image, strip_stride, lx, 2u * gy + 1u, r);
-                if (gy == 0u) store_record(image, strip_stride, lx, 0u, r);
-            }
-            // strip `lx-1`: this vertex is (column+1, row 2*gy+1) -> position 2*gy+2 (+ duplicated last index)
-            if (lx >= 1u) {
-                store_record(image, strip_stride, lx - 1u, 2u * gy + 2u, r);
-                if (gy == g) store_record(image, strip_stride, lx - 1u, vpr - 1u, r);
+        // chunk c of this item goes to warp (c + rotation) mod GEN_COMPUTE_WARPS; the rotation spreads the ragged tail
+        const uint32_t rot = (it * 11u) % GEN_COMPUTE_WARPS;
+        uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;
+        if (first >= GEN_COMPUTE_WARPS) first -= GEN_COMPUTE_WARPS;
+        for (uint32_t c = first; c < n_chunks; c += GEN_COMPUTE_WARPS) {
+            const uint32_t i = (c << 5) + (uint32_t)lane;
+            if (i < n_verts) {
+                const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
+                const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
+                // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
+                if (lx < n_strips) {
+                    store_record(image, strip_stride, lx, 2u * gy + 1u, r);
+                    if (gy == 0u) store_record(image, strip_stride, lx, 0u, r);
+                }
+                // strip `lx-1`: this vertex is (column+1, row 2*gy+1) -> position 2*gy+2 (+ duplicated last index)
+                if (lx >= 1u) {
+                    store_record(image, strip_stride, lx - 1u, 2u * gy + 2u, r);
+                    if (gy == g) store_record(image, strip_stride, lx - 1u, vpr - 1u, r);
+                }
             }
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
-                                 ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
-            for (uint32_t s = 0; s < n_strips; ++s)
-                bulk_store(out + (size_t)s * strip_bytes, image + (size_t)s * strip_stride, strip_bytes);
-            bulk_commit();
-        }
+        fence_proxy_async();   // this lane's generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&H.full[b]);
     }
-    if (tid == 0) bulk_wait<0>();
 }
 
 }  // namespace btd
