@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbevy_terrain_b200.so")
+# BT_LIB_PATH lets kernel A/B experiments point at an alternative build of the SAME library; there is still no fallback
+LIB_PATH = os.environ.get("BT_LIB_PATH") or os.path.join(_HERE, "csrc", "libbevy_terrain_b200.so")
 
 u32, i32, f32, f64, u64 = C.c_uint32, C.c_int32, C.c_float, C.c_double, C.c_uint64
 

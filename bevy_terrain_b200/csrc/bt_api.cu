@@ -394,19 +394,19 @@ bt_status bt_synth_source(bt_context* ctx, uint32_t format, uint32_t width, uint
     return BT_OK;
 }
 
-bt_status bt_selftest_numerics(bt_context* ctx, const float* x, float* log2_out, uint32_t n, uint32_t mismatches[3]) {
+bt_status bt_selftest_numerics(bt_context* ctx, const float* x, float* log2_out, uint32_t n, uint32_t mismatches[4]) {
     if (!ctx || !mismatches || (n && (!x || !log2_out))) return BT_ERR_INVALID_ARG;
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
     float *dx = nullptr, *dy = nullptr;
     uint32_t* dm = nullptr;
     BT_CUDA(ctx, cudaMalloc((void**)&dx, (size_t)(n ? n : 1) * sizeof(float)));
     BT_CUDA(ctx, cudaMalloc((void**)&dy, (size_t)(n ? n : 1) * sizeof(float)));
-    BT_CUDA(ctx, cudaMalloc((void**)&dm, 3 * sizeof(uint32_t)));
-    BT_CUDA(ctx, cudaMemset(dm, 0, 3 * sizeof(uint32_t)));
+    BT_CUDA(ctx, cudaMalloc((void**)&dm, 4 * sizeof(uint32_t)));
+    BT_CUDA(ctx, cudaMemset(dm, 0, 4 * sizeof(uint32_t)));
     if (n) BT_CUDA(ctx, cudaMemcpy(dx, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
     BT_CUDA(ctx, bt_launch_selftest(dx, dy, n, dm, nullptr));
     if (n) BT_CUDA(ctx, cudaMemcpy(log2_out, dy, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    BT_CUDA(ctx, cudaMemcpy(mismatches, dm, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    BT_CUDA(ctx, cudaMemcpy(mismatches, dm, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(dm);
     return BT_OK;
 }

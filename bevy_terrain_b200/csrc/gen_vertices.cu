@@ -25,7 +25,10 @@
 
 namespace btd {
 
-constexpr int GEN_COMPUTE_WARPS = 23;  // compute warps per CTA (+ 1 store warp): 24 warps, one CTA per SM
+#ifndef BT_GEN_COMPUTE_WARPS
+#define BT_GEN_COMPUTE_WARPS 23
+#endif
+constexpr int GEN_COMPUTE_WARPS = BT_GEN_COMPUTE_WARPS;  // compute warps per CTA (+ 1 store warp), one CTA per SM
 constexpr int GEN_THREADS = (GEN_COMPUTE_WARPS + 1) * 32;
 constexpr int GEN_CTAS_PER_SM = 1;
 constexpr int GEN_BUFFERS = 2;         // output images per CTA: compute of item i+1 overlaps the TMA stores of item i

@@ -602,6 +602,8 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
         const bool ordinary = fabsf(b) >= 1.17549435e-38f && fabsf(b) < 1e37f && fabsf(a) < 1e37f &&
                               (q == 0.0f ? a == 0.0f : (fabsf(q) >= 1.17549435e-38f && fabsf(q) < 1e37f));
         if (ordinary && div_rn(a, b) != q) atomicAdd(&mismatches[2], 1u);
+        const float ax = fabsf(a);
+        if (ax >= 1.17549435e-38f && ax < 1e37f && sqrt_rn(ax) != sqrtf(ax)) atomicAdd(&mismatches[3], 1u);
     }
 }
 }  // namespace btd
