@@ -97,7 +97,8 @@ def test_full_frame_vertices(ctx, pyramid):
             assert np.array_equal(v[:-1, 2::2]["position"][:, :65], v[1:, 1::2]["position"][:, :65])
             assert (v["tile_index"] == t).all()
             nrm = np.linalg.norm(v["normal"].astype(np.float64), axis=-1)
-            assert np.abs(nrm - 1.0).max() < 1e-5
+            # blended normals are mix(n_a, n_b, ratio) without renormalisation (fragment.wgsl:103-107): |n| <= 1
+            assert nrm.max() <= 1.0 + 1e-5 and nrm.min() > 0.5
             y = v["position"][..., 1]
             assert y.min() >= -100.0 - 1e-3 and y.max() <= 400.0 + 1e-3
         # bit-exact against the oracle on whole tiles, with the product's own inputs (atlas + table downloaded)
