@@ -39,8 +39,8 @@ VIEW_SEED = 0x5EED0010
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--source", type=int, default=4096, help="config-2 heightmap size")
     ap.add_argument("--lods", type=int, default=8)
