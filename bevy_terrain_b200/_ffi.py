@@ -171,6 +171,8 @@ def _declare(lib: C.CDLL) -> None:
         "bt_atlas_upload_tile": (i32, [vp, u32, u32, vp, C.c_size_t, vp]),
         "bt_atlas_copy_tile": (i32, [vp, u32, u32, vp, C.c_size_t, vp]),
         "bt_atlas_download_tile": (i32, [vp, u32, u32, vp, C.c_size_t]),
+        "bt_atlas_load_tile_file": (i32, [vp, u32, u32, C.c_char_p, P(Tile), vp]),
+        "bt_tile_config_load": (i32, [C.c_char_p, P(Tile), u32, P(u32)]),
         "bt_atlas_device_ptr": (i32, [vp, u32, P(vp)]),
         "bt_view_create": (i32, [vp, P(ViewDesc), P(vp)]),
         "bt_view_destroy": (None, [vp]),

@@ -193,6 +193,11 @@ class TileAtlas:
         nbytes = a.texture_size * a.texture_size * a.pixel_size
         self.ctx.check(self.ctx.lib.bt_atlas_copy_tile(self._h, attachment, atlas_index, C.c_void_p(device_ptr), nbytes, C.c_void_p(stream)))
 
+    def load_tile_file(self, attachment: int, atlas_index: int, directory: str, tile, stream: int = 0) -> None:
+        """AtlasTileAttachmentWithData::start_loading (tile_atlas.rs:118-149), raw .bin variant"""
+        t = F.Tile(*[int(v) for v in tile])
+        self.ctx.check(self.ctx.lib.bt_atlas_load_tile_file(self._h, attachment, atlas_index, directory.encode(), C.byref(t), C.c_void_p(stream)))
+
     def download_tile(self, attachment: int, atlas_index: int) -> np.ndarray:
         dt, shape = self.attachments[attachment].dtype_shape
         out = np.empty(shape, dtype=dt)
@@ -465,6 +470,18 @@ class Preprocessor:
         if self._h:
             self.ctx.lib.bt_preprocessor_destroy(self._h)
             self._h = C.c_void_p()
+
+
+def load_tile_config(path: str) -> np.ndarray:
+    """TileAtlas::load_tile_config (tile_atlas.rs:616-623): the tiles listed in config.tc as an (n, 4) uint32 array"""
+    lib = F.load_library()
+    n = F.u32()
+    if lib.bt_tile_config_load(path.encode(), None, 0, C.byref(n)) != F.BT_OK:
+        raise F.BtError(F.BT_ERR_IO, f"cannot read {path}")
+    out = np.empty((n.value, 4), dtype=np.uint32)
+    if n.value:
+        lib.bt_tile_config_load(path.encode(), out.ctypes.data_as(C.POINTER(F.Tile)), n.value, C.byref(n))
+    return out
 
 
 def load_resident_tiles(tile_tree: TileTree, preprocessor: Preprocessor, view_world_position, attachments: Iterable[int] = (0,), stream: int = 0) -> int:

@@ -112,6 +112,8 @@ void bt_terrain_destroy(bt_terrain* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     for (int i = 0; i < 8; ++i) if (t->atlas[i]) cudaFree(t->atlas[i]);
+    if (t->h_stage) cudaFreeHost(t->h_stage);
+    if (t->stage_free) cudaEventDestroy(t->stage_free);
     delete t;
 }
 
@@ -153,6 +155,69 @@ bt_status bt_atlas_download_tile(bt_terrain* t, uint32_t attachment, uint32_t at
     if (s != BT_OK) return s;
     BT_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
     BT_CUDA(t->ctx, cudaMemcpy(texels, src, bytes, cudaMemcpyDeviceToHost));
+    return BT_OK;
+}
+
+bt_status bt_atlas_load_tile_file(bt_terrain* t, uint32_t attachment, uint32_t atlas_index, const char* directory, const bt_tile* tile, void* stream) {
+    if (!t || !directory || !tile || attachment >= t->desc.attachment_count) return BT_ERR_INVALID_ARG;
+    unsigned char* dst;
+    const size_t bytes = t->tile_bytes[attachment];
+    bt_status s = atlas_slot(t, attachment, atlas_index, bytes, &dst);
+    if (s != BT_OK) return s;
+    bt_context* ctx = t->ctx;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (t->h_stage_bytes < bytes) {
+        if (t->h_stage) BT_CUDA(ctx, cudaFreeHost(t->h_stage));
+        t->h_stage = nullptr;
+        BT_CUDA(ctx, cudaHostAlloc(&t->h_stage, bytes, cudaHostAllocDefault));
+        t->h_stage_bytes = bytes;
+    }
+    if (!t->stage_free) BT_CUDA(ctx, cudaEventCreateWithFlags(&t->stage_free, cudaEventDisableTiming));
+    BT_CUDA(ctx, cudaEventSynchronize(t->stage_free));  // the previous copy out of the staging buffer has finished
+    const std::string path = std::string(directory) + "/" + std::to_string(tile->side) + "_" + std::to_string(tile->lod) + "_" +
+                             std::to_string(tile->x) + "_" + std::to_string(tile->y) + ".bin";   // TileCoordinate::path, coordinate.rs:184-186,282-285
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) { ctx->set_error("bt_atlas_load_tile_file: cannot open %s", path.c_str()); return BT_ERR_IO; }
+    const size_t got = std::fread(t->h_stage, 1, bytes, f);
+    const bool extra = std::fgetc(f) != EOF;
+    std::fclose(f);
+    if (got != bytes || extra) { ctx->set_error("bt_atlas_load_tile_file: %s holds %zu%s bytes, expected %zu", path.c_str(), got, extra ? "+" : "", bytes); return BT_ERR_IO; }
+    BT_CUDA(ctx, cudaMemcpyAsync(dst, t->h_stage, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    BT_CUDA(ctx, cudaEventRecord(t->stage_free, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_tile_config_load(const char* path, bt_tile* tiles, uint32_t capacity, uint32_t* count) {
+    if (!path || !count) return BT_ERR_INVALID_ARG;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return BT_ERR_IO;
+    std::vector<unsigned char> buf;
+    unsigned char chunk[4096];
+    size_t n;
+    while ((n = std::fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + n);
+    std::fclose(f);
+    size_t pos = 0;
+    auto varint = [&](uint64_t* out) -> bool {  // bincode 2 "standard" varint
+        if (pos >= buf.size()) return false;
+        const unsigned char b = buf[pos++];
+        if (b < 251) { *out = b; return true; }
+        const size_t len = b == 251 ? 2 : b == 252 ? 4 : b == 253 ? 8 : 0;
+        if (len == 0 || pos + len > buf.size()) return false;
+        uint64_t v = 0;
+        for (size_t i = 0; i < len; ++i) v |= (uint64_t)buf[pos + i] << (8 * i);
+        pos += len;
+        *out = v;
+        return true;
+    };
+    uint64_t total;
+    if (!varint(&total) || total > 0xFFFFFFFFull) return BT_ERR_IO;
+    for (uint64_t i = 0; i < total; ++i) {
+        uint64_t v[4];
+        for (int k = 0; k < 4; ++k) if (!varint(&v[k]) || v[k] > 0xFFFFFFFFull) return BT_ERR_IO;
+        if (tiles && i < capacity) tiles[i] = bt_tile{(uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]};
+    }
+    if (pos != buf.size()) return BT_ERR_IO;
+    *count = (uint32_t)total;
     return BT_OK;
 }
 

@@ -33,6 +33,9 @@ struct bt_terrain {
     bt_terrain_desc desc{};
     void* atlas[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t tile_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* h_stage = nullptr;        // pinned staging for file loads
+    size_t h_stage_bytes = 0;
+    cudaEvent_t stage_free = nullptr;
 };
 
 struct bt_view {

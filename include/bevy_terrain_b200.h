@@ -227,6 +227,13 @@ bt_status bt_atlas_copy_tile(bt_terrain* terrain, uint32_t attachment, uint32_t 
                              const void* device_texels, size_t bytes, void* stream);
 bt_status bt_atlas_download_tile(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index,
                                  void* texels, size_t bytes);
+/* Tile streaming from disk = AtlasTileAttachmentWithData::start_loading (tile_atlas.rs:118-149) with STORE_PNG = false:
+ * reads <directory>/<side>_<lod>_<x>_<y>.bin (raw mip-0 texels, as written by bt_preprocessor_save / the reference's
+ * Save tasks) through a pinned staging buffer into the atlas slot.  Returns BT_ERR_IO if the file is missing or short. */
+bt_status bt_atlas_load_tile_file(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index, const char* directory,
+                                  const bt_tile* tile, void* stream);
+/* TC::load_file / decode_alloc (formats/mod.rs:14-31): bincode-standard Vec<TileCoordinate>; *count receives the total */
+bt_status bt_tile_config_load(const char* path, bt_tile* tiles, uint32_t capacity, uint32_t* count);
 /* device base pointer of an attachment's atlas array (for zero-copy interop / tests) */
 bt_status bt_atlas_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out);
 

@@ -174,6 +174,20 @@ def test_save_writes_reference_tile_files_and_config_tc(ctx, tmp_path):
                 vals.append(v)
             listed.add(tuple(vals))
         assert pos == len(buf) and listed == tiles and n == 21
+        # ... and back: config.tc through the C decoder, tiles streamed from the files into an atlas
+        cfg_tiles = api.load_tile_config(str(tmp_path / "config.tc"))
+        assert {tuple(int(v) for v in t) for t in cfg_tiles} == tiles
+        atlas = api.TileAtlas(ctx, _config(api, F.BT_KIND_PLANAR, L, T, B, F.BT_FORMAT_R16))
+        try:
+            for i, tc in enumerate(sorted(tiles)):
+                atlas.load_tile_file(0, i, str(tmp_path), tc)
+            for i, tc in enumerate(sorted(tiles)):
+                assert np.array_equal(atlas.download_tile(0, i), pre.get_tile(0, tc))
+            with pytest.raises(F.BtError) as e:
+                atlas.load_tile_file(0, 0, str(tmp_path), (0, 9, 9, 9))
+            assert e.value.status == F.BT_ERR_IO
+        finally:
+            atlas.close()
     finally:
         pre.close()
 
