@@ -218,6 +218,7 @@ def _declare(lib: C.CDLL) -> None:
         "bt_preprocessor_tile_device_ptr": (i32, [vp, u32, P(Tile), P(vp)]),
         "bt_preprocessor_get_tile": (i32, [vp, u32, P(Tile), vp, C.c_size_t]),
         "bt_preprocessor_save": (i32, [vp, u32, C.c_char_p]),
+        "bt_culling_planes": (None, [P(f32), P(f32 * 4)]),
         "bt_generate_mipmaps": (i32, [vp, u32, u32, u32, vp, vp, vp]),
         "bt_synth_source": (i32, [vp, u32, u32, u32, u32, u32, u32, u32, vp, vp]),
         "bt_selftest_numerics": (i32, [vp, P(f32), P(f32), u32, P(u32)]),

@@ -344,13 +344,9 @@ bt_status bt_select_tiles(bt_view* v, uint32_t flags, void* stream) {
     if (!v) return BT_ERR_INVALID_ARG;
     bt_context* ctx = v->terrain->ctx;
     if (!v->updated) { ctx->set_error("bt_select_tiles: bt_view_update has not been called"); return BT_ERR_INVALID_ARG; }
-    if (flags & BT_FLAG_FRUSTUM_CULL) {
-        ctx->set_error("bt_select_tiles: BT_FLAG_FRUSTUM_CULL is not implemented (the reference does not cull at this commit either)");
-        return BT_ERR_INVALID_ARG;
-    }
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
     BT_CUDA(ctx, bt_launch_select_tiles(v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->desc.geometry_tile_count, v->d_indirect,
-                                        v->d_select_status, v->terrain->desc.kind == BT_KIND_SPHERICAL, (cudaStream_t)stream));
+                                        v->d_select_status, v->terrain->desc.kind == BT_KIND_SPHERICAL, flags, (cudaStream_t)stream));
     return BT_OK;
 }
 
@@ -443,6 +439,16 @@ bt_status bt_view_device_ptrs(bt_view* v, bt_tile** final_tiles, bt_indirect** i
 // ------------------------------------------------------------------------------------------------
 // utilities
 // ------------------------------------------------------------------------------------------------
+// planes() — src/render/culling_bind_group.rs:25-38 (Gribb-Hartmann rows of clip_from_world, column-major input)
+void bt_culling_planes(const float clip_from_world[16], float planes[5][4]) {
+    auto row = [&](int r, int c) { return clip_from_world[c * 4 + r]; };
+    for (int i = 0; i < 5; ++i) {
+        const int r = i / 2;
+        const bool add = (i & 1) == 0 && i != 4;
+        for (int c = 0; c < 4; ++c) planes[i][c] = add ? row(3, c) + row(r, c) : row(3, c) - row(r, c);
+    }
+}
+
 bt_status bt_generate_mipmaps(bt_context* ctx, uint32_t format, uint32_t texture_size, uint32_t mip_level_count,
                               const void* device_mip0, void* device_mips_out, void* stream) {
     if (!ctx || !device_mip0 || !device_mips_out || (format != BT_FORMAT_R16 && format != BT_FORMAT_RGBA8)) return BT_ERR_INVALID_ARG;

@@ -55,7 +55,7 @@ struct DatasetDevice {
 extern "C" {
 cudaError_t bt_launch_select_tiles(const void* uniforms, bt_tile* final_tiles, bt_tile* temporary_tiles,
                                    uint32_t capacity, bt_indirect* indirect, btd::SelectStatus* status,
-                                   int spherical, cudaStream_t stream);
+                                   int spherical, uint32_t flags, cudaStream_t stream);
 cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_tile* final_tiles, const bt_indirect* indirect,
                                    const bt_tile_tree_entry* tile_tree, const uint16_t* height_atlas,
                                    bt_vertex* vertices, uint64_t vertex_capacity, btd::GenStatus* status,

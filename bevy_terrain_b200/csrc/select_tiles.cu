@@ -47,6 +47,34 @@ __device__ __forceinline__ bool should_be_divided(const ViewUniforms& U, const b
     return d < U.view_config.subdivision_distance * exp2i(-(int)(tile.lod & 31u));
 }
 
+// EXTENSION (BT_FLAG_FRUSTUM_CULL, default off — the reference does not cull at this commit): ten bounding
+// points (four corners + centre, at min_height and max_height) against the five planes of culling_bind_group.rs:25-38;
+// culled when all ten lie on the negative side of one plane.  Same arithmetic as the oracle's tile_outside_frustum.
+template <bool SPHERICAL>
+__device__ __forceinline__ bool tile_outside_frustum(const ViewUniforms& U, const bt_tile& tile) {
+    uint32_t outside = 0x1Fu;  // bit p: all points so far are outside plane p
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float u = i == 4 ? 0.5f : (float)(i & 1), v = i == 4 ? 0.5f : (float)(i >> 1);
+        const Coord c{tile.side, tile.lod, tile.x, tile.y, u, v};
+        const Vec3 lp = local_position<SPHERICAL>(c);
+        const Vec3 wp = position_local_to_world(U.mesh, lp);
+        const Vec3 wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const float h = hsel ? U.terrain_config.max_height : U.terrain_config.min_height;
+            const Vec3 q{wp.x + h * wn.x, wp.y + h * wn.y, wp.z + h * wn.z};
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const float* pl = U.culling.planes[p];
+                const float dist = ((pl[0] * q.x + pl[1] * q.y) + pl[2] * q.z) + pl[3];
+                if (!(dist < 0.0f)) outside &= ~(1u << p);
+            }
+        }
+    }
+    return outside != 0u;
+}
+
 struct SelectSmem {
     ViewUniforms U;
     uint64_t bar;
@@ -59,8 +87,8 @@ struct SelectSmem {
 template <bool SPHERICAL>
 __global__ void __launch_bounds__(SELECT_THREADS, 1)
 select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restrict__ final_tiles,
-                    bt_tile* __restrict__ temporary_tiles, uint32_t capacity, bt_indirect* __restrict__ indirect,
-                    SelectStatus* __restrict__ status) {
+                    bt_tile* temporary_tiles, uint32_t capacity, bt_indirect* __restrict__ indirect,
+                    SelectStatus* __restrict__ status, uint32_t flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SelectSmem& S = *reinterpret_cast<SelectSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -105,7 +133,8 @@ select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restri
             bool valid = i < n_cur, divide = false;
             if (valid) {
                 tile = cur[i];
-                divide = should_be_divided<SPHERICAL>(U, tile);
+                if ((flags & BT_FLAG_FRUSTUM_CULL) && tile_outside_frustum<SPHERICAL>(U, tile)) valid = false;  // culled: neither refined nor emitted
+                else divide = should_be_divided<SPHERICAL>(U, tile);
             }
             const uint32_t div_mask = __ballot_sync(0xffffffffu, valid && divide);
             const uint32_t fin_mask = __ballot_sync(0xffffffffu, valid && !divide);
@@ -172,7 +201,7 @@ select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restri
 
 extern "C" cudaError_t bt_launch_select_tiles(const void* uniforms, bt_tile* final_tiles, bt_tile* temporary_tiles,
                                               uint32_t capacity, bt_indirect* indirect, btd::SelectStatus* status,
-                                              int spherical, cudaStream_t stream) {
+                                              int spherical, uint32_t flags, cudaStream_t stream) {
     using namespace btd;
     const size_t smem = sizeof(SelectSmem);
     cudaError_t e = cudaFuncSetAttribute(spherical ? select_tiles_kernel<true> : select_tiles_kernel<false>,
@@ -180,8 +209,8 @@ extern "C" cudaError_t bt_launch_select_tiles(const void* uniforms, bt_tile* fin
     if (e != cudaSuccess) return e;
     const ViewUniforms* u = static_cast<const ViewUniforms*>(uniforms);
     if (spherical)
-        select_tiles_kernel<true><<<1, SELECT_THREADS, smem, stream>>>(u, final_tiles, temporary_tiles, capacity, indirect, status);
+        select_tiles_kernel<true><<<1, SELECT_THREADS, smem, stream>>>(u, final_tiles, temporary_tiles, capacity, indirect, status, flags);
     else
-        select_tiles_kernel<false><<<1, SELECT_THREADS, smem, stream>>>(u, final_tiles, temporary_tiles, capacity, indirect, status);
+        select_tiles_kernel<false><<<1, SELECT_THREADS, smem, stream>>>(u, final_tiles, temporary_tiles, capacity, indirect, status, flags);
     return cudaGetLastError();
 }

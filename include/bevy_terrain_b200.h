@@ -155,7 +155,9 @@ enum {
     BT_FLAG_BLEND          = 1u << 2,
     BT_FLAG_HIGH_PRECISION = 1u << 3,
     BT_FLAG_NORMALS        = 1u << 4,  /* fuse sample_normal into the vertex record            */
-    BT_FLAG_FRUSTUM_CULL   = 1u << 6   /* extension; default off = reference behaviour          */
+    BT_FLAG_FRUSTUM_CULL   = 1u << 6   /* bt_select_tiles extension; default off = reference behaviour: tiles whose
+                                          ten bounding points (corners + centre at min/max height) lie outside
+                                          one of culling.planes[5] are neither refined nor emitted            */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -415,6 +417,9 @@ bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const ch
 /* ------------------------------------------------------------------------------------------ */
 /* utilities                                                                                   */
 /* ------------------------------------------------------------------------------------------ */
+/* planes() of src/render/culling_bind_group.rs:25-38 from a column-major clip_from_world matrix (never called by the
+ * reference at this commit; feeds bt_culling_uniform.planes for BT_FLAG_FRUSTUM_CULL) */
+void bt_culling_planes(const float clip_from_world[16], float planes[5][4]);
 /* CPU mip chain at tile load (AttachmentData::generate_mipmaps, terrain_data/mod.rs:143-219)
  * is replaced by a device kernel operating on an uploaded tile; out is a device pointer pair.  */
 bt_status bt_generate_mipmaps(bt_context* ctx, uint32_t format, uint32_t texture_size, uint32_t mip_level_count,

@@ -215,10 +215,45 @@ static int should_be_divided(const bt_view_config_uniform* vc, const bt_model_ap
     return d < vc->subdivision_distance / o_tile_count(tile->lod);
 }
 
+/* EXTENSION (default off, not in the reference at this commit: SURVEY F4): frustum culling of tiles against the five
+ * planes of culling_bind_group.rs:25-38, with the bounding volume docs/implementation.md:69-70 describes approximated
+ * by ten points: the four tile corners and the tile centre, each at min_height and max_height.  A tile is culled when
+ * all ten points lie on the negative side of one plane. */
+static int tile_outside_frustum(const bt_culling_uniform* cull, const bt_mesh_transform* mesh, int spherical,
+                                float min_height, float max_height, const bt_tile* tile) {
+    static const float UV[5][2] = {{0.0f, 0.0f}, {1.0f, 0.0f}, {0.0f, 1.0f}, {1.0f, 1.0f}, {0.5f, 0.5f}};
+    float pts[10][3];
+    for (int i = 0; i < 5; ++i) {
+        coord c = {tile->side, tile->lod, {tile->x, tile->y}, {UV[i][0], UV[i][1]}};
+        float lp[3], wp[3], wn[3];
+        local_position(spherical, &c, lp);
+        position_local_to_world(mesh, lp, wp);
+        normal_local_to_world(mesh, spherical, lp, wn);
+        for (int k = 0; k < 3; ++k) { pts[2 * i][k] = wp[k] + min_height * wn[k]; pts[2 * i + 1][k] = wp[k] + max_height * wn[k]; }
+    }
+    for (int p = 0; p < 5; ++p) {
+        const float* pl = cull->planes[p];
+        int all_out = 1;
+        for (int i = 0; i < 10; ++i) {
+            float dist = ((pl[0] * pts[i][0] + pl[1] * pts[i][1]) + pl[2] * pts[i][2]) + pl[3];
+            if (!(dist < 0.0f)) { all_out = 0; break; }
+        }
+        if (all_out) return 1;
+    }
+    return 0;
+}
+
 void bto_select_tiles(const bt_view_config_uniform* vc, const bt_model_approximation* approx,
                       const bt_culling_uniform* culling, const bt_mesh_transform* mesh,
                       int spherical, bt_tile* final_tiles, uint32_t capacity,
                       bt_indirect* indirect, bto_select_result* result) {
+    bto_select_tiles_ex(vc, approx, culling, mesh, spherical, 0, 0.0f, 0.0f, final_tiles, capacity, indirect, result);
+}
+
+void bto_select_tiles_ex(const bt_view_config_uniform* vc, const bt_model_approximation* approx,
+                         const bt_culling_uniform* culling, const bt_mesh_transform* mesh,
+                         int spherical, int frustum_cull, float min_height, float max_height,
+                         bt_tile* final_tiles, uint32_t capacity, bt_indirect* indirect, bto_select_result* result) {
     /* The reference keeps parents and children in ONE buffer used as a double-ended stack
      * (refine_tiles.wgsl:9-11); executed with invocations in id order this is a FIFO queue:
      * children are read back in the order they were written.  We keep two growable arrays.   */
@@ -233,6 +268,7 @@ void bto_select_tiles(const bt_view_config_uniform* vc, const bt_model_approxima
         uint32_t n_nxt = 0;
         for (uint32_t i = 0; i < n_cur; ++i) {
             bt_tile tile = cur[i];
+            if (frustum_cull && tile_outside_frustum(culling, mesh, spherical, min_height, max_height, &tile)) continue;
             if (should_be_divided(vc, approx, culling, mesh, spherical, &tile)) {
                 if ((size_t)n_nxt + 4 > cap_b) { cap_b *= 2; nxt = (bt_tile*)realloc(nxt, cap_b * sizeof(bt_tile)); }
                 for (uint32_t c = 0; c < 4; ++c) { /* subdivide — refine_tiles.wgsl:24-31 */

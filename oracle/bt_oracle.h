@@ -38,6 +38,12 @@ void bto_select_tiles(const bt_view_config_uniform* vc, const bt_model_approxima
                       int spherical, bt_tile* final_tiles, uint32_t capacity,
                       bt_indirect* indirect, bto_select_result* result);
 
+/* with the opt-in frustum-cull extension (BT_FLAG_FRUSTUM_CULL) */
+void bto_select_tiles_ex(const bt_view_config_uniform* vc, const bt_model_approximation* approx,
+                         const bt_culling_uniform* culling, const bt_mesh_transform* mesh,
+                         int spherical, int frustum_cull, float min_height, float max_height,
+                         bt_tile* final_tiles, uint32_t capacity, bt_indirect* indirect, bto_select_result* result);
+
 /* ---- per-frame: vertex generation ---- */
 typedef struct bto_vertex_inputs {
     bt_view_config_uniform    view_config;

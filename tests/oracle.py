@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         "bto_local_position": (None, [i32, u32, u32, P(u32), P(f32), P(f32)]),
         "bto_select_tiles": (None, [P(F.ViewConfigUniform), P(F.ModelApproximation), P(F.CullingUniform),
                                     P(F.MeshTransform), i32, P(F.Tile), u32, P(F.Indirect), P(SelectResult)]),
+        "bto_select_tiles_ex": (None, [P(F.ViewConfigUniform), P(F.ModelApproximation), P(F.CullingUniform), P(F.MeshTransform), i32, i32,
+                                       f32, f32, P(F.Tile), u32, P(F.Indirect), P(SelectResult)]),
         "bto_gen_vertices": (None, [P(VertexInputs), u64, u64, vp, i32]),
         "bto_pyramid_create": (vp, [u32, u32, u32, u32, u32]),
         "bto_pyramid_destroy": (None, [vp]),
@@ -164,13 +166,14 @@ def culling(view_pos) -> F.CullingUniform:
     return c
 
 
-def select_tiles(vc, approx, cull, mesh, spherical: bool, capacity: int | None = None):
+def select_tiles(vc, approx, cull, mesh, spherical: bool, capacity: int | None = None, frustum_cull: bool = False,
+                 min_height: float = 0.0, max_height: float = 0.0):
     cap = capacity if capacity is not None else vc.geometry_tile_count
     tiles = (F.Tile * cap)()
     ind = F.Indirect()
     res = SelectResult()
-    lib().bto_select_tiles(C.byref(vc), C.byref(approx), C.byref(cull), C.byref(mesh), int(spherical), tiles, cap,
-                           C.byref(ind), C.byref(res))
+    lib().bto_select_tiles_ex(C.byref(vc), C.byref(approx), C.byref(cull), C.byref(mesh), int(spherical), int(frustum_cull),
+                              min_height, max_height, tiles, cap, C.byref(ind), C.byref(res))
     arr = np.frombuffer(tiles, dtype=np.uint32).reshape(-1, 4)[: res.final_count].copy()
     return arr, ind, res
 
