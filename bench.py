@@ -249,6 +249,24 @@ def run_b200(args):
     w1 = time.time()
     e2e_ms = max(f0.elapsed_time(f1), (w1 - w0) * 1e3)   # the blocking readback makes wall >= device time
 
+    # ---- flag variants (short device-resident runs; informational) --------------------------------------
+    variants = {}
+    for name, vflags in (("reference_default_MORPH_BLEND_plus_NORMALS", F.BT_FLAG_MORPH | F.BT_FLAG_BLEND | F.BT_FLAG_NORMALS),
+                         ("vertex_stage_only_no_normals", 0), ("MORPH_BLEND_no_normals", F.BT_FLAG_MORPH | F.BT_FLAG_BLEND)):
+        for i in range(3):
+            views[i % NUM_VIEWS]["tree"].gen_vertices(vflags)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nv = 0
+        g0.record()
+        for i in range(16):
+            views[i % NUM_VIEWS]["tree"].select_tiles()
+            views[i % NUM_VIEWS]["tree"].gen_vertices(vflags)
+            nv += views[i % NUM_VIEWS]["verts"]
+        g1.record()
+        torch.cuda.synchronize()
+        variants[name] = {"Mverts_per_s": nv / (g0.elapsed_time(g1) * 1e-3) / 1e6, "ms_per_step": g0.elapsed_time(g1) / 16}
+
     # ---- reduce over ranks (max time, sum work) ---------------------------------------------------------
     def reduce(vals, op):
         if world == 1:
@@ -317,6 +335,7 @@ def run_b200(args):
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "frame": frame_state,
+            "variants_rank0": variants,
             "preprocess": preprocess,
         }
         emit(out)
