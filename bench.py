@@ -204,10 +204,9 @@ def run_b200(args):
     def step_e2e(i):
         v = views[i % NUM_VIEWS]
         t = v["tree"]
-        t.prepare()                      # host f64 Taylor approximation + H2D (pinned) of uniforms and tile-tree table
-        t.select_tiles()
-        t.gen_vertices(flags)
-        tiles, ind = t.readback()        # D2H: tile list + indirect record (blocking)
+        # bt_view_run_frame: host f64 Taylor approximation + H2D (pinned) of uniforms and tile-tree table, select_tiles,
+        # gen_vertices, and the D2H of tile list + indirect record (blocking for the host; overlaps gen_vertices on the device)
+        tiles, ind, _ = t.frame_step(flags)
         return int(ind.vertex_count), len(tiles)
 
     # ---- device-resident timed region --------------------------------------------------------------

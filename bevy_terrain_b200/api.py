@@ -295,6 +295,31 @@ class TileTree:
         self.ctx.check(self.ctx.lib.bt_view_update(self._view, C.byref(f), C.c_void_p(stream)))
         return f
 
+    def build_frame(self) -> F.ViewFrame:
+        """the host half of Prepare: fills self.frame from the tree's current state (no device work)"""
+        f = self.frame
+        f.view_config = self.view_config_uniform
+        vp = (F.f64 * 3)(*self.view_world_position)
+        self.ctx.check(self.ctx.lib.bt_model_approximation_compute(C.byref(self.model.c), vp, self.view_config.origin_lod,
+                                                                   self.approximate_height, C.byref(f.approximation)))
+        pos32 = [float(np.float32(v)) for v in self.view_world_position]
+        f.culling.world_position[:] = pos32
+        f.view_world_position[:] = pos32
+        f.tile_tree_entry_count = self.entry_count
+        f.tile_tree = C.cast(self.entries, C.POINTER(F.TileTreeEntry))
+        f.origins = C.cast(self.origins, C.POINTER(F.u32))
+        return f
+
+    def frame_step(self, gen_flags: int, select_flags: int = 0, stream: int = 0, tile_capacity: int = 8192):
+        """one frame through bt_view_run_frame: upload + select + gen_vertices + overlapped tile-list read-back"""
+        if getattr(self, "_tile_buf_cap", 0) < tile_capacity:
+            self._tile_buf = np.empty((tile_capacity, 4), dtype=np.uint32)
+            self._tile_buf_cap = tile_capacity
+        n, ind, vb = F.u32(), F.Indirect(), F.VertexBuffer()
+        self.ctx.check(self.ctx.lib.bt_view_run_frame(self._view, C.byref(self.build_frame()), select_flags, gen_flags, C.c_void_p(stream),
+                                                  self._tile_buf.ctypes.data_as(C.POINTER(F.Tile)), tile_capacity, C.byref(n), C.byref(ind), C.byref(vb)))
+        return self._tile_buf[: min(n.value, tile_capacity)], ind, vb
+
     # -- render graph: TilingPrepassNode::run + the draw's vertex stage -------------------------------
     def select_tiles(self, flags: int = 0, stream: int = 0) -> None:
         self.ctx.check(self.ctx.lib.bt_select_tiles(self._view, flags, C.c_void_p(stream)))

@@ -285,6 +285,10 @@ void bt_view_destroy(bt_view* v) {
     if (v->h_tile_tree) cudaFreeHost(v->h_tile_tree);
     if (v->h_readback) cudaFreeHost(v->h_readback);
     if (v->staging_free) cudaEventDestroy(v->staging_free);
+    if (v->select_done) cudaEventDestroy(v->select_done);
+    if (v->copy_done) cudaEventDestroy(v->copy_done);
+    if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+    if (v->h_tiles) cudaFreeHost(v->h_tiles);
     delete v;
 }
 
@@ -400,6 +404,54 @@ bt_status bt_view_readback(bt_view* v, bt_tile* tiles, uint32_t capacity, uint32
         }
     }
     if (st.overflow) { ctx->set_error("select_tiles: tile list exceeded geometry_tile_count = %u", v->desc.geometry_tile_count); return BT_ERR_CAPACITY; }
+    return BT_OK;
+}
+
+// One frame of one (terrain, view) pair in a single call: Prepare-stage uploads, TilingPrepassNode::run, the vertex stage,
+// and the host read-back of the tile list + indirect record.  The read-back is issued on an internal copy stream right after
+// select_tiles and overlaps gen_vertices; the call returns when the tile list is on the host while gen_vertices may still be
+// running on `stream` (stream-ordered: the next frame's work queues behind it).  The vertex buffer stays on the device.
+bt_status bt_view_run_frame(bt_view* v, const bt_view_frame* frame, uint32_t select_flags, uint32_t gen_flags, void* stream,
+                        bt_tile* tiles, uint32_t capacity, uint32_t* count, bt_indirect* indirect, bt_vertex_buffer* vertices) {
+    if (!v || !frame) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    if (v->desc.max_vertices == 0) { ctx->set_error("bt_view_run_frame: needs a view created with max_vertices (no blocking growth on the frame path)"); return BT_ERR_INVALID_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!v->copy_stream) {
+        BT_CUDA(ctx, cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+        BT_CUDA(ctx, cudaEventCreateWithFlags(&v->select_done, cudaEventDisableTiming));
+        BT_CUDA(ctx, cudaEventCreateWithFlags(&v->copy_done, cudaEventDisableTiming));
+    }
+    const uint32_t want = tiles ? (capacity < v->desc.geometry_tile_count ? capacity : v->desc.geometry_tile_count) : 0u;
+    if (want > v->h_tiles_cap) {
+        if (v->h_tiles) BT_CUDA(ctx, cudaFreeHost(v->h_tiles));
+        v->h_tiles = nullptr;
+        BT_CUDA(ctx, cudaHostAlloc((void**)&v->h_tiles, (size_t)want * sizeof(bt_tile), cudaHostAllocDefault));
+        v->h_tiles_cap = want;
+    }
+    bt_status st = bt_view_update(v, frame, stream);
+    if (st != BT_OK) return st;
+    st = bt_select_tiles(v, select_flags, stream);
+    if (st != BT_OK) return st;
+    BT_CUDA(ctx, cudaEventRecord(v->select_done, s));
+    BT_CUDA(ctx, cudaStreamWaitEvent(v->copy_stream, v->select_done, 0));
+    unsigned char* hb = static_cast<unsigned char*>(v->h_readback);
+    BT_CUDA(ctx, cudaMemcpyAsync(hb, v->d_select_status, sizeof(btd::SelectStatus), cudaMemcpyDeviceToHost, v->copy_stream));
+    BT_CUDA(ctx, cudaMemcpyAsync(hb + sizeof(btd::SelectStatus), v->d_indirect, sizeof(bt_indirect), cudaMemcpyDeviceToHost, v->copy_stream));
+    if (want) BT_CUDA(ctx, cudaMemcpyAsync(v->h_tiles, v->d_final_tiles, (size_t)want * sizeof(bt_tile), cudaMemcpyDeviceToHost, v->copy_stream));
+    BT_CUDA(ctx, cudaEventRecord(v->copy_done, v->copy_stream));
+    st = bt_gen_vertices(v, gen_flags, stream, vertices);
+    if (st != BT_OK) return st;
+    // the next select on `stream` must not overwrite final_tiles / status while this copy is in flight
+    BT_CUDA(ctx, cudaStreamWaitEvent(s, v->copy_done, 0));
+    BT_CUDA(ctx, cudaEventSynchronize(v->copy_done));
+    btd::SelectStatus sst;
+    std::memcpy(&sst, hb, sizeof(sst));
+    if (indirect) std::memcpy(indirect, hb + sizeof(btd::SelectStatus), sizeof(bt_indirect));
+    if (count) *count = sst.final_count;
+    if (tiles) std::memcpy(tiles, v->h_tiles, (size_t)(sst.final_count < want ? sst.final_count : want) * sizeof(bt_tile));
+    if (sst.overflow) { ctx->set_error("select_tiles: tile list exceeded geometry_tile_count = %u", v->desc.geometry_tile_count); return BT_ERR_CAPACITY; }
     return BT_OK;
 }
 

@@ -55,6 +55,11 @@ struct bt_view {
     void* h_tile_tree = nullptr;
     void* h_readback = nullptr;
     cudaEvent_t staging_free = nullptr;
+    // bt_view_frame: the tile-list readback runs on its own stream so that it overlaps gen_vertices
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t select_done = nullptr, copy_done = nullptr;
+    bt_tile* h_tiles = nullptr;      // pinned
+    uint32_t h_tiles_cap = 0;
     size_t h2d_bytes_last_update = 0;
     bool updated = false;
 };

@@ -266,6 +266,12 @@ bt_status bt_select_tiles(bt_view* view, uint32_t flags, void* stream);
  * stream (indirect.vertex_count records) to a device buffer.                                  */
 bt_status bt_gen_vertices(bt_view* view, uint32_t flags, void* stream, bt_vertex_buffer* out);
 
+/* One frame in one call = bt_view_update + bt_select_tiles + bt_gen_vertices + read-back of the tile list and indirect
+ * record (Prepare + TilingPrepassNode::run + the draw's vertex stage of the reference's frame).  The read-back overlaps
+ * gen_vertices on an internal copy stream; on return the tile list is on the host, the vertex buffer is (being) written
+ * on the device, stream-ordered on `stream`.  Needs a view created with max_vertices > 0.                          */
+bt_status bt_view_run_frame(bt_view* view, const bt_view_frame* frame, uint32_t select_flags, uint32_t gen_flags, void* stream,
+                        bt_tile* tiles, uint32_t capacity, uint32_t* count, bt_indirect* indirect, bt_vertex_buffer* vertices);
 /* blocking D2H of final_tiles + indirect (the reference never reads these back; the draw
  * consumes them on-device)                                                                    */
 bt_status bt_view_readback(bt_view* view, bt_tile* tiles, uint32_t capacity, uint32_t* count,

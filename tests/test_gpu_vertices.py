@@ -126,3 +126,34 @@ def test_vertex_buffer_overflow_is_reported(ctx):
     with pytest.raises(F.BtError) as e:
         _gpu_frame(ctx, scene, [(100.0, 170.0, -50.0)], 0, max_vertices=576 * 10)
     assert e.value.status in (F.BT_ERR_CAPACITY, F.BT_ERR_INVALID_ARG)
+
+
+def test_run_frame_equals_separate_calls(ctx):
+    """bt_view_run_frame (upload + select + gen + overlapped tile-list read-back) == the four separate entry points"""
+    from bevy_terrain_b200 import api
+    scene = Scene("planar", lod_count=4, T=64, B=2, src=256, grid_size=16)
+    atlas = api.TileAtlas(ctx, scene.terrain_config())
+    tree = api.TileTree(atlas, scene.cfg, max_vertices=6000 * 576)
+    try:
+        tree.add_existing_tiles(np.array(sorted(scene.existing), dtype=np.uint32))
+        for pos in planar_view_positions(4):
+            loads = scene.move_view(pos)
+            for tc, idx in loads:
+                atlas.upload_tile(0, idx, scene.atlas[idx])
+            # drive the product's own clipmap so that build_frame() has its table
+            for tile, atlas_index in tree.compute_requests(pos):
+                tree.mark_loaded(tile)
+            tree.adjust_to_tile_atlas()
+            tiles_f, ind_f, vb = tree.frame_step(ALL)
+            verts_f = tree.download_vertices(0, ind_f.vertex_count)
+            tree.prepare()
+            tree.select_tiles()
+            tiles_s, ind_s = tree.readback()
+            tree.gen_vertices(ALL)
+            verts_s = tree.download_vertices(0, ind_s.vertex_count)
+            assert np.array_equal(tiles_f, tiles_s) and ind_f.vertex_count == ind_s.vertex_count
+            assert verts_f.tobytes() == verts_s.tobytes()
+            exp_tiles, _, _ = scene.oracle_select()
+            assert np.array_equal(tiles_f, exp_tiles)
+    finally:
+        tree.close(); atlas.close()
