@@ -133,7 +133,7 @@ def test_run_frame_equals_separate_calls(ctx):
     from bevy_terrain_b200 import api
     scene = Scene("planar", lod_count=4, T=64, B=2, src=256, grid_size=16)
     atlas = api.TileAtlas(ctx, scene.terrain_config())
-    tree = api.TileTree(atlas, scene.cfg, max_vertices=6000 * 576)
+    tree = api.TileTree(atlas, scene.cfg, max_vertices=9000 * 576)
     try:
         tree.add_existing_tiles(np.array(sorted(scene.existing), dtype=np.uint32))
         for pos in planar_view_positions(4):
@@ -144,7 +144,7 @@ def test_run_frame_equals_separate_calls(ctx):
             for tile, atlas_index in tree.compute_requests(pos):
                 tree.mark_loaded(tile)
             tree.adjust_to_tile_atlas()
-            tiles_f, ind_f, vb = tree.frame_step(ALL)
+            tiles_f, ind_f, vb = tree.frame_step(ALL, tile_capacity=9000)
             verts_f = tree.download_vertices(0, ind_f.vertex_count)
             tree.prepare()
             tree.select_tiles()
