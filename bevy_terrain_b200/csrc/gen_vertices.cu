@@ -48,6 +48,8 @@ struct GenParams {
     uint32_t strips_per_item;  // CB
     uint32_t items_per_tile;   // ceil(g / CB)
     uint32_t image_bytes;      // CB * (strip_bytes + STRIP_PAD), per buffer
+    uint32_t magic_items;      // ceil(2^32 / items_per_tile): w / items_per_tile == umulhi(w, magic_items) (w < 2^32 / items_per_tile)
+    uint32_t magic_cols;       // ceil(2^32 / (CB + 1)) for full-width items
 };
 
 struct Record {  // one bt_vertex as five 8-byte words
@@ -376,11 +378,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
             uint32_t it = 0;
             for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
                 const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
-                const uint32_t tile_index = w / P.items_per_tile;
+                const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
                 const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
                 const uint32_t n_strips = min(P.strips_per_item, g - c0);
                 unsigned char* image = images + (size_t)b * P.image_bytes;
-                mbar_wait(&H.full[b], use & 1u);          // every compute warp has written (and proxy-fenced) its records
+                mbar_wait_parked(&H.full[b], use & 1u, 2000u);   // every compute warp has written (and proxy-fenced) its records
                 fence_proxy_async();
                 unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
                                      ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
@@ -400,18 +402,19 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
     uint32_t it = 0;
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
-        const uint32_t tile_index = w / P.items_per_tile;
+        const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
         const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
         const uint32_t n_strips = min(P.strips_per_item, g - c0);
         const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
         unsigned char* image = images + (size_t)b * P.image_bytes;
-        if (use > 0u) mbar_wait(&H.empty[b], (use - 1u) & 1u);   // the stores of the previous user of image b have read it
+        if (use > 0u) mbar_wait_parked(&H.empty[b], (use - 1u) & 1u, 500u);   // the stores of the previous user of image b have read it
 
         const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
         const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
         const uint32_t n_verts = n_cols * n_rows;
         const uint32_t n_chunks = (n_verts + 31u) >> 5;
-        const uint32_t magic = 0xFFFFFFFFu / n_cols + 1u;   // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32
+        // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32; the full-width magic comes from the host
+        const uint32_t magic = n_strips == P.strips_per_item ? P.magic_cols : 0xFFFFFFFFu / n_cols + 1u;
         // chunk c of this item goes to warp (c + rotation) mod GEN_COMPUTE_WARPS; the rotation spreads the ragged tail
         const uint32_t rot = (it * 11u) % GEN_COMPUTE_WARPS;
         uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;
@@ -469,6 +472,8 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     P.strips_per_item = cb;
     P.items_per_tile = (grid_size + cb - 1u) / cb;
     P.image_bytes = cb * strip_stride;
+    P.magic_items = P.items_per_tile == 1u ? 0u : 0xFFFFFFFFu / P.items_per_tile + 1u;
+    P.magic_cols = 0xFFFFFFFFu / (cb + 1u) + 1u;
     const size_t smem = header + (size_t)GEN_BUFFERS * P.image_bytes;
     cudaError_t e = cudaFuncSetAttribute(spherical ? gen_vertices_kernel<true> : gen_vertices_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
