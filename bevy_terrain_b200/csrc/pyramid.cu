@@ -251,20 +251,26 @@ __global__ void __launch_bounds__(PYR_THREADS) downsample_kernel(PyramidLayout L
     // ---- fast path: the whole packet lies in the centre, inside ONE child, and the child texel pairs are 4-byte
     // (R16) / 8-byte (Rgba8) aligned: vector loads, no per-pixel indexing.  Same operands in the same order as the
     // general path below (sum over OFFSETS (0,0),(0,1),(1,0),(1,1); adding an invalid R16 texel adds exactly +0).
-    if (aligned && (L.B % 2u) == 0u && (L.C % 2u) == 0u && y >= L.B && y < L.B + L.C && x0 >= L.B && x0 + N <= L.B + L.C) {
-        const uint32_t tx0 = x0 - L.B, txl = tx0 + N - 1u, ty = y - L.B;
-        const uint32_t qx = tx0 >= child_size, qy = ty >= child_size;
-        if (qx == (uint32_t)(txl >= child_size)) {
+    // (packets that also contain border columns take it too - their border pixels are masked to zero - because one slow
+    //  lane would make its whole warp execute the general path)
+    const uint32_t i_lo = x0 < L.B ? L.B - x0 : 0u;                                   // first centre pixel of the packet
+    const uint32_t i_hi = min((uint32_t)N, (L.B + L.C > x0 ? L.B + L.C - x0 : 0u));   // one past the last centre pixel
+    if (aligned && (L.B % 2u) == 0u && (L.C % 2u) == 0u && y >= L.B && y < L.B + L.C && i_lo < i_hi && x0 + N <= L.T) {
+        const uint32_t tx_first = x0 + i_lo - L.B, tx_last = x0 + i_hi - 1u - L.B, ty = y - L.B;
+        const uint32_t qx = tx_first >= child_size, qy = ty >= child_size;
+        if (qx == (uint32_t)(tx_last >= child_size)) {
             const uint32_t child_slot = task.dep[qx + 2u * qy];
-            const uint32_t cx = 2u * (tx0 - qx * child_size) + L.B, cy = 2u * (ty - qy * child_size) + L.B;
-            if (child_slot == INVALID_SLOT) {
+            // child column of pixel i: 2 * (x0 + i - B - qx*child_size) + B = cbase + 2*i (cbase may be negative for i < i_lo)
+            const int cbase = 2 * ((int)x0 - (int)L.B - (int)(qx * child_size)) + (int)L.B;
+            const uint32_t cy = 2u * (ty - qy * child_size) + L.B;
 #pragma unroll
-                for (int i = 0; i < N; ++i) out.t[i] = F::zero();
-            } else {
-                const texel* r0 = reinterpret_cast<const texel*>(L.arena + (size_t)child_slot * L.tile_bytes) + (size_t)cy * L.T + cx;
+            for (int i = 0; i < N; ++i) out.t[i] = F::zero();
+            if (child_slot != INVALID_SLOT) {
+                const texel* r0 = reinterpret_cast<const texel*>(L.arena + (size_t)child_slot * L.tile_bytes) + (size_t)cy * L.T + cbase;
                 const texel* r1 = r0 + L.T;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
+                    if ((uint32_t)i < i_lo || (uint32_t)i >= i_hi) continue;   // border pixel of an edge packet
                     texel a, b, c, e;  // (cx,cy) (cx+1,cy) (cx,cy+1) (cx+1,cy+1)
                     if constexpr (FORMAT == BT_FORMAT_R16) {
                         const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(r0) + i), w1 = __ldg(reinterpret_cast<const uint32_t*>(r1) + i);
