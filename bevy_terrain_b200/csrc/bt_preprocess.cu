@@ -123,8 +123,6 @@ struct bt_preprocessor {
     std::vector<Store> stores;
     std::vector<Job> jobs;
     // scratch device buffers (grown on demand)
-    PyramidTask* d_tasks = nullptr; size_t d_tasks_cap = 0;
-    DatasetDevice* d_datasets = nullptr; size_t d_datasets_cap = 0;
     RowCopy* d_copies = nullptr; size_t d_copies_cap = 0;
 
     bool spherical() const { return kind == BT_KIND_SPHERICAL; }
@@ -145,11 +143,6 @@ struct bt_preprocessor {
         if (shard.world == 1 || lod < root_lod) { *y0 = 0; *y1 = n; return; }
         *y0 = (uint32_t)((uint64_t)shard.rank * n / shard.world);
         *y1 = (uint32_t)((uint64_t)(shard.rank + 1) * n / shard.world);
-    }
-    bool owns(const TileKey& k) const {
-        uint32_t y0, y1;
-        owned_rows(k.lod, &y0, &y1);
-        return k.y >= y0 && k.y < y1;
     }
 
     uint32_t get_or_allocate(Store& s, const TileKey& k, uint32_t job, uint8_t kind_) {
@@ -453,7 +446,7 @@ void bt_preprocessor_destroy(bt_preprocessor* p) {
     cudaDeviceSynchronize();
     for (Store& s : p->stores) if (s.arena) cudaFree(s.arena);
     for (Job& j : p->jobs) { for (void* px : j.owned_pixels) cudaFree(px); cudaFree(j.plan.d_tasks); cudaFree(j.plan.d_datasets); }
-    cudaFree(p->d_tasks); cudaFree(p->d_datasets); cudaFree(p->d_copies);
+    cudaFree(p->d_copies);
     delete p;
 }
 
