@@ -115,6 +115,10 @@ class TileLoad(C.Structure):
     _fields_ = [("tile", Tile), ("atlas_index", u32), ("_pad", u32 * 3)]
 
 
+class TileLookup(C.Structure):  # tile_tree.rs:67-83
+    _fields_ = [("atlas_index", u32), ("atlas_lod", u32), ("atlas_uv", f32 * 2)]
+
+
 class Dataset(C.Structure):  # preprocessor.rs:36-55
     _fields_ = [("attachment_index", u32), ("side", u32), ("top_left", f32 * 2), ("bottom_right", f32 * 2),
                 ("lod_begin", u32), ("lod_end", u32), ("width", u32), ("height", u32),
@@ -198,6 +202,8 @@ def _declare(lib: C.CDLL) -> None:
         "bt_tile_tree_mark_loaded": (i32, [vp, P(Tile)]),
         "bt_tile_tree_entries": (i32, [vp, P(TileTreeEntry), u32, P(u32), u32]),
         "bt_tile_tree_set_approximate_height": (None, [vp, f32]),
+        "bt_tile_tree_sample_lookup": (i32, [vp, P(f64), P(TileLookup), P(u32), P(f32)]),
+        "bt_atlas_sample": (i32, [vp, u32, P(TileLookup), P(f32)]),
         "bt_preprocessor_create": (i32, [vp, u32, P(AttachmentConfig), u32, u32, Shard, P(vp)]),
         "bt_preprocessor_destroy": (None, [vp]),
         "bt_preprocessor_add_datasets": (i32, [vp, P(Dataset), u32]),

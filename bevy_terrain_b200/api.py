@@ -271,6 +271,28 @@ class TileTree:
     def adjust_to_tile_atlas(self) -> None:
         self.ctx.check(self.ctx.lib.bt_tile_tree_entries(self._tree, self.entries, self.entry_count, self.origins, len(self.origins)))
 
+    def sample_attachment(self, attachment: int, sample_world_position) -> np.ndarray:
+        """sample_attachment (terrain_data/mod.rs:267-295): host lookup + device texels, blended with Vec4::lerp"""
+        lk = (F.TileLookup * 2)()
+        n, ratio = F.u32(), F.f32()
+        self.ctx.check(self.ctx.lib.bt_tile_tree_sample_lookup(self._tree, (F.f64 * 3)(*[float(v) for v in sample_world_position]), lk, C.byref(n), C.byref(ratio)))
+        out = (F.f32 * 4)()
+        self.ctx.check(self.ctx.lib.bt_atlas_sample(self.atlas._h, attachment, C.byref(lk[0]), out))
+        value = np.array(out[:], dtype=np.float32)
+        if ratio.value > 0.0:
+            self.ctx.check(self.ctx.lib.bt_atlas_sample(self.atlas._h, attachment, C.byref(lk[1]), out))
+            v2 = np.array(out[:], dtype=np.float32)
+            value = (value + (v2 - value) * np.float32(ratio.value)).astype(np.float32)
+        return value
+
+    def update_approximate_height(self) -> float:
+        """TileTree::approximate_height (tile_tree.rs:376-386): sample_height at the view position"""
+        m = self.model.c
+        s = self.sample_attachment(0, self.view_world_position)[0]
+        h = np.float32(m.min_height) + (np.float32(m.max_height) - np.float32(m.min_height)) * s   # f32::lerp
+        self.set_approximate_height(float(h))
+        return float(h)
+
     def set_approximate_height(self, h: float) -> None:
         """TileTree::approximate_height result (tile_tree.rs:376-386); the caller samples it."""
         self.approximate_height = float(h)

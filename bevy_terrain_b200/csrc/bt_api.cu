@@ -3,6 +3,7 @@
 // The preprocessor lives in bt_preprocess.cu, the f64 host math in host_math.cpp.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -218,6 +219,46 @@ bt_status bt_tile_config_load(const char* path, bt_tile* tiles, uint32_t capacit
     }
     if (pos != buf.size()) return BT_ERR_IO;
     *count = (uint32_t)total;
+    return BT_OK;
+}
+
+bt_status bt_atlas_sample(bt_terrain* t, uint32_t attachment, const bt_tile_lookup* lookup, float out[4]) {
+    if (!t || !lookup || !out || attachment >= t->desc.attachment_count) return BT_ERR_INVALID_ARG;
+    out[0] = out[1] = out[2] = out[3] = 0.0f;
+    if (lookup->atlas_index == 0xFFFFFFFFu) return BT_OK;   // AtlasAttachment::sample: "Todo: Handle this better" -> zeros
+    bt_context* ctx = t->ctx;
+    const bt_attachment_config& a = t->desc.attachments[attachment];
+    if (lookup->atlas_index >= t->desc.atlas_size) { ctx->set_error("bt_atlas_sample: atlas_index out of range"); return BT_ERR_INVALID_ARG; }
+    const float size = (float)a.texture_size;
+    const float scale = (float)(a.texture_size - 2 * a.border_size) / size, offset = (float)a.border_size / size;   // AtlasAttachment::new, tile_atlas.rs:172-193
+    // AttachmentData::sample — terrain_data/mod.rs:221-264
+    const float ux = (lookup->atlas_uv[0] * scale + offset) * size - 0.5f, uy = (lookup->atlas_uv[1] * scale + offset) * size - 0.5f;
+    const float rx = std::fmod(ux, 1.0f), ry = std::fmod(uy, 1.0f);
+    const int ix = (int)ux, iy = (int)uy;
+    if (ix < 0 || iy < 0 || ix + 1 >= (int)a.texture_size || iy + 1 >= (int)a.texture_size) {
+        ctx->set_error("bt_atlas_sample: sample footprint leaves the tile (the reference would index out of bounds)");
+        return BT_ERR_INVALID_ARG;
+    }
+    const size_t px = a.format == BT_FORMAT_R16 ? 2 : 4;
+    unsigned char texels[2][8];
+    const unsigned char* base = static_cast<const unsigned char*>(t->atlas[attachment]) + t->tile_bytes[attachment] * lookup->atlas_index;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int y = 0; y < 2; ++y)
+        BT_CUDA(ctx, cudaMemcpy(texels[y], base + ((size_t)(iy + y) * a.texture_size + ix) * px, 2 * px, cudaMemcpyDeviceToHost));
+    float v[2][2][4];   // [x][y][channel]
+    for (int x = 0; x < 2; ++x) for (int y = 0; y < 2; ++y) {
+        if (a.format == BT_FORMAT_R16) {
+            uint16_t w; std::memcpy(&w, texels[y] + x * 2, 2);
+            v[x][y][0] = (float)w / 65535.0f; v[x][y][1] = v[x][y][2] = v[x][y][3] = 0.0f;
+        } else {
+            for (int c = 0; c < 4; ++c) v[x][y][c] = (float)texels[y][x * 4 + c] / 255.0f;
+        }
+    }
+    for (int c = 0; c < 4; ++c) {  // Vec4::lerp(lerp(v00, v01, ry), lerp(v10, v11, ry), rx), glam: a + (b - a) * s
+        const float l0 = v[0][0][c] + (v[0][1][c] - v[0][0][c]) * ry;
+        const float l1 = v[1][0][c] + (v[1][1][c] - v[1][0][c]) * ry;
+        out[c] = l0 + (l1 - l0) * rx;
+    }
     return BT_OK;
 }
 

@@ -441,6 +441,48 @@ bt_status bt_tile_tree_add_existing(bt_tile_tree* tree, const bt_tile* tiles, ui
 
 void bt_tile_tree_set_approximate_height(bt_tile_tree* tree, float h) { if (tree) tree->approximate_height = h; }
 
+// sample_attachment's host half — terrain_data/mod.rs:267-295 with TileTree::compute_blend / lookup_tile (tile_tree.rs:223-266)
+bt_status bt_tile_tree_sample_lookup(bt_tile_tree* tree, const double sample_world_position[3], bt_tile_lookup lookups[2],
+                                     uint32_t* lookup_count, float* blend_ratio) {
+    if (!tree || !sample_world_position || !lookups || !lookup_count || !blend_ratio) return BT_ERR_INVALID_ARG;
+    const bt_tile_tree& t = *tree;
+    // TerrainModel::surface_position — terrain_model.rs:170-172
+    const D3 local = position_world_to_local(t.model, D3{sample_world_position[0], sample_world_position[1], sample_world_position[2]});
+    const D3 surface = position_local_to_world(t.model, local, (double)t.approximate_height);
+    // TileTree::compute_blend — tile_tree.rs:223-237
+    const double blend_distance = t.cfg.blend_distance * bt_terrain_model_scale(&t.model);
+    const double view_distance = length(t.view_world_position - surface);
+    const float target_lod = (float)std::fmin(std::log2(blend_distance / view_distance), (double)t.lod_count - 0.00001);
+    const uint32_t lod = target_lod > 0.0f ? (target_lod >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)target_lod) : 0u;   // `as u32` saturates
+    float ratio = 0.0f;
+    if (lod != 0) {  // util::inverse_mix — util.rs:8-10
+        const float a = (float)lod + t.cfg.blend_range, b = (float)lod;
+        const float v = (target_lod - a) / (b - a);
+        ratio = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+    }
+    auto lookup = [&](uint32_t tree_lod) {  // TileTree::lookup_tile — tile_tree.rs:239-266
+        const Coordinate c = coordinate_from_world(t.model, surface);
+        const double tile_count = (double)(1u << tree_lod);
+        const double m = tile_count - 0.000001;
+        const D2 xy{std::fmin(c.uv.x * tile_count, m), std::fmin(c.uv.y * tile_count, m)};
+        const TreeSlot& slot = t.tiles[t.slot_index(c.side, tree_lod, (uint32_t)(size_t)xy.x, (uint32_t)(size_t)xy.y)];
+        const bt_tile_tree_entry e = t.best_tile(slot.coordinate);
+        bt_tile_lookup out{0xFFFFFFFFu, 0xFFFFFFFFu, {0.0f, 0.0f}};   // TileLookup::INVALID
+        if (e.atlas_lod == 0xFFFFFFFFu) return out;
+        const double div = (double)(1u << (tree_lod - e.atlas_lod));
+        out.atlas_index = e.atlas_index;
+        out.atlas_lod = e.atlas_lod;
+        out.atlas_uv[0] = (float)std::fmod(xy.x / div, 1.0);
+        out.atlas_uv[1] = (float)std::fmod(xy.y / div, 1.0);
+        return out;
+    };
+    lookups[0] = lookup(lod);
+    *lookup_count = 1;
+    if (ratio > 0.0f) { lookups[1] = lookup(lod - 1); *lookup_count = 2; }
+    *blend_ratio = ratio;
+    return BT_OK;
+}
+
 // TileTree::update (tile_tree.rs:268-333) followed by TileAtlas::update's request/release pass
 // (tile_atlas.rs:574-601: released tiles first, then requested ones)
 bt_status bt_tile_tree_update(bt_tile_tree* tree, const double view_world_position[3], bt_tile_load* loads, uint32_t cap, uint32_t* count) {

@@ -121,6 +121,9 @@ typedef struct bt_attachment_uniform { float size, scale, offset; uint32_t _pad;
  * table index = ((side*lod_count + lod)*tree_size + x%tree_size)*tree_size + y%tree_size     */
 typedef struct bt_tile_tree_entry { uint32_t atlas_index, atlas_lod; } bt_tile_tree_entry;
 
+/* TileLookup — src/terrain_data/tile_tree.rs:67-83 (CPU-side sampling); INVALID = {0xFFFFFFFF, 0xFFFFFFFF, (0,0)} */
+typedef struct bt_tile_lookup { uint32_t atlas_index, atlas_lod; float atlas_uv[2]; } bt_tile_lookup;
+
 /* Mesh transform consumed by position_local_to_world / normal_local_to_world
  * (functions.wgsl:14-29; bevy_pbr MeshUniform built at terrain_bind_group.rs:185-205).
  * world_from_local: column-major 3x4 affine (cols x,y,z,translation);
@@ -236,6 +239,10 @@ bt_status bt_atlas_load_tile_file(bt_terrain* terrain, uint32_t attachment, uint
                                   const bt_tile* tile, void* stream);
 /* TC::load_file / decode_alloc (formats/mod.rs:14-31): bincode-standard Vec<TileCoordinate>; *count receives the total */
 bt_status bt_tile_config_load(const char* path, bt_tile* tiles, uint32_t capacity, uint32_t* count);
+/* AtlasAttachment::sample + AttachmentData::sample (tile_atlas.rs:249-258, terrain_data/mod.rs:221-264): bilinear sample of
+ * one atlas tile at lookup.atlas_uv with the twin's exact f32 arithmetic; fetches the four texels from the device (blocking).
+ * An INVALID lookup yields zeros, as in the reference.                                                                   */
+bt_status bt_atlas_sample(bt_terrain* terrain, uint32_t attachment, const bt_tile_lookup* lookup, float out[4]);
 /* device base pointer of an attachment's atlas array (for zero-copy interop / tests) */
 bt_status bt_atlas_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out);
 
@@ -345,6 +352,12 @@ bt_status bt_tile_tree_mark_loaded(bt_tile_tree* tree, const bt_tile* tile);
 bt_status bt_tile_tree_entries(bt_tile_tree* tree, bt_tile_tree_entry* entries, uint32_t entry_cap,
                                uint32_t* origins_xy, uint32_t origin_cap);
 void      bt_tile_tree_set_approximate_height(bt_tile_tree* tree, float h);
+/* CPU-side sampling chain of TileTree::approximate_height (tile_tree.rs:376-386 -> sample_attachment,
+ * terrain_data/mod.rs:267-295): surface position, TileTree::compute_blend (tile_tree.rs:223-237) and TileTree::lookup_tile
+ * (:239-266) for the blend LOD and, when blend_ratio > 0, the LOD below it.  The texels live on the device: feed the lookups
+ * to bt_atlas_sample and mix the two results with blend_ratio (sample_attachment does Vec4::lerp).                      */
+bt_status bt_tile_tree_sample_lookup(bt_tile_tree* tree, const double sample_world_position[3], bt_tile_lookup lookups[2],
+                                     uint32_t* lookup_count, float* blend_ratio);
 
 /* ------------------------------------------------------------------------------------------ */
 /* preprocessor = Preprocessor + TerrainPreprocessNode (src/preprocess/preprocessor.rs:214-343,  */
