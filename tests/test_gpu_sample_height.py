@@ -84,8 +84,8 @@ def test_sample_attachment_matches_cpu_twin(ctx):
                                               scene.cfg.blend_distance * 1000.0, scene.cfg.blend_range, 4)
                 seen_blend |= ratio > 0
                 assert got.tobytes() == exp.tobytes(), (sample_pos, got, exp, lod, ratio)
-            h = tree.update_approximate_height()
-            s = tree.sample_attachment(0, pos)[0]
+            h = tree.update_approximate_height()      # TileTree::approximate_height: feeds the next frame's clipmap + Taylor series
+            scene.clipmap.approximate_height = h      # keep the reference clipmap in step
             assert 0.0 <= h <= 500.0
         assert seen_blend
     finally:
