@@ -63,6 +63,7 @@ struct FrameConsts {
     bool  g_pow2;
     float Tf;                  // f32(texture_size)
     int   T, Tm1;
+    uint32_t interior;         // texel (i, j) with i-1, j-1 < interior has its 4x4 neighbourhood inside the texture
     float min_h, max_h;
     float a_scale, a_offset;   // attachment_uv (attachments.wgsl:7-10)
     float normal_offset;       // 0.5 / attachments[0].size (attachments.wgsl:85)
@@ -82,6 +83,7 @@ __device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) 
     F.inv_g = 1.0f / F.g;      // exact when g is a power of two: x * inv_g == x / g bit for bit
     F.T = (int)U.texture_size;
     F.Tm1 = F.T - 1;
+    F.interior = F.T >= 4 ? (uint32_t)(F.T - 3) : 0u;   // 1 <= i <= T-3  <=>  i-1 >= 0 and i+2 <= T-1
     F.Tf = (float)U.texture_size;
     F.min_h = U.terrain_config.min_height;
     F.max_h = U.terrain_config.max_height;
@@ -167,18 +169,33 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
     const uint32_t ju = (uint32_t)((int)fyu - iy + 1), jd = (uint32_t)((int)fyd - iy);
     FiveTaps out;
     out.ok = (jl | jr | ju | jd) <= 1u;   // offsets of 0.5/size texture units = ~0.5 texel: always true; guarded anyway
-    const int c0 = min(max(ix - 1, 0), F.Tm1), c1 = min(max(ix, 0), F.Tm1), c2 = min(max(ix + 1, 0), F.Tm1), c3 = min(max(ix + 2, 0), F.Tm1);
-    const uint16_t* q0 = layer + min(max(iy - 1, 0), F.Tm1) * F.T;
-    const uint16_t* q1 = layer + min(max(iy, 0), F.Tm1) * F.T;
-    const uint16_t* q2 = layer + min(max(iy + 1, 0), F.Tm1) * F.T;
-    const uint16_t* q3 = layer + min(max(iy + 2, 0), F.Tm1) * F.T;
-    // texel t<row><col>
-    const float t10 = unorm16_to_float(__ldg(q1 + c0)), t11 = unorm16_to_float(__ldg(q1 + c1));
-    const float t12 = unorm16_to_float(__ldg(q1 + c2)), t13 = unorm16_to_float(__ldg(q1 + c3));
-    const float t20 = unorm16_to_float(__ldg(q2 + c0)), t21 = unorm16_to_float(__ldg(q2 + c1));
-    const float t22 = unorm16_to_float(__ldg(q2 + c2)), t23 = unorm16_to_float(__ldg(q2 + c3));
-    const float t01 = unorm16_to_float(__ldg(q0 + c1)), t02 = unorm16_to_float(__ldg(q0 + c2));
-    const float t31 = unorm16_to_float(__ldg(q3 + c1)), t32 = unorm16_to_float(__ldg(q3 + c2));
+    // raw texel r<row><col>
+    uint32_t r10, r11, r12, r13, r20, r21, r22, r23, r01, r02, r31, r32;
+    if ((uint32_t)(ix - 1) < F.interior && (uint32_t)(iy - 1) < F.interior) {
+        // the whole plus lies inside the texture (always the case for uv inside a tile with border_size >= 2):
+        // one base address, row pointers by +-T, column offsets as immediates; no clamping
+        const uint16_t* p1 = layer + (iy * F.T + ix);
+        const uint16_t* p0 = p1 - F.T;
+        const uint16_t* p2 = p1 + F.T;
+        const uint16_t* p3 = p2 + F.T;
+        r10 = __ldg(p1 - 1); r11 = __ldg(p1); r12 = __ldg(p1 + 1); r13 = __ldg(p1 + 2);
+        r20 = __ldg(p2 - 1); r21 = __ldg(p2); r22 = __ldg(p2 + 1); r23 = __ldg(p2 + 2);
+        r01 = __ldg(p0); r02 = __ldg(p0 + 1);
+        r31 = __ldg(p3); r32 = __ldg(p3 + 1);
+    } else {
+        const int c0 = min(max(ix - 1, 0), F.Tm1), c1 = min(max(ix, 0), F.Tm1), c2 = min(max(ix + 1, 0), F.Tm1), c3 = min(max(ix + 2, 0), F.Tm1);
+        const uint16_t* q0 = layer + min(max(iy - 1, 0), F.Tm1) * F.T;
+        const uint16_t* q1 = layer + min(max(iy, 0), F.Tm1) * F.T;
+        const uint16_t* q2 = layer + min(max(iy + 1, 0), F.Tm1) * F.T;
+        const uint16_t* q3 = layer + min(max(iy + 2, 0), F.Tm1) * F.T;
+        r10 = __ldg(q1 + c0); r11 = __ldg(q1 + c1); r12 = __ldg(q1 + c2); r13 = __ldg(q1 + c3);
+        r20 = __ldg(q2 + c0); r21 = __ldg(q2 + c1); r22 = __ldg(q2 + c2); r23 = __ldg(q2 + c3);
+        r01 = __ldg(q0 + c1); r02 = __ldg(q0 + c2);
+        r31 = __ldg(q3 + c1); r32 = __ldg(q3 + c2);
+    }
+    const float t10 = unorm16_to_float(r10), t11 = unorm16_to_float(r11), t12 = unorm16_to_float(r12), t13 = unorm16_to_float(r13);
+    const float t20 = unorm16_to_float(r20), t21 = unorm16_to_float(r21), t22 = unorm16_to_float(r22), t23 = unorm16_to_float(r23);
+    const float t01 = unorm16_to_float(r01), t02 = unorm16_to_float(r02), t31 = unorm16_to_float(r31), t32 = unorm16_to_float(r32);
     out.centre = lerp2(t11, t21, t12, t22, rxc, ryc);
     // left: columns (ix-1+jl, ix+jl); right: columns (ix+jr, ix+1+jr); rows iy, iy+1 (py == centre's)
     out.left = jl ? lerp2(t11, t21, t12, t22, rxl, ryc) : lerp2(t10, t20, t11, t21, rxl, ryc);
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
                 const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
                 const uint32_t n_strips = min(P.strips_per_item, g - c0);
                 unsigned char* image = images + (size_t)b * P.image_bytes;
-                mbar_wait_parked(&H.full[b], use & 1u, 2000u);   // every compute warp has written (and proxy-fenced) its records
+                mbar_wait_parked(&H.full[b], use & 1u, 256u);   // every compute warp has written (and proxy-fenced) its records
                 fence_proxy_async();
                 unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
                                      ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
@@ -407,14 +424,15 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         const uint32_t n_strips = min(P.strips_per_item, g - c0);
         const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
         unsigned char* image = images + (size_t)b * P.image_bytes;
-        if (use > 0u) mbar_wait_parked(&H.empty[b], (use - 1u) & 1u, 500u);   // the stores of the previous user of image b have read it
+        if (use > 0u) mbar_wait_parked(&H.empty[b], (use - 1u) & 1u, 64u);   // the stores of the previous user of image b have read it
 
         const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
         const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
         const uint32_t n_verts = n_cols * n_rows;
         const uint32_t n_chunks = (n_verts + 31u) >> 5;
         // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32; the full-width magic comes from the host
-        const uint32_t magic = n_strips == P.strips_per_item ? P.magic_cols : 0xFFFFFFFFu / n_cols + 1u;
+        uint32_t magic = P.magic_cols;
+        if (n_strips != P.strips_per_item) magic = 0xFFFFFFFFu / n_cols + 1u;   // ragged last item of a tile only
         // chunk c of this item goes to warp (c + rotation) mod GEN_COMPUTE_WARPS; the rotation spreads the ragged tail
         const uint32_t rot = (it * 11u) % GEN_COMPUTE_WARPS;
         uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;

@@ -27,6 +27,13 @@ struct PyramidLayout {
 
 struct Px4 { float v[4]; };
 
+// floor(0.5 + M * saturate(v)) delivered in the low mantissa bits of a float: 0.5 <= 0.5 + M*c < 2^23, so the round-DOWN
+// sum with 2^23 is exactly 2^23 + floor(.) (one full-rate FADD.RM instead of FRND + F2I).  Same two roundings (product,
+// then + 0.5) as pack4x8unorm / pack2x16unorm in the oracle; saturate(NaN) = 0 like min(max(NaN, 0), 1).
+__device__ __forceinline__ uint32_t unorm_bits(float v, float M) {
+    return __float_as_uint(__fadd_rd(0.5f + M * __saturatef(v), 8388608.0f));
+}
+
 template <int FORMAT> struct Fmt;
 template <> struct Fmt<BT_FORMAT_R16> {
     using texel = uint16_t;
@@ -34,8 +41,7 @@ template <> struct Fmt<BT_FORMAT_R16> {
     static __device__ __forceinline__ Px4 decode(uint16_t t) { return Px4{{unorm16_to_float(t), 0.0f, 0.0f, 1.0f}}; }  // == (float)t / 65535.0f
     static __device__ __forceinline__ uint16_t zero() { return 0; }
     static __device__ __forceinline__ uint16_t pack(const Px4& p) {  // pack2x16unorm — preprocessing.wgsl:85-88
-        float c = fminf(fmaxf(p.v[0], 0.0f), 1.0f);
-        return (uint16_t)(uint32_t)floorf(0.5f + 65535.0f * c);
+        return (uint16_t)(unorm_bits(p.v[0], 65535.0f) & 0xFFFFu);
     }
 };
 template <> struct Fmt<BT_FORMAT_RGBA8> {
@@ -46,12 +52,9 @@ template <> struct Fmt<BT_FORMAT_RGBA8> {
     }
     static __device__ __forceinline__ uchar4 zero() { return make_uchar4(0, 0, 0, 0); }
     static __device__ __forceinline__ uchar4 pack(const Px4& p) {  // pack4x8unorm — preprocessing.wgsl:81-84
-        uchar4 r;
-        r.x = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[0], 0.0f), 1.0f));
-        r.y = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[1], 0.0f), 1.0f));
-        r.z = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[2], 0.0f), 1.0f));
-        r.w = (unsigned char)(uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(p.v[3], 0.0f), 1.0f));
-        return r;
+        const uint32_t b = __byte_perm(__byte_perm(unorm_bits(p.v[0], 255.0f), unorm_bits(p.v[1], 255.0f), 0x0040),
+                                       __byte_perm(unorm_bits(p.v[2], 255.0f), unorm_bits(p.v[3], 255.0f), 0x0040), 0x5410);
+        return *reinterpret_cast<const uchar4*>(&b);
     }
 };
 
@@ -78,158 +81,7 @@ __device__ __forceinline__ void store_packet(texel* row, uint32_t x, uint32_t T,
 // ------------------------------------------------------------------------------------------------
 // split — split.wgsl:18-43
 // ------------------------------------------------------------------------------------------------
-template <int FORMAT>
-__device__ __forceinline__ Px4 source_texel(const DatasetDevice& d, int x, int y) {
-    using F = Fmt<FORMAT>;
-    x = min(max(x, 0), (int)d.width - 1);   // clamp-to-edge (ImageSampler::linear, preprocessor.rs:408-409)
-    y = min(max(y, 0), (int)d.height - 1);
-    // row window of a sharded source: rows outside the band are never needed by the band's tiles
-    // (bt_preprocess.cu validates the window); clamp so that a bad window cannot fault
-    const int ry = min(max(y - (int)d.row_begin, 0), (int)d.row_count - 1);
-    return F::decode(__ldg(reinterpret_cast<const typename F::texel*>(d.pixels) + (size_t)ry * d.width + (size_t)x));
-}
-
-// Each thread owns a strip of N pixels x SPLIT_ROWS rows (N * sizeof(texel) = 8 bytes: one 64-bit store per row).
-// Per pixel column the x terms (tile coordinate, source coordinate, bilinear weight, clamped texel column) are
-// computed once; per source row the horizontal lerp  h(row) = mix(texel(row, x0), texel(row, x1), rx)  and its
-// validity bit are cached in registers, so at the native 1:1 ratio every output row fetches ONE new source row
-// (2 texels per pixel instead of 4) and vertically adjacent outputs share h(row).  value = mix(h(y0), h(y1), ry)
-// is exactly the shader's mix(mix(v00,v10,rx), mix(v01,v11,rx), ry): same operands, same order, bit-identical.
-// The code is branch-free per pixel (clamped coordinates make every load legal; masks select at the end).
-constexpr int SPLIT_ROWS = 16;
-
-template <int FORMAT> struct SplitCfg;
-template <> struct SplitCfg<BT_FORMAT_R16> { static constexpr int N = 4, CH = 1; };    // R16 packs only .x (preprocessing.wgsl:85-88)
-template <> struct SplitCfg<BT_FORMAT_RGBA8> { static constexpr int N = 2, CH = 4; };
-
-template <int FORMAT>
-__global__ void __launch_bounds__(PYR_THREADS, 4) split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks,
-                                                               const DatasetDevice* __restrict__ datasets) {
-    using F = Fmt<FORMAT>;
-    using texel = typename F::texel;
-    constexpr int N = SplitCfg<FORMAT>::N, CH = SplitCfg<FORMAT>::CH;
-    const PyramidTask& task = tasks[blockIdx.y];
-    const DatasetDevice d = datasets[task.dataset];
-    const uint32_t packets_per_row = (L.T + N - 1) / N;
-    const uint32_t row_groups = (L.T + SPLIT_ROWS - 1) / SPLIT_ROWS;
-    const uint32_t pid = blockIdx.x * PYR_THREADS + threadIdx.x;
-    if (pid >= packets_per_row * row_groups) return;
-    const uint32_t yg = pid / packets_per_row, x0 = (pid - yg * packets_per_row) * N;
-    texel* tile = reinterpret_cast<texel*>(L.arena + (size_t)task.slot * L.tile_bytes);
-    const bool aligned = ((L.T * sizeof(texel)) % 8 == 0) && (L.tile_bytes % 8 == 0) && x0 + N <= L.T;
-    const bool fresh = (task.flags & kTaskFresh) != 0u;
-    const float inv_tile_scale = exp2i(-(int)(task.tile.lod & 31u));  // x / tile_count(lod) == x * 2^-lod exactly
-    const float Cf = (float)L.C;
-    // inverse_mix with top_left = 0, bottom_right = 1 is (x - 0) / (1 - 0) = x exactly: skip the division
-    const bool full_x = d.top_left[0] == 0.0f && d.bottom_right[0] == 1.0f;
-    const bool full_y = d.top_left[1] == 0.0f && d.bottom_right[1] == 1.0f;
-    const float range_x = d.bottom_right[0] - d.top_left[0], range_y = d.bottom_right[1] - d.top_left[1];
-    const float Wf = (float)d.width, Hf = (float)d.height;
-    const int wm1 = (int)d.width - 1, hm1 = (int)d.height - 1;
-    const texel* __restrict__ src = reinterpret_cast<const texel*>(d.pixels);
-
-    // ---- per-column terms (computed for every lane, masked at the end) ----
-    float rx[N];
-    uint32_t cx0[N];
-    uint32_t col_centre = 0, col_inside = 0;  // bit i: pixel column lies in the tile centre / passes inside_square in x
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const uint32_t x = x0 + i;
-        const float tcx = div_rn((float)((int)x - (int)L.B), Cf);   // == IEEE quotient (bt_device.cuh)
-        float sx = ((float)task.tile.x + tcx) * inv_tile_scale;
-        if (!full_x) sx = (sx - d.top_left[0]) / range_x;   // inverse_mix — preprocessing.wgsl:44-46
-        const float px = sx * Wf - 0.5f;
-        const float fx = floorf(px);
-        rx[i] = px - fx;
-        const int ix = (int)fx;
-        cx0[i] = (uint32_t)min(max(ix, 0), wm1) | ((uint32_t)(min(max(ix + 1, 0), wm1) - min(max(ix, 0), wm1)) << 31);  // clamp-to-edge; bit 31 = step to x1
-        if (x < L.T && x >= L.B && x < L.B + L.C) col_centre |= 1u << i;
-        if (tcx >= 0.0f && tcx <= 1.0f) col_inside |= 1u << i;   // inside_square, x part
-    }
-
-    // ---- cached horizontal lerps of two source rows ----
-    float hA[N][CH], hB[N][CH];
-    uint32_t vA = 0, vB = 0;       // bit i: both texels of the row have red != 0 (textureGather(0, ..) validity)
-    int rowA = -1, rowB = -1;      // clamped source row held in A / B
-    auto load_row = [&](float (&h)[N][CH], uint32_t& valid, int y) {
-        // row window of a sharded source (bt_preprocess.cu validates it); clamp so a bad window cannot fault
-        const int ry_ = min(max(y - (int)d.row_begin, 0), (int)d.row_count - 1);
-        const texel* __restrict__ r = src + (size_t)ry_ * d.width;
-        valid = 0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const uint32_t c0 = cx0[i] & 0x7FFFFFFFu, c1 = c0 + (cx0[i] >> 31);
-            const Px4 t0 = F::decode(__ldg(r + c0)), t1 = F::decode(__ldg(r + c1));
-#pragma unroll
-            for (int k = 0; k < CH; ++k) h[i][k] = mix(t0.v[k], t1.v[k], rx[i]);
-            valid |= (uint32_t)(t0.v[0] != 0.0f && t1.v[0] != 0.0f) << i;
-        }
-    };
-
-#pragma unroll 1
-    for (int r = 0; r < SPLIT_ROWS; ++r) {
-        const uint32_t y = yg * SPLIT_ROWS + r;
-        if (y >= L.T) break;
-        texel* row = tile + (size_t)y * L.T;
-        Packet8<texel, N> out;
-#pragma unroll
-        for (int i = 0; i < N; ++i) out.t[i] = F::zero();
-        if (y >= L.B && y < L.B + L.C && col_centre != 0u) {   // border rows stay zero (split.wgsl:19-21); warp-uniform in y
-            const float tcy = div_rn((float)(y - L.B), Cf);
-            float sy = ((float)task.tile.y + tcy) * inv_tile_scale;
-            if (!full_y) sy = (sy - d.top_left[1]) / range_y;
-            const float py = sy * Hf - 0.5f;
-            const float fy = floorf(py);
-            const float ry = py - fy;
-            const int iy = (int)fy;
-            const bool inside_y = tcy >= 0.0f && tcy <= 1.0f;
-            const int ya = min(max(iy, 0), hm1), yb = min(max(iy + 1, 0), hm1);
-            if (ya != rowA) {
-                if (ya == rowB) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i)
-#pragma unroll
-                        for (int k = 0; k < CH; ++k) hA[i][k] = hB[i][k];
-                    vA = vB;
-                } else {
-                    load_row(hA, vA, ya);
-                }
-                rowA = ya;
-            }
-            if (yb != rowB) {
-                if (yb == rowA) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i)
-#pragma unroll
-                        for (int k = 0; k < CH; ++k) hB[i][k] = hA[i][k];
-                    vB = vA;
-                } else {
-                    load_row(hB, vB, yb);
-                }
-                rowB = yb;
-            }
-            const uint32_t write_mask = inside_y ? (col_centre & col_inside & vA & vB) : 0u;
-            const uint32_t keep_mask = col_centre & ~write_mask;   // textureLoad(atlas, coords): keep earlier datasets' texels
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                Px4 value{{0.0f, 0.0f, 0.0f, 0.0f}};
-#pragma unroll
-                for (int k = 0; k < CH; ++k) value.v[k] = mix(hA[i][k], hB[i][k], ry);
-                if (write_mask >> i & 1u) out.t[i] = F::pack(value);
-            }
-            if (keep_mask != 0u && !fresh) {
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    if (keep_mask >> i & 1u) out.t[i] = row[x0 + i];
-            }
-        }
-        if (aligned) {
-            *reinterpret_cast<uint2*>(row + x0) = *reinterpret_cast<const uint2*>(&out);
-        } else {
-            for (int i = 0; i < N; ++i) if (x0 + i < L.T) row[x0 + i] = out.t[i];
-        }
-    }
-}
+#include "split_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // downsample — downsample.wgsl:12-40
