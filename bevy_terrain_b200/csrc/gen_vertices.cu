@@ -193,16 +193,38 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
         r01 = __ldg(q0 + c1); r02 = __ldg(q0 + c2);
         r31 = __ldg(q3 + c1); r32 = __ldg(q3 + c2);
     }
-    const float t10 = unorm16_to_float(r10), t11 = unorm16_to_float(r11), t12 = unorm16_to_float(r12), t13 = unorm16_to_float(r13);
-    const float t20 = unorm16_to_float(r20), t21 = unorm16_to_float(r21), t22 = unorm16_to_float(r22), t23 = unorm16_to_float(r23);
-    const float t01 = unorm16_to_float(r01), t02 = unorm16_to_float(r02), t31 = unorm16_to_float(r31), t32 = unorm16_to_float(r32);
-    out.centre = lerp2(t11, t21, t12, t22, rxc, ryc);
+    // decode in pairs (row 1, row 2) of one column / (row 0, row 3): the pairs the y-lerps consume
+    const float2 k0 = unorm16x2_to_float(r10, r20), k1 = unorm16x2_to_float(r11, r21);   // k<col> = (t1<col>, t2<col>)
+    const float2 k2 = unorm16x2_to_float(r12, r22), k3 = unorm16x2_to_float(r13, r23);
+    const float2 e1 = unorm16x2_to_float(r01, r31), e2 = unorm16x2_to_float(r02, r32);   // e<col> = (t0<col>, t3<col>)
+    // y-lerps of rows (1, 2) with the centre's ry:  L<col> = t1c + (t2c - t1c) * ryc  — lerp2's `a` / `b` for centre, left, right.
+    // Packed: difference and product for two columns per instruction; the final additions stay scalar (a packed mul feeding a
+    // packed add would be contracted into FFMA2 by ptxas, which the numerics contract forbids).
+    const float2 ryc2 = make_float2(ryc, ryc);
+    const float2 d01 = __fmul2_rn(__fadd2_rn(make_float2(k0.y, k1.y), make_float2(-k0.x, -k1.x)), ryc2);
+    const float2 d23 = __fmul2_rn(__fadd2_rn(make_float2(k2.y, k3.y), make_float2(-k2.x, -k3.x)), ryc2);
+    const float L0 = k0.x + d01.x, L1 = k1.x + d01.y, L2 = k2.x + d23.x, L3 = k3.x + d23.y;
+    // x-stage: a + (b - a) * rx
+    out.centre = L1 + (L2 - L1) * rxc;
     // left: columns (ix-1+jl, ix+jl); right: columns (ix+jr, ix+1+jr); rows iy, iy+1 (py == centre's)
-    out.left = jl ? lerp2(t11, t21, t12, t22, rxl, ryc) : lerp2(t10, t20, t11, t21, rxl, ryc);
-    out.right = jr ? lerp2(t12, t22, t13, t23, rxr, ryc) : lerp2(t11, t21, t12, t22, rxr, ryc);
+    {
+        const float la = jl ? L1 : L0, lb = jl ? L2 : L1, ra = jr ? L2 : L1, rb = jr ? L3 : L2;
+        const float2 m = __fmul2_rn(__fadd2_rn(make_float2(lb, rb), make_float2(-la, -ra)), make_float2(rxl, rxr));
+        out.left = la + m.x;
+        out.right = ra + m.y;
+    }
     // up: rows (iy-1+ju, iy+ju); down: rows (iy+jd, iy+1+jd); columns ix, ix+1 (px == centre's)
-    out.up = ju ? lerp2(t11, t21, t12, t22, rxc, ryu) : lerp2(t01, t11, t02, t12, rxc, ryu);
-    out.down = jd ? lerp2(t21, t31, t22, t32, rxc, ryd) : lerp2(t11, t21, t12, t22, rxc, ryd);
+    {
+        // (v00, v01) per column c in {1, 2}: up = ju ? (t1c, t2c) : (t0c, t1c);  down = jd ? (t2c, t3c) : (t1c, t2c)
+        const float u00 = ju ? k1.x : e1.x, u01 = ju ? k1.y : k1.x, u10 = ju ? k2.x : e2.x, u11 = ju ? k2.y : k2.x;
+        const float w00 = jd ? k1.y : k1.x, w01 = jd ? e1.y : k1.y, w10 = jd ? k2.y : k2.x, w11 = jd ? e2.y : k2.y;
+        const float2 mu = __fmul2_rn(__fadd2_rn(make_float2(u01, u11), make_float2(-u00, -u10)), make_float2(ryu, ryu));
+        const float2 md = __fmul2_rn(__fadd2_rn(make_float2(w01, w11), make_float2(-w00, -w10)), make_float2(ryd, ryd));
+        const float ua = u00 + mu.x, ub = u10 + mu.y, da = w00 + md.x, db = w10 + md.y;
+        const float2 m = __fmul2_rn(__fadd2_rn(make_float2(ub, db), make_float2(-ua, -da)), make_float2(rxc, rxc));
+        out.up = ua + m.x;
+        out.down = da + m.y;
+    }
     return out;
 }
 
