@@ -32,7 +32,10 @@ constexpr int GEN_COMPUTE_WARPS = BT_GEN_COMPUTE_WARPS;  // compute warps per CT
 constexpr int GEN_THREADS = (GEN_COMPUTE_WARPS + 1) * 32;
 constexpr int GEN_CTAS_PER_SM = 1;
 constexpr int GEN_BUFFERS = 2;         // output images per CTA: compute of item i+1 overlaps the TMA stores of item i
-constexpr uint32_t STRIP_PAD = 16;     // bytes between strips in the smem image (bank spreading; keeps 16-B alignment)
+// Strips are laid out in the smem image with a stride that is 16 (mod 128) bytes: lanes of a warp write records of 32 different
+// strips, and with that stride each quarter-warp of a 128-bit store (and each half-warp of a 64-bit one) covers all 32 banks
+// once (the 40-byte records themselves are 8-byte aligned; the stride keeps every strip 16-byte aligned for the TMA).
+__host__ __device__ constexpr uint32_t strip_stride_for(uint32_t strip_bytes) { return strip_bytes + (144u - strip_bytes % 128u) % 128u; }
 
 struct GenParams {
     const ViewUniforms* uniforms;
@@ -47,7 +50,8 @@ struct GenParams {
     uint32_t grid_size;        // g
     uint32_t strips_per_item;  // CB
     uint32_t items_per_tile;   // ceil(g / CB)
-    uint32_t image_bytes;      // CB * (strip_bytes + STRIP_PAD), per buffer
+    uint32_t image_bytes;      // CB * strip_stride, per buffer
+    uint32_t strip_stride;     // strip_stride_for(vertices_per_row * sizeof(bt_vertex))
     uint32_t magic_items;      // ceil(2^32 / items_per_tile): w / items_per_tile == umulhi(w, magic_items) (w < 2^32 / items_per_tile)
     uint32_t magic_cols;       // ceil(2^32 / (CB + 1)) for full-width items
 };
@@ -159,11 +163,18 @@ __device__ __forceinline__ float lerp2(float v00, float v01, float v10, float v1
 
 __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
     const float o = F.normal_offset;
-    const float pxc = u * F.Tf - 0.5f, pyc = v * F.Tf - 0.5f;
-    const float pxl = (u + -o) * F.Tf - 0.5f, pxr = (u + o) * F.Tf - 0.5f;
-    const float pyu = (v + -o) * F.Tf - 0.5f, pyd = (v + o) * F.Tf - 0.5f;
+    // tap coordinates: (centre x, centre y), (left x, right x), (up y, down y) as packed pairs; each product is followed by a
+    // scalar "- 0.5" (same two roundings per value as sample_r16)
+    const float2 Tf2 = make_float2(F.Tf, F.Tf);
+    const float2 pc = __fmul2_rn(make_float2(u, v), Tf2);
+    const float2 plr = __fmul2_rn(__fadd2_rn(make_float2(u, u), make_float2(-o, o)), Tf2);
+    const float2 pud = __fmul2_rn(__fadd2_rn(make_float2(v, v), make_float2(-o, o)), Tf2);
+    const float pxc = pc.x - 0.5f, pyc = pc.y - 0.5f, pxl = plr.x - 0.5f, pxr = plr.y - 0.5f, pyu = pud.x - 0.5f, pyd = pud.y - 0.5f;
     const float fxc = floorf(pxc), fyc = floorf(pyc), fxl = floorf(pxl), fxr = floorf(pxr), fyu = floorf(pyu), fyd = floorf(pyd);
-    const float rxc = pxc - fxc, ryc = pyc - fyc, rxl = pxl - fxl, rxr = pxr - fxr, ryu = pyu - fyu, ryd = pyd - fyd;
+    const float2 rc = __fadd2_rn(make_float2(pxc, pyc), make_float2(-fxc, -fyc));
+    const float2 rlr = __fadd2_rn(make_float2(pxl, pxr), make_float2(-fxl, -fxr));
+    const float2 rud = __fadd2_rn(make_float2(pyu, pyd), make_float2(-fyu, -fyd));
+    const float rxc = rc.x, ryc = rc.y, rxl = rlr.x, rxr = rlr.y, ryu = rud.x, ryd = rud.y;
     const int ix = (int)fxc, iy = (int)fyc;
     const uint32_t jl = (uint32_t)((int)fxl - ix + 1), jr = (uint32_t)((int)fxr - ix);  // expected jl in {0,1}, jr in {0,1}
     const uint32_t ju = (uint32_t)((int)fyu - iy + 1), jd = (uint32_t)((int)fyd - iy);
@@ -237,10 +248,15 @@ __device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16
     const float offset = F.normal_offset;
     float left, up, right, down;
     if (pre && pre->ok) {
-        left = mix(F.min_h, F.max_h, pre->left);
-        up = mix(F.min_h, F.max_h, pre->up);
-        right = mix(F.min_h, F.max_h, pre->right);
-        down = mix(F.min_h, F.max_h, pre->down);
+        // mix(min_h, max_h, s) = min_h * (1 - s) + max_h * s for two taps at a time; the sum of the two products stays scalar
+        const float2 lo = make_float2(F.min_h, F.min_h), hi = make_float2(F.max_h, F.max_h), one = make_float2(1.0f, 1.0f);
+        const float2 s_lr = make_float2(pre->left, pre->right), s_ud = make_float2(pre->up, pre->down);
+        const float2 a_lr = __fmul2_rn(lo, __fadd2_rn(one, make_float2(-s_lr.x, -s_lr.y))), b_lr = __fmul2_rn(hi, s_lr);
+        const float2 a_ud = __fmul2_rn(lo, __fadd2_rn(one, make_float2(-s_ud.x, -s_ud.y))), b_ud = __fmul2_rn(hi, s_ud);
+        left = a_lr.x + b_lr.x;
+        right = a_lr.y + b_lr.y;
+        up = a_ud.x + b_ud.x;
+        down = a_ud.y + b_ud.y;
     } else {
         left = sample_height_uv(F, layer, u + -offset, v + 0.0f);
         up = sample_height_uv(F, layer, u + 0.0f, v + -offset);
@@ -344,7 +360,8 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
         }
     }
     Record r;  // vertex_output — vertex.wgsl:73-83
-    r.w[0] = make_float2(wp.x + height * wn.x, wp.y + height * wn.y);
+    const float2 hn = __fmul2_rn(make_float2(height, height), make_float2(wn.x, wn.y));
+    r.w[0] = make_float2(wp.x + hn.x, wp.y + hn.y);
     r.w[1] = make_float2(wp.z + height * wn.z, 1.0f);
     r.w[2] = make_float2(nrm.x, nrm.y);
     r.w[3] = make_float2(nrm.z, c.u);
@@ -352,10 +369,20 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     return r;
 }
 
+// Record k of a strip starts at 40*k bytes: 16-byte aligned for even k, 8 (mod 16) for odd k — the parity is static at every
+// call site, so each copy is two 128-bit stores and one 64-bit store.
+template <int ODD>
 __device__ __forceinline__ void store_record(unsigned char* image, uint32_t strip_stride, uint32_t strip, uint32_t k, const Record& r) {
-    float2* dst = reinterpret_cast<float2*>(image + (size_t)strip * strip_stride + (size_t)k * sizeof(bt_vertex));
-#pragma unroll
-    for (int i = 0; i < 5; ++i) dst[i] = r.w[i];
+    unsigned char* dst = image + strip * strip_stride + k * (uint32_t)sizeof(bt_vertex);
+    if (ODD) {
+        *reinterpret_cast<float2*>(dst) = r.w[0];
+        *reinterpret_cast<float4*>(dst + 8) = make_float4(r.w[1].x, r.w[1].y, r.w[2].x, r.w[2].y);
+        *reinterpret_cast<float4*>(dst + 24) = make_float4(r.w[3].x, r.w[3].y, r.w[4].x, r.w[4].y);
+    } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(r.w[0].x, r.w[0].y, r.w[1].x, r.w[1].y);
+        *reinterpret_cast<float4*>(dst + 16) = make_float4(r.w[2].x, r.w[2].y, r.w[3].x, r.w[3].y);
+        *reinterpret_cast<float2*>(dst + 32) = r.w[4];
+    }
 }
 
 struct GenSmemHeader {
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
     const uint32_t g = P.grid_size;
     const uint32_t vpr = U.view_config.vertices_per_row, vpt = U.view_config.vertices_per_tile;
     const uint32_t strip_bytes = vpr * (uint32_t)sizeof(bt_vertex);
-    const uint32_t strip_stride = strip_bytes + STRIP_PAD;
+    const uint32_t strip_stride = P.strip_stride;
     uint32_t n_tiles = __ldg(&P.indirect->vertex_count) / vpt;
     const uint64_t cap_tiles = P.vertex_capacity / vpt;
     if (n_tiles > cap_tiles) {
@@ -438,7 +465,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
 
     // ---------------- compute warps ----------------
     const FrameConsts F = make_frame_consts<SPHERICAL>(U);
-    uint32_t it = 0;
+    uint32_t it = 0, rot = 0;
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
         const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
@@ -456,9 +483,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         uint32_t magic = P.magic_cols;
         if (n_strips != P.strips_per_item) magic = 0xFFFFFFFFu / n_cols + 1u;   // ragged last item of a tile only
         // chunk c of this item goes to warp (c + rotation) mod GEN_COMPUTE_WARPS; the rotation spreads the ragged tail
-        const uint32_t rot = (it * 11u) % GEN_COMPUTE_WARPS;
-        uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;
+        uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;   // rot == (it * 11) % GEN_COMPUTE_WARPS
         if (first >= GEN_COMPUTE_WARPS) first -= GEN_COMPUTE_WARPS;
+        rot += 11u % GEN_COMPUTE_WARPS;
+        if (rot >= GEN_COMPUTE_WARPS) rot -= GEN_COMPUTE_WARPS;
         for (uint32_t c = first; c < n_chunks; c += GEN_COMPUTE_WARPS) {
             const uint32_t i = (c << 5) + (uint32_t)lane;
             if (i < n_verts) {
@@ -466,13 +494,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
                 const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
                 // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
                 if (lx < n_strips) {
-                    store_record(image, strip_stride, lx, 2u * gy + 1u, r);
-                    if (gy == 0u) store_record(image, strip_stride, lx, 0u, r);
+                    store_record<1>(image, strip_stride, lx, 2u * gy + 1u, r);
+                    if (gy == 0u) store_record<0>(image, strip_stride, lx, 0u, r);
                 }
                 // strip `lx-1`: this vertex is (column+1, row 2*gy+1) -> position 2*gy+2 (+ duplicated last index)
                 if (lx >= 1u) {
-                    store_record(image, strip_stride, lx - 1u, 2u * gy + 2u, r);
-                    if (gy == g) store_record(image, strip_stride, lx - 1u, vpr - 1u, r);
+                    store_record<0>(image, strip_stride, lx - 1u, 2u * gy + 2u, r);
+                    if (gy == g) store_record<1>(image, strip_stride, lx - 1u, vpr - 1u, r);   // vpr = 2 * (g + 2) is even
                 }
             }
         }
@@ -491,7 +519,7 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
                                               cudaStream_t stream) {
     using namespace btd;
     if (grid_size == 0) return cudaErrorInvalidValue;
-    const uint32_t strip_stride = 2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex) + STRIP_PAD;
+    const uint32_t strip_stride = strip_stride_for(2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex));
     const size_t header = (sizeof(GenSmemHeader) + 127) & ~size_t(127);
     const size_t budget = (200 * 1024) / GEN_CTAS_PER_SM - header - 1024;  // per CTA; leaves L1 some room out of the 227 KiB
     uint32_t cb = (uint32_t)(budget / ((size_t)GEN_BUFFERS * strip_stride));
@@ -512,6 +540,7 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     P.strips_per_item = cb;
     P.items_per_tile = (grid_size + cb - 1u) / cb;
     P.image_bytes = cb * strip_stride;
+    P.strip_stride = strip_stride;
     P.magic_items = P.items_per_tile == 1u ? 0u : 0xFFFFFFFFu / P.items_per_tile + 1u;
     P.magic_cols = 0xFFFFFFFFu / (cb + 1u) + 1u;
     const size_t smem = header + (size_t)GEN_BUFFERS * P.image_bytes;
