@@ -26,8 +26,12 @@
 namespace btd {
 
 #ifndef BT_GEN_COMPUTE_WARPS
-#define BT_GEN_COMPUTE_WARPS 23
+#define BT_GEN_COMPUTE_WARPS 19
 #endif
+#ifndef BT_GEN_ROTATION
+#define BT_GEN_ROTATION 11
+#endif
+constexpr uint32_t GEN_ROTATION = BT_GEN_ROTATION;
 constexpr int GEN_COMPUTE_WARPS = BT_GEN_COMPUTE_WARPS;  // compute warps per CTA (+ 1 store warp), one CTA per SM
 constexpr int GEN_THREADS = (GEN_COMPUTE_WARPS + 1) * 32;
 constexpr int GEN_CTAS_PER_SM = 1;
@@ -54,6 +58,7 @@ struct GenParams {
     uint32_t strip_stride;     // strip_stride_for(vertices_per_row * sizeof(bt_vertex))
     uint32_t magic_items;      // ceil(2^32 / items_per_tile): w / items_per_tile == umulhi(w, magic_items) (w < 2^32 / items_per_tile)
     uint32_t magic_cols;       // ceil(2^32 / (CB + 1)) for full-width items
+    uint32_t magic_cols_ragged;  // the same for the narrower last item of a tile (g % CB strips), if any
 };
 
 struct Record {  // one bt_vertex as five 8-byte words
@@ -204,17 +209,17 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
         r01 = __ldg(q0 + c1); r02 = __ldg(q0 + c2);
         r31 = __ldg(q3 + c1); r32 = __ldg(q3 + c2);
     }
-    // decode in pairs (row 1, row 2) of one column / (row 0, row 3): the pairs the y-lerps consume
-    const float2 k0 = unorm16x2_to_float(r10, r20), k1 = unorm16x2_to_float(r11, r21);   // k<col> = (t1<col>, t2<col>)
-    const float2 k2 = unorm16x2_to_float(r12, r22), k3 = unorm16x2_to_float(r13, r23);
-    const float2 e1 = unorm16x2_to_float(r01, r31), e2 = unorm16x2_to_float(r02, r32);   // e<col> = (t0<col>, t3<col>)
+    // decode in pairs of adjacent columns of one row — the layout the packed y-lerps consume without re-pairing
+    const float2 A01 = unorm16x2_to_float(r10, r11), A23 = unorm16x2_to_float(r12, r13);   // row 1: (t10, t11), (t12, t13)
+    const float2 B01 = unorm16x2_to_float(r20, r21), B23 = unorm16x2_to_float(r22, r23);   // row 2
+    const float2 E0 = unorm16x2_to_float(r01, r02), E3 = unorm16x2_to_float(r31, r32);     // rows 0 and 3: columns 1, 2
     // y-lerps of rows (1, 2) with the centre's ry:  L<col> = t1c + (t2c - t1c) * ryc  — lerp2's `a` / `b` for centre, left, right.
     // Packed: difference and product for two columns per instruction; the final additions stay scalar (a packed mul feeding a
     // packed add would be contracted into FFMA2 by ptxas, which the numerics contract forbids).
     const float2 ryc2 = make_float2(ryc, ryc);
-    const float2 d01 = __fmul2_rn(__fadd2_rn(make_float2(k0.y, k1.y), make_float2(-k0.x, -k1.x)), ryc2);
-    const float2 d23 = __fmul2_rn(__fadd2_rn(make_float2(k2.y, k3.y), make_float2(-k2.x, -k3.x)), ryc2);
-    const float L0 = k0.x + d01.x, L1 = k1.x + d01.y, L2 = k2.x + d23.x, L3 = k3.x + d23.y;
+    const float2 d01 = __fmul2_rn(__fadd2_rn(B01, make_float2(-A01.x, -A01.y)), ryc2);
+    const float2 d23 = __fmul2_rn(__fadd2_rn(B23, make_float2(-A23.x, -A23.y)), ryc2);
+    const float L0 = A01.x + d01.x, L1 = A01.y + d01.y, L2 = A23.x + d23.x, L3 = A23.y + d23.y;
     // x-stage: a + (b - a) * rx
     out.centre = L1 + (L2 - L1) * rxc;
     // left: columns (ix-1+jl, ix+jl); right: columns (ix+jr, ix+1+jr); rows iy, iy+1 (py == centre's)
@@ -226,12 +231,13 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
     }
     // up: rows (iy-1+ju, iy+ju); down: rows (iy+jd, iy+1+jd); columns ix, ix+1 (px == centre's)
     {
-        // (v00, v01) per column c in {1, 2}: up = ju ? (t1c, t2c) : (t0c, t1c);  down = jd ? (t2c, t3c) : (t1c, t2c)
-        const float u00 = ju ? k1.x : e1.x, u01 = ju ? k1.y : k1.x, u10 = ju ? k2.x : e2.x, u11 = ju ? k2.y : k2.x;
-        const float w00 = jd ? k1.y : k1.x, w01 = jd ? e1.y : k1.y, w10 = jd ? k2.y : k2.x, w11 = jd ? e2.y : k2.y;
-        const float2 mu = __fmul2_rn(__fadd2_rn(make_float2(u01, u11), make_float2(-u00, -u10)), make_float2(ryu, ryu));
-        const float2 md = __fmul2_rn(__fadd2_rn(make_float2(w01, w11), make_float2(-w00, -w10)), make_float2(ryd, ryd));
-        const float ua = u00 + mu.x, ub = u10 + mu.y, da = w00 + md.x, db = w10 + md.y;
+        const float2 M1 = make_float2(A01.y, A23.x), M2 = make_float2(B01.y, B23.x);   // (t11, t12), (t21, t22)
+        // (v00, v10) / (v01, v11): up = ju ? rows (1, 2) : rows (0, 1);  down = jd ? rows (2, 3) : rows (1, 2)
+        const float2 ulo = ju ? M1 : E0, uhi = ju ? M2 : M1;
+        const float2 wlo = jd ? M2 : M1, whi = jd ? E3 : M2;
+        const float2 mu = __fmul2_rn(__fadd2_rn(uhi, make_float2(-ulo.x, -ulo.y)), make_float2(ryu, ryu));
+        const float2 md = __fmul2_rn(__fadd2_rn(whi, make_float2(-wlo.x, -wlo.y)), make_float2(ryd, ryd));
+        const float ua = ulo.x + mu.x, ub = ulo.y + mu.y, da = wlo.x + md.x, db = wlo.y + md.y;
         const float2 m = __fmul2_rn(__fadd2_rn(make_float2(ub, db), make_float2(-ua, -da)), make_float2(rxc, rxc));
         out.up = ua + m.x;
         out.down = da + m.y;
@@ -480,12 +486,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         const uint32_t n_verts = n_cols * n_rows;
         const uint32_t n_chunks = (n_verts + 31u) >> 5;
         // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32; the full-width magic comes from the host
-        uint32_t magic = P.magic_cols;
-        if (n_strips != P.strips_per_item) magic = 0xFFFFFFFFu / n_cols + 1u;   // ragged last item of a tile only
+        const uint32_t magic = n_strips == P.strips_per_item ? P.magic_cols : P.magic_cols_ragged;
         // chunk c of this item goes to warp (c + rotation) mod GEN_COMPUTE_WARPS; the rotation spreads the ragged tail
-        uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;   // rot == (it * 11) % GEN_COMPUTE_WARPS
+        uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;   // chunk c of this item goes to warp (rot + c) mod GEN_COMPUTE_WARPS
         if (first >= GEN_COMPUTE_WARPS) first -= GEN_COMPUTE_WARPS;
-        rot += 11u % GEN_COMPUTE_WARPS;
+        rot += GEN_ROTATION % GEN_COMPUTE_WARPS;                     // spreads the ragged tail (measured: DESIGN.md section 6)
         if (rot >= GEN_COMPUTE_WARPS) rot -= GEN_COMPUTE_WARPS;
         for (uint32_t c = first; c < n_chunks; c += GEN_COMPUTE_WARPS) {
             const uint32_t i = (c << 5) + (uint32_t)lane;
@@ -543,6 +548,10 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     P.strip_stride = strip_stride;
     P.magic_items = P.items_per_tile == 1u ? 0u : 0xFFFFFFFFu / P.items_per_tile + 1u;
     P.magic_cols = 0xFFFFFFFFu / (cb + 1u) + 1u;
+    {
+        const uint32_t last_strips = grid_size - (P.items_per_tile - 1u) * cb;   // 1..cb
+        P.magic_cols_ragged = 0xFFFFFFFFu / (last_strips + 1u) + 1u;
+    }
     const size_t smem = header + (size_t)GEN_BUFFERS * P.image_bytes;
     cudaError_t e = cudaFuncSetAttribute(spherical ? gen_vertices_kernel<true> : gen_vertices_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
