@@ -117,20 +117,56 @@ split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks, const Datas
     }
 
     // ---- cached horizontal lerps of two source rows ----
-    float hA[N][CH], hB[N][CH];
+    // Values are held as packed pairs (sm_100 FMUL2 / FFMA2 / FADD2: two IEEE f32 results per instruction, element-wise
+    // identical to the scalar operations).  R16: pair j = pixels (2j, 2j+1); Rgba8: pairs (2i, 2i+1) = channels (r,g), (b,a)
+    // of pixel i.  A packed product never feeds a packed add (ptxas would contract the pair into FFMA2): sums are scalar.
+    constexpr int V2 = N * CH / 2;
+    static_assert((N * CH) % 2 == 0, "pairs");
+    float2 rx2[V2], omrx2[V2];     // bilinear x weight (and 1 - weight) of the pixel each pair element belongs to
+#pragma unroll
+    for (int j = 0; j < V2; ++j) {
+        const int i0 = (2 * j) / CH, i1 = (2 * j + 1) / CH;
+        rx2[j] = make_float2(rx[i0], rx[i1]);
+        omrx2[j] = make_float2(1.0f - rx[i0], 1.0f - rx[i1]);
+    }
+    float2 hA[V2], hB[V2];
     float mA[N], mB[N];            // min(red0, red1): > 0 iff both texels of the row are valid (textureGather(0, ..) != 0)
     int rowA = -1, rowB = -1;      // clamped source row held in A / B
-    auto load_row = [&](float (&h)[N][CH], float (&m)[N], int y) {
+    auto load_row = [&](float2 (&h)[V2], float (&m)[N], int y) {
         // row window of a sharded source (bt_preprocess.cu validates it); clamp so a bad window cannot fault
         const int ry_ = min(max(y - (int)d.row_begin, 0), (int)d.row_count - 1);
         const texel* r = src + (size_t)ry_ * d.width;
+        float2 t0[V2], t1[V2];
+        if constexpr (FORMAT == BT_FORMAT_R16) {
+            uint32_t a[N], b[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const Px4 t0 = F::decode(__ldg(static_cast<const texel*>(ptr_add_u32(r, c0[i]))));
-            const Px4 t1 = F::decode(__ldg(static_cast<const texel*>(ptr_add_u32(r, c1[i]))));
+            for (int i = 0; i < N; ++i) {
+                a[i] = __ldg(static_cast<const uint16_t*>(ptr_add_u32(r, c0[i])));
+                b[i] = __ldg(static_cast<const uint16_t*>(ptr_add_u32(r, c1[i])));
+            }
 #pragma unroll
-            for (int k = 0; k < CH; ++k) h[i][k] = mix(t0.v[k], t1.v[k], rx[i]);
-            m[i] = fminf(t0.v[0], t1.v[0]);
+            for (int j = 0; j < V2; ++j) {
+                t0[j] = unorm16x2_to_float(a[2 * j], a[2 * j + 1]);
+                t1[j] = unorm16x2_to_float(b[2 * j], b[2 * j + 1]);
+                m[2 * j] = fminf(t0[j].x, t1[j].x);
+                m[2 * j + 1] = fminf(t0[j].y, t1[j].y);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const uint32_t a = __ldg(static_cast<const uint32_t*>(ptr_add_u32(r, c0[i])));
+                const uint32_t b = __ldg(static_cast<const uint32_t*>(ptr_add_u32(r, c1[i])));
+                t0[2 * i] = unorm8x2_to_float(a & 0xFFu, (a >> 8) & 0xFFu);
+                t0[2 * i + 1] = unorm8x2_to_float((a >> 16) & 0xFFu, a >> 24);
+                t1[2 * i] = unorm8x2_to_float(b & 0xFFu, (b >> 8) & 0xFFu);
+                t1[2 * i + 1] = unorm8x2_to_float((b >> 16) & 0xFFu, b >> 24);
+                m[i] = fminf(t0[2 * i].x, t1[2 * i].x);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V2; ++j) {   // mix(t0, t1, rx) = t0 * (1 - rx) + t1 * rx
+            const float2 p = __fmul2_rn(t0[j], omrx2[j]), q = __fmul2_rn(t1[j], rx2[j]);
+            h[j] = make_float2(p.x + q.x, p.y + q.y);
         }
     };
 
@@ -140,22 +176,27 @@ split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks, const Datas
     for (int i = 0; i < N; ++i) wthresh[i] = (col_write >> i & 1u) ? 0.0f : __int_as_float(0x7f800000);
 
     // one output row from the cached lerps: P holds source row ya, Q holds yb
-    auto emit = [&](const float (&P)[N][CH], const float (&mP)[N], const float (&Q)[N][CH], const float (&mQ)[N],
+    auto emit = [&](const float2 (&P)[V2], const float (&mP)[N], const float2 (&Q)[V2], const float (&mQ)[N],
                     const SplitRow& t, const texel* row, uint32_t (&pix)[N]) {
         const bool inside_y = (t.flags & 1u) != 0u;
+        const float2 ry2 = make_float2(t.ry, t.ry), omry2 = make_float2(1.0f - t.ry, 1.0f - t.ry);
+        const float2 M2 = make_float2(M, M), big2 = make_float2(8388608.0f, 8388608.0f);
+        uint32_t bits[2 * V2];     // pack: floor(0.5 + M * saturate(v)) in the low mantissa bits (see unorm_bits)
+#pragma unroll
+        for (int j = 0; j < V2; ++j) {
+            const float2 p = __fmul2_rn(P[j], omry2), q = __fmul2_rn(Q[j], ry2);        // mix(P, Q, ry)
+            const float2 s = __fmul2_rn(make_float2(__saturatef(p.x + q.x), __saturatef(p.y + q.y)), M2);
+            const float2 f = __fadd2_rd(make_float2(0.5f + s.x, 0.5f + s.y), big2);
+            bits[2 * j] = __float_as_uint(f.x);
+            bits[2 * j + 1] = __float_as_uint(f.y);
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const bool w = inside_y && fminf(mP[i], mQ[i]) > wthresh[i];
-            uint32_t bits;
-            if constexpr (FORMAT == BT_FORMAT_R16) {
-                bits = unorm_bits(mix(P[i][0], Q[i][0], t.ry), M);
-            } else {
-                uint32_t b[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) b[k] = unorm_bits(mix(P[i][k], Q[i][k], t.ry), M);
-                bits = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
-            }
-            pix[i] = w ? bits : 0u;
+            uint32_t texel_bits;
+            if constexpr (FORMAT == BT_FORMAT_R16) texel_bits = bits[i];
+            else texel_bits = __byte_perm(__byte_perm(bits[4 * i], bits[4 * i + 1], 0x0040), __byte_perm(bits[4 * i + 2], bits[4 * i + 3], 0x0040), 0x5410);
+            pix[i] = w ? texel_bits : 0u;
         }
         if (!fresh) {   // textureLoad(atlas, coords): centre pixels not written keep earlier datasets' texels
 #pragma unroll
