@@ -34,6 +34,13 @@ __device__ __forceinline__ uint32_t unorm_bits(float v, float M) {
     return __float_as_uint(__fadd_rd(0.5f + M * __saturatef(v), 8388608.0f));
 }
 
+// two unorm_bits at once: product and the round-down sum packed (FMUL2, FADD2.RM); the "+ 0.5" after the product stays scalar
+__device__ __forceinline__ uint2 unorm_bits2(float2 v, float M) {
+    const float2 s = __fmul2_rn(make_float2(__saturatef(v.x), __saturatef(v.y)), make_float2(M, M));
+    const float2 f = __fadd2_rd(make_float2(0.5f + s.x, 0.5f + s.y), make_float2(8388608.0f, 8388608.0f));
+    return make_uint2(__float_as_uint(f.x), __float_as_uint(f.y));
+}
+
 template <int FORMAT> struct Fmt;
 template <> struct Fmt<BT_FORMAT_R16> {
     using texel = uint16_t;
@@ -48,12 +55,13 @@ template <> struct Fmt<BT_FORMAT_RGBA8> {
     using texel = uchar4;
     static constexpr int PX_PER_THREAD = 4;
     static __device__ __forceinline__ Px4 decode(uchar4 t) {
-        return Px4{{unorm8_to_float(t.x), unorm8_to_float(t.y), unorm8_to_float(t.z), unorm8_to_float(t.w)}};  // == (float)c / 255.0f
+        const float2 xy = unorm8x2_to_float(t.x, t.y), zw = unorm8x2_to_float(t.z, t.w);   // == (float)c / 255.0f, two per instruction
+        return Px4{{xy.x, xy.y, zw.x, zw.y}};
     }
     static __device__ __forceinline__ uchar4 zero() { return make_uchar4(0, 0, 0, 0); }
     static __device__ __forceinline__ uchar4 pack(const Px4& p) {  // pack4x8unorm — preprocessing.wgsl:81-84
-        const uint32_t b = __byte_perm(__byte_perm(unorm_bits(p.v[0], 255.0f), unorm_bits(p.v[1], 255.0f), 0x0040),
-                                       __byte_perm(unorm_bits(p.v[2], 255.0f), unorm_bits(p.v[3], 255.0f), 0x0040), 0x5410);
+        const uint2 lo = unorm_bits2(make_float2(p.v[0], p.v[1]), 255.0f), hi = unorm_bits2(make_float2(p.v[2], p.v[3]), 255.0f);
+        const uint32_t b = __byte_perm(__byte_perm(lo.x, lo.y, 0x0040), __byte_perm(hi.x, hi.y, 0x0040), 0x5410);
         return *reinterpret_cast<const uchar4*>(&b);
     }
 };
@@ -129,7 +137,8 @@ __global__ void __launch_bounds__(PYR_THREADS) downsample_kernel(PyramidLayout L
                         a = (uint16_t)(w0 & 0xFFFFu); b = (uint16_t)(w0 >> 16); c = (uint16_t)(w1 & 0xFFFFu); e = (uint16_t)(w1 >> 16);
                         const float count = (float)((a != 0) + (c != 0) + (b != 0) + (e != 0));
                         // invalid texels are exactly 0.0: adding them leaves the sum unchanged, as skipping them does
-                        float sum = ((unorm16_to_float(a) + unorm16_to_float(c)) + unorm16_to_float(b)) + unorm16_to_float(e);
+                        const float2 ac = unorm16x2_to_float(a, c), be = unorm16x2_to_float(b, e);
+                        float sum = ((ac.x + ac.y) + be.x) + be.y;
                         if (count == 3.0f) sum = sum / 3.0f;
                         else sum = sum * (count == 4.0f ? 0.25f : (count == 2.0f ? 0.5f : 1.0f));
                         out.t[i] = count != 0.0f ? F::pack(Px4{{sum, 0.0f, 0.0f, 0.0f}}) : F::zero();
