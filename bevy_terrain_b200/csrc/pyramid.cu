@@ -459,7 +459,13 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
     if (i < 65536u) {
         volatile float m16 = 65535.0f, m8 = 255.0f;   // volatile: keep the reference form a true IEEE division
         if (unorm16_to_float(i) != (float)i / m16) atomicAdd(&mismatches[0], 1u);
-        if (i < 256u && unorm8_to_float(i) != (float)i / m8) atomicAdd(&mismatches[1], 1u);
+        const float2 p16 = unorm16x2_to_float(i, 65535u - i);    // packed (FMUL2 / FFMA2) decode, both halves
+        if (p16.x != (float)i / m16 || p16.y != (float)(65535u - i) / m16) atomicAdd(&mismatches[0], 1u);
+        if (i < 256u) {
+            if (unorm8_to_float(i) != (float)i / m8) atomicAdd(&mismatches[1], 1u);
+            const float2 p8 = unorm8x2_to_float(i, 255u - i);
+            if (p8.x != (float)i / m8 || p8.y != (float)(255u - i) / m8) atomicAdd(&mismatches[1], 1u);
+        }
     }
     if (i < n) {
         log2_out[i] = log2_det(x[i]);
@@ -471,6 +477,37 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
         if (ordinary && div_rn(a, b) != q) atomicAdd(&mismatches[2], 1u);
         const float ax = fabsf(a);
         if (ax >= 1.17549435e-38f && ax < 1e37f && sqrt_rn(ax) != sqrtf(ax)) atomicAdd(&mismatches[3], 1u);
+        // ---- packed-f32 forms against the scalar IEEE operations they stand for ----
+        const float fa = a, fb = b, fc = x[(uint32_t)(((uint64_t)i * 104729u + 7u) % n)];
+        if (fabsf(fa) < 1e18f && fabsf(fb) < 1e18f && fabsf(fc) < 1e18f) {
+            // product packed, sum scalar: must be TWO roundings (a fused multiply-add here would break the contract)
+            const float2 pr = __fmul2_rn(make_float2(fa, fb), make_float2(fb, fc));
+            const float s0 = pr.x + fc, s1 = pr.y + fa;
+            if (s0 != __fadd_rn(__fmul_rn(fa, fb), fc) || s1 != __fadd_rn(__fmul_rn(fb, fc), fa)) atomicAdd(&mismatches[2], 1u);
+            // packed difference, packed product, scalar sum: the lerp  v0 + (v1 - v0) * t  of the vertex taps
+            const float2 df = __fmul2_rn(__fadd2_rn(make_float2(fb, fc), make_float2(-fa, -fb)), make_float2(fc, fa));
+            if (fa + df.x != __fadd_rn(fa, __fmul_rn(__fadd_rn(fb, -fa), fc)) ||
+                fb + df.y != __fadd_rn(fb, __fmul_rn(__fadd_rn(fc, -fb), fa))) atomicAdd(&mismatches[2], 1u);
+            // two quotients by a common divisor (normalize3) and the packed squared length
+            const float len = fabsf(fc);
+            if (len >= 1e-18f && fabsf(fa) >= 1e-18f && fabsf(fb) >= 1e-18f) {
+                const float r = rcp_refined(len);
+                const float2 q2 = div_by_rcp2(make_float2(fa, fb), len, r);
+                volatile float vl = len;
+                if (q2.x != fa / vl || q2.y != fb / vl) atomicAdd(&mismatches[2], 1u);
+                const float l3 = length3(Vec3{fa, fb, fc});
+                volatile float ss = __fadd_rn(__fadd_rn(__fmul_rn(fa, fa), __fmul_rn(fb, fb)), __fmul_rn(fc, fc));
+                if (ss >= 1.17549435e-38f && l3 != sqrtf(ss)) atomicAdd(&mismatches[3], 1u);
+            }
+        }
+        // round-down pack (FADD.RM with 2^23) against floor(0.5 + M * clamp(v, 0, 1)), v spread over [-0.25, 1.25]
+        const float v = (float)(i % 60001u) * (1.5f / 60000.0f) - 0.25f, v2 = 1.0f - v;
+        const uint32_t e16 = (uint32_t)floorf(0.5f + 65535.0f * fminf(fmaxf(v, 0.0f), 1.0f));
+        const uint32_t e16b = (uint32_t)floorf(0.5f + 65535.0f * fminf(fmaxf(v2, 0.0f), 1.0f));
+        const uint32_t e8 = (uint32_t)floorf(0.5f + 255.0f * fminf(fmaxf(v, 0.0f), 1.0f));
+        const uint2 pk = unorm_bits2(make_float2(v, v2), 65535.0f);
+        if ((unorm_bits(v, 65535.0f) & 0xFFFFu) != e16 || (pk.x & 0xFFFFu) != e16 || (pk.y & 0xFFFFu) != e16b ||
+            (unorm_bits(v, 255.0f) & 0xFFu) != e8) atomicAdd(&mismatches[1], 1u);
     }
 }
 }  // namespace btd

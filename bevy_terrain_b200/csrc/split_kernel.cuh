@@ -18,12 +18,19 @@
 constexpr int SPLIT_ROWS = 16;
 constexpr int SPLIT_TAB_ROWS = 128;   // rows of y terms a CTA can cache (covers every tile size >= 128 px; smaller tiles compute inline)
 
+#ifndef BT_SPLIT_MIN_BLOCKS
+#define BT_SPLIT_MIN_BLOCKS 4   // resident CTAs per SM (R16; Rgba8 one more): the kernel hides its load latency by occupancy.
+                                // Measured at 65536^2: R16 3/4/5 blocks -> 13.9/12.0/12.1 ms, Rgba8 3/4/5 -> 29.1/25.4/24.2 ms
+#endif
+#ifndef BT_SPLIT_N_R16
+#define BT_SPLIT_N_R16 4
+#endif
 #ifndef BT_SPLIT_N_RGBA8
 #define BT_SPLIT_N_RGBA8 2
 #endif
 
 template <int FORMAT> struct SplitCfg;
-template <> struct SplitCfg<BT_FORMAT_R16> { static constexpr int N = 4, CH = 1, WORDS = 2; };    // R16 packs only .x (preprocessing.wgsl:85-88)
+template <> struct SplitCfg<BT_FORMAT_R16> { static constexpr int N = BT_SPLIT_N_R16, CH = 1, WORDS = BT_SPLIT_N_R16 / 2; };    // R16 packs only .x (preprocessing.wgsl:85-88)
 template <> struct SplitCfg<BT_FORMAT_RGBA8> { static constexpr int N = BT_SPLIT_N_RGBA8, CH = 4, WORDS = BT_SPLIT_N_RGBA8; };
 
 // base + off as ONE IMAD.WIDE.U32 (the compiler otherwise rebuilds row * width + column in 64 bits for every texel)
@@ -36,7 +43,7 @@ __device__ __forceinline__ const void* ptr_add_u32(const void* base, uint32_t of
 struct SplitRow { float ry; int ya, yb; uint32_t flags; };   // flags bit 0: inside_square (y part); bit 1: centre row
 
 template <int FORMAT>
-__global__ void __launch_bounds__(PYR_THREADS, (SplitCfg<FORMAT>::N * SplitCfg<FORMAT>::CH > 8) ? 3 : 4)
+__global__ void __launch_bounds__(PYR_THREADS, FORMAT == BT_FORMAT_RGBA8 ? BT_SPLIT_MIN_BLOCKS + 1 : BT_SPLIT_MIN_BLOCKS)
 split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks, const DatasetDevice* __restrict__ datasets) {
     using F = Fmt<FORMAT>;
     using texel = typename F::texel;
@@ -246,7 +253,8 @@ split_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks, const Datas
             for (int j = 0; j < WORDS; ++j) words[j] = pix[j];
         }
         if (aligned) {
-            if constexpr (WORDS == 2) *reinterpret_cast<uint2*>(row + x0) = make_uint2(words[0], words[1]);
+            if constexpr (WORDS == 1) *reinterpret_cast<uint32_t*>(row + x0) = words[0];
+            else if constexpr (WORDS == 2) *reinterpret_cast<uint2*>(row + x0) = make_uint2(words[0], words[1]);
             else *reinterpret_cast<uint4*>(row + x0) = make_uint4(words[0], words[1], words[2], words[3]);
         } else {
 #pragma unroll

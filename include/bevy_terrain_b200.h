@@ -447,11 +447,13 @@ bt_status bt_generate_mipmaps(bt_context* ctx, uint32_t format, uint32_t texture
  * reference; see DESIGN.md "synthetic inputs")                                                */
 bt_status bt_synth_source(bt_context* ctx, uint32_t format, uint32_t width, uint32_t height,
                           uint32_t x0, uint32_t y0, uint32_t seed, uint32_t holes, void* device_out, void* stream);
-/* numerics self-test: mismatches[0]/[1] = number of 16-/8-bit unorm values whose fast exact decode
- * differs from the IEEE division it replaces, mismatches[2] = pairs (x[i], x[j]) whose branch-free exact
- * division differs from `/`, mismatches[3] = inputs whose branch-free square root differs from sqrtf (all must
- * be 0); log2_out[i] = the kernels' deterministic log2 of x[i]
- * (host arrays), compared with the oracle by tests/test_gpu_numerics.py                           */
+/* numerics self-test (all counters must be 0): mismatches[0]/[1] = 16-/8-bit unorm values whose fast exact decode
+ * (scalar and packed-f32 forms) differs from the IEEE division it replaces, plus ([1]) values whose round-down pack
+ * differs from floor(0.5 + M*clamp(v,0,1)); mismatches[2] = operand pairs whose branch-free exact division differs from
+ * `/`, or whose packed-f32 product / difference / quotient differs from the scalar IEEE operations (a contracted
+ * multiply-add would show up here); mismatches[3] = inputs whose branch-free square root / packed length differs from
+ * sqrtf.  log2_out[i] = the kernels' deterministic log2 of x[i] (host arrays), compared with the oracle by
+ * tests/test_gpu_numerics.py                                                                      */
 bt_status bt_selftest_numerics(bt_context* ctx, const float* x, float* log2_out, uint32_t n, uint32_t mismatches[4]);
 /* raw device memory helpers for hosts without a CUDA binding (ctypes tests) */
 bt_status bt_device_alloc(bt_context* ctx, size_t bytes, void** out);
