@@ -413,7 +413,10 @@ class PreprocessDataset:  # preprocessor.rs:36-55 — `pixels` replaces `path` (
 @dataclass
 class SphericalDataset:  # preprocessor.rs:29-34 — one image per cube face
     attachment_index: int = 0
-    faces: list = field(default_factory=list)   # six host images
+    faces: list = field(default_factory=list)   # six host images ...
+    device_faces: list = field(default_factory=list)   # ... or six device pointers with width/height
+    width: int = 0
+    height: int = 0
     lod_range: range = range(0, 1)
 
 
@@ -445,7 +448,11 @@ class Preprocessor:
         return self
 
     def preprocess_spherical(self, dataset: SphericalDataset) -> "Preprocessor":
-        ds = [PreprocessDataset(attachment_index=dataset.attachment_index, pixels=dataset.faces[s], side=s, lod_range=dataset.lod_range) for s in range(6)]
+        if dataset.device_faces:
+            ds = [PreprocessDataset(attachment_index=dataset.attachment_index, device_pixels=dataset.device_faces[s], width=dataset.width,
+                                    height=dataset.height, side=s, lod_range=dataset.lod_range) for s in range(6)]
+        else:
+            ds = [PreprocessDataset(attachment_index=dataset.attachment_index, pixels=dataset.faces[s], side=s, lod_range=dataset.lod_range) for s in range(6)]
         arr = (F.Dataset * 6)(*[d.to_c() for d in ds])
         self._keep.append((ds, arr))
         self.ctx.check(self.ctx.lib.bt_preprocessor_add_datasets(self._h, arr, 6))
