@@ -50,61 +50,64 @@ def test_globe_pyramid_tiles_and_same_face_borders(globe):
     assert (edge[:, :B] != 0).all()
 
 
-def test_globe_frame_vertices(ctx, globe):
+def _direction(v):
+    v = np.asarray(v, dtype=np.float64)
+    return v / np.linalg.norm(v)
+
+
+ALL = F.BT_FLAG_NORMALS | F.BT_FLAG_MORPH | F.BT_FLAG_BLEND
+VIEWS = [   # the example's camera altitudes (examples/spherical.rs:96-100) + corner / edge views
+    ("corner_30km", _direction([0.62, 0.55, 0.56]) * (R + 30000.0), ALL),
+    ("minus_x_3km_high_precision", _direction([-1.0, 0.003, 0.002]) * (R + 3000.0), ALL | F.BT_FLAG_HIGH_PRECISION),   # < 0.001 R from the surface
+    ("face_edge_100km", _direction([1.0, 0.02, 1.0]) * (R + 100000.0), ALL),
+    ("far_3R", _direction([-1.0, 0.2, 0.1]) * (3.0 * R), ALL),
+]
+
+
+@pytest.mark.parametrize("name,pos,flags", VIEWS, ids=[v[0] for v in VIEWS])
+def test_globe_frame_vertices(ctx, globe, name, pos, flags):
     from bevy_terrain_b200 import api
+    from tests.fullsize_util import assert_tiles_bit_exact, check_strip_structure, oracle_inputs
     cfg, pre = globe
+    pos = tuple(float(v) for v in pos)
     vcfg = api.TerrainViewConfig(grid_size=64)
     atlas = api.TileAtlas(ctx, cfg)
     tree = api.TileTree(atlas, vcfg)
     try:
         tree.add_existing_tiles(pre.tiles())
-        # 30 km above the surface near a cube-face corner region (three faces in view)
-        d = np.array([0.62, 0.55, 0.56]); d /= np.linalg.norm(d)
-        pos = tuple(float(v) for v in d * (R + 30000.0))
         n_loads = api.load_resident_tiles(tree, pre, pos)
         assert 0 < n_loads <= cfg.atlas_size
         tree.prepare()
         tree.select_tiles()
         tiles, ind = tree.readback()
-        assert 500 < len(tiles) < 60000 and ind.vertex_count == len(tiles) * 8448
-        assert len({int(t[0]) for t in tiles}) >= 3                     # several cube faces contribute tiles
-        flags = F.BT_FLAG_NORMALS | F.BT_FLAG_MORPH | F.BT_FLAG_BLEND
+        assert 6 <= len(tiles) < 120000 and ind.vertex_count == len(tiles) * 8448
+        if name != "minus_x_3km_high_precision":
+            assert len({int(t[0]) for t in tiles}) >= 2                  # several cube faces contribute tiles
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tree.gen_vertices(flags)
         e0.record(); tree.gen_vertices(flags); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"\nconfigs[3] spherical frame: {len(tiles)} tiles, {ind.vertex_count / 1e6:.1f} M vertices, gen_vertices {ms:.3f} ms "
+        print(f"\nconfigs[3] {name}: {len(tiles)} tiles, {ind.vertex_count / 1e6:.1f} M vertices, gen_vertices {ms:.3f} ms "
               f"-> {ind.vertex_count / ms / 1e3:.0f} Mverts/s")
         rng = np.random.default_rng(1)
-        for t in rng.choice(len(tiles), 16, replace=False):
-            v = tree.download_vertices(int(t) * 8448, 8448).reshape(64, 132)
-            raw = np.ascontiguousarray(v).view(np.uint8).reshape(64, 132, 40)
-            assert np.array_equal(raw[:, 0], raw[:, 1]) and np.array_equal(raw[:, -1], raw[:, -2])
-            assert np.array_equal(v[:-1, 2::2]["position"][:, :65], v[1:, 1::2]["position"][:, :65])
-            assert (v["tile_index"] == t).all()
+        for t in rng.choice(len(tiles), min(16, len(tiles)), replace=False):
+            v = check_strip_structure(tree, int(t))
             radius = np.linalg.norm(v["position"][..., :3].astype(np.float64), axis=-1)
             assert radius.min() >= R + MIN_H - 2.0 and radius.max() <= R + MAX_H + 2.0
             nrm = np.linalg.norm(v["normal"].astype(np.float64), axis=-1)
             assert nrm.max() <= 1.0 + 1e-5 and nrm.min() > 0.5
         # bit-exact against the oracle on whole tiles, with the product's own inputs
-        host_atlas = np.empty((cfg.atlas_size, T, T), dtype=np.uint16)
-        ctx.d2h(host_atlas, atlas.device_ptr(0))
-        vi = O.VertexInputs()
-        vi.view_config, vi.approximation = tree.frame.view_config, tree.frame.approximation
-        vi.terrain_config = F.TerrainConfigUniform(L, MIN_H, MAX_H, float(np.float32(cfg.model.scale())))
-        vi.attachments[0].size, vi.attachments[0].scale, vi.attachments[0].offset = float(Cn), float(np.float32(Cn) / np.float32(T)), float(np.float32(B) / np.float32(T))
-        vi.mesh = cfg.model.mesh_transform()
-        vi.view_world_position[:] = [float(np.float32(p)) for p in pos]
-        vi.spherical, vi.texture_size = 1, T
-        entries = np.frombuffer(tree.entries, dtype=np.uint32).reshape(-1, 2).copy()
-        vi.tile_tree = entries.ctypes.data_as(C.POINTER(F.TileTreeEntry))
-        vi.height_atlas = host_atlas.ctypes.data
-        vi.tiles = tiles.ctypes.data_as(C.POINTER(F.Tile))
-        vi.tile_count, vi.flags = len(tiles), flags
-        for t in rng.choice(len(tiles), 32, replace=False):
-            exp = O.gen_vertices(vi, int(t) * 8448, 8448)
-            got = tree.download_vertices(int(t) * 8448, 8448)
-            assert got.tobytes() == exp.tobytes(), f"tile {t} differs"
+        vi = oracle_inputs(ctx, cfg, atlas, tree, tiles, flags, pos, True, T, B, MIN_H, MAX_H)
+        assert_tiles_bit_exact(tree, vi, rng.choice(len(tiles), min(32, len(tiles)), replace=False))
+        if flags & F.BT_FLAG_HIGH_PRECISION:
+            # the deepest tiles lie within precision_threshold_distance of the camera: the Taylor path must be taken there
+            deepest = np.flatnonzero(tiles[:, 1] >= tiles[:, 1].max() - 1)
+            vi.flags = flags & ~F.BT_FLAG_HIGH_PRECISION
+            taken = [int(t) for t in deepest if O.gen_vertices(vi, int(t) * 8448, 8448).tobytes() != tree.download_vertices(int(t) * 8448, 8448).tobytes()]
+            assert taken, "the view does not exercise HIGH_PRECISION"
+            vi.flags = flags
+            assert_tiles_bit_exact(tree, vi, taken[:16])      # ... and where it is taken, the result is still the oracle's
+            print(f"HIGH_PRECISION path taken in {len(taken)} of the {len(deepest)} deepest tiles")
     finally:
         tree.close(); atlas.close()
