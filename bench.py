@@ -46,8 +46,9 @@ def parse_args():
     ap.add_argument("--lods", type=int, default=8)
     ap.add_argument("--preprocess-source", type=int, default=65536, help="config-5 source size (0 = skip)")
     ap.add_argument("--preprocess-lods", type=int, default=8)
-    ap.add_argument("--cpu-sample-mverts", type=float, default=24.0, help="cpu_baseline sample size (million vertices)")
-    ap.add_argument("--ref-sample-mverts", type=float, default=4.0, help="reference arm: vertices per step (millions)")
+    ap.add_argument("--cpu-sample-mverts", type=float, default=64.0, help="cpu_baseline: vertices per pass (million; capped at view 0's count)")
+    ap.add_argument("--ref-sample-mverts", type=float, default=0.0, help="reference arm: vertices per step (millions); 0 = size from --ref-budget-s")
+    ap.add_argument("--ref-budget-s", type=float, default=100.0, help="reference arm: target wall time of the whole --steps/--warmup run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -390,12 +391,17 @@ def cpu_vertex_baseline(h, sample_mverts):
     n = int(min(h["verts"], sample_mverts * 1e6))
     threads = O.lib().bto_max_threads()
     out = np.empty(n, dtype=O.VERTEX_DTYPE)
-    O.lib().bto_gen_vertices(C.byref(vi), 0, min(n, 1 << 20), out.ctypes.data, threads)  # warm-up (page faults)
-    t0 = time.time()
-    O.lib().bto_gen_vertices(C.byref(vi), 0, n, out.ctypes.data, threads)
-    dt = time.time() - t0
-    return {"value": n / dt / 1e6, "unit": "Mverts/s", "cores": threads, "kind": "port",
-            "sample": f"first {n} strip vertices of view 0 of the same workload (oracle/bt_oracle.c gen_vertices, OpenMP, {threads} threads, {dt:.2f} s)"}
+    O.lib().bto_gen_vertices(C.byref(vi), 0, n, out.ctypes.data, threads)  # warm-up pass: page faults, thread pool, caches
+    passes, t0 = 0, time.time()
+    while True:   # about 10 s of CPU work (at least two passes)
+        O.lib().bto_gen_vertices(C.byref(vi), 0, n, out.ctypes.data, threads)
+        passes += 1
+        dt = time.time() - t0
+        if dt >= 10.0 and passes >= 2 or passes >= 64:
+            break
+    return {"value": passes * n / dt / 1e6, "unit": "Mverts/s", "cores": threads, "kind": "port",
+            "sample": f"{passes} passes over the first {n} strip vertices of view 0 of the same workload, after one warm-up pass "
+                      f"(oracle/bt_oracle.c gen_vertices, OpenMP, {threads} threads, {dt:.1f} s)"}
 
 
 def run_preprocess_bench(api, F, ctx, args, rank, world, barrier, reduce):
@@ -499,7 +505,7 @@ def run_reference(args):
     n_pyr = len(existing)
     pyr.close()
     setup_s = time.time() - t_setup
-    sample = int(args.ref_sample_mverts * 1e6)
+    max_verts = int(vc.vertices_per_tile) * 6000      # buffer for the largest view (~4.8 k tiles)
 
     def step(i):
         v = views[i % NUM_VIEWS]
@@ -508,12 +514,28 @@ def run_reference(args):
         h = {"tree_frame": bytes(vc), "approx": bytes(approx), "mesh": bytes(mesh), "lod_count": args.lods, "min_h": 0.0, "max_h": 500.0,
              "scale": 1000.0, "T": 512, "B": 2, "pos": v["pos"], "entries": v["entries"], "atlas": v["atlas"], "tiles": tiles}
         vi = oracle_vertex_inputs(h, F.BT_FLAG_NORMALS)
-        n = min(sample, int(ind.vertex_count))
+        n = min(step.sample, int(ind.vertex_count), max_verts)
         out = step.buf[:n]
+        t_gen = time.time()
         O.lib().bto_gen_vertices(C.byref(vi), 0, n, out.ctypes.data, threads)
+        step.gen_s = time.time() - t_gen
         return n
 
-    step.buf = np.empty(sample, dtype=O.VERTEX_DTYPE)
+    step.buf = np.empty(max_verts, dtype=O.VERTEX_DTYPE)
+    step.buf[:] = 0                                    # touch the pages once, outside every timed region
+    # bounded sample per step: calibrate on one untimed step, then size the vertex sample so that the whole
+    # --steps/--warmup run takes about --ref-budget-s seconds (capped at the whole view = the GPU arm's step)
+    step.sample = 4_000_000
+    t0 = time.time()
+    n_cal = step(0)
+    cal_s = time.time() - t0
+    rate, overhead = n_cal / max(step.gen_s, 1e-6), max(cal_s - step.gen_s, 0.0)
+    if args.ref_sample_mverts > 0:
+        step.sample = int(args.ref_sample_mverts * 1e6)
+    else:
+        per_step = args.ref_budget_s / max(args.steps + args.warmup, 1)
+        step.sample = int(min(max((per_step - overhead) * rate, 1e6), max_verts))
+    sample = step.sample
     for i in range(args.warmup):
         step(i)
     t0 = time.time()
@@ -529,7 +551,7 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "Mverts/s", "cores": threads, "kind": "port",
-                         "sample": f"per step: select (1 view) + the first {sample} strip vertices of that view; oracle/ (C port of the reference WGSL), OpenMP {threads} threads"},
+                         "sample": f"per step: select (1 view) + up to {sample} strip vertices of that view (sized from --ref-budget-s; a whole view has 36-41 M); oracle/ (C port of the reference WGSL), OpenMP {threads} threads"},
         "e2e": {"value": value, "unit": "Mverts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference ships no CPU implementation of this path (SURVEY F3) and cannot be built here (no Rust/WGSL toolchain): this arm times the CPU restatement under oracle/",
