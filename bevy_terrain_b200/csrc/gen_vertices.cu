@@ -405,7 +405,9 @@ struct GenSmemHeader {
 //     filled with the next item's work
 //   * one store warp waits on full[b], issues the item's TMA bulk stores, waits until they have READ the image
 //     (cp.async.bulk.wait_group.read) and arrives on empty[b], which the compute warps wait on before reusing image b
-template <bool SPHERICAL>
+// FLAGS_CT >= 0: the flag word is a compile-time constant (the two common sets get their own instantiation, so the flag
+// branches and the code of the disabled features disappear); FLAGS_CT < 0: generic kernel, flags read from the parameters.
+template <bool SPHERICAL, int FLAGS_CT>
 __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     GenSmemHeader& H = *reinterpret_cast<GenSmemHeader*>(smem_raw);
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
             const uint32_t i = (c << 5) + (uint32_t)lane;
             if (i < n_verts) {
                 const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
-                const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, P.flags, tile, tile_index, c0 + lx, gy);
+                const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags, tile, tile_index, c0 + lx, gy);
                 // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
                 if (lx < n_strips) {
                     store_record<1>(image, strip_stride, lx, 2u * gy + 1u, r);
@@ -553,11 +555,21 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
         P.magic_cols_ragged = 0xFFFFFFFFu / (last_strips + 1u) + 1u;
     }
     const size_t smem = header + (size_t)GEN_BUFFERS * P.image_bytes;
-    cudaError_t e = cudaFuncSetAttribute(spherical ? gen_vertices_kernel<true> : gen_vertices_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // kernels specialised for the common flag sets (measured: 6 % faster than the generic kernel for NORMALS, 3 % for the
+    // reference default + NORMALS); everything else (HIGH_PRECISION, partial sets) takes the generic one
+    constexpr int kNone = 0, kNormals = BT_FLAG_NORMALS, kMorphBlend = BT_FLAG_MORPH | BT_FLAG_BLEND, kDefault = kMorphBlend | BT_FLAG_NORMALS;
+    const uint32_t vertex_flags = flags & (BT_FLAG_MORPH | BT_FLAG_BLEND | BT_FLAG_HIGH_PRECISION | BT_FLAG_NORMALS);
+    void (*kernel)(const GenParams);
+    switch (vertex_flags) {
+        case kNone: kernel = spherical ? gen_vertices_kernel<true, kNone> : gen_vertices_kernel<false, kNone>; break;
+        case kNormals: kernel = spherical ? gen_vertices_kernel<true, kNormals> : gen_vertices_kernel<false, kNormals>; break;
+        case kMorphBlend: kernel = spherical ? gen_vertices_kernel<true, kMorphBlend> : gen_vertices_kernel<false, kMorphBlend>; break;
+        case kDefault: kernel = spherical ? gen_vertices_kernel<true, kDefault> : gen_vertices_kernel<false, kDefault>; break;
+        default: kernel = spherical ? gen_vertices_kernel<true, -1> : gen_vertices_kernel<false, -1>; break;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (sm_count > 0 ? sm_count : 148) * GEN_CTAS_PER_SM;
-    if (spherical) gen_vertices_kernel<true><<<grid, GEN_THREADS, smem, stream>>>(P);
-    else gen_vertices_kernel<false><<<grid, GEN_THREADS, smem, stream>>>(P);
+    kernel<<<grid, GEN_THREADS, smem, stream>>>(P);
     return cudaGetLastError();
 }
