@@ -94,4 +94,20 @@ impl TerrainView {
         Ok(vb)
     }
 }
+impl TerrainView {
+    /// One frame in one call (update + select + generate + overlapped tile-list read-back): the path `bench.py` times as `e2e`.
+    pub fn run_frame(&mut self, frame: &ffi::bt_view_frame, select_flags: u32, gen_flags: u32, tiles: &mut Vec<ffi::bt_tile>)
+        -> Result<(ffi::bt_indirect, ffi::bt_vertex_buffer)> {
+        let mut count = 0u32;
+        let mut indirect = ffi::bt_indirect::default();
+        let mut vb = ffi::bt_vertex_buffer { vertices: ptr::null_mut(), capacity: 0 };
+        let cap = tiles.capacity() as u32;
+        check(self.ctx, unsafe {
+            ffi::bt_view_run_frame(self.raw, frame, select_flags, gen_flags, ptr::null_mut(), tiles.as_mut_ptr(), cap, &mut count, &mut indirect, &mut vb)
+        })?;
+        unsafe { tiles.set_len(count.min(cap) as usize) };
+        Ok((indirect, vb))
+    }
+}
+
 impl Drop for TerrainView { fn drop(&mut self) { unsafe { ffi::bt_view_destroy(self.raw) } } }
