@@ -1,4 +1,4 @@
-"""World-size-2 `gloo` test (CPU) of the N>1 preprocess path.
+"""World-size-2 and -4 `gloo` tests (CPU) of the N>1 preprocess path.
 
 What runs where:
   * the PRODUCT's host-side sharding logic — row ownership, ghost/replica tiles, the byte layout of the
@@ -153,9 +153,9 @@ def _worker(rank, world, port, fmt, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fmt", [F.BT_FORMAT_R16, F.BT_FORMAT_RGBA8])
-def test_sharded_preprocess_exchange_world2_gloo(fmt, tmp_path):
-    world = 2
+@pytest.mark.parametrize("fmt,world", [(F.BT_FORMAT_R16, 2), (F.BT_FORMAT_RGBA8, 2), (F.BT_FORMAT_R16, 4)])
+def test_sharded_preprocess_exchange_gloo(fmt, world, tmp_path):
+    """world 2: the sub-root level is LOD 1; world 4: LOD 2, two redundant top levels, interior ranks with halos on both sides"""
     mp.spawn(_worker, args=(world, _free_port(), fmt, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
