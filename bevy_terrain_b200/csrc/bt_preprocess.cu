@@ -112,6 +112,9 @@ uint32_t f32_to_u32(float x) {
 
 uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << (l + 1)) <= v) ++l; return l; }
 
+// TileCoordinate::neighbours order — coordinate.rs:209-218: top, right, bottom, left, TL, TR, BR, BL
+constexpr int32_t kNeighbourOffsets[8][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+
 }  // namespace
 
 struct bt_preprocessor {
@@ -144,6 +147,9 @@ struct bt_preprocessor {
         *y0 = (uint32_t)((uint64_t)shard.rank * n / shard.world);
         *y1 = (uint32_t)((uint64_t)(shard.rank + 1) * n / shard.world);
     }
+
+    // rank that owns tile row y of `lod` (lod >= root_lod; the band split is the same on every cube face)
+    uint32_t owner_of_row(uint32_t lod, uint32_t y) const { return (uint32_t)((uint64_t)y * shard.world >> lod); }
 
     uint32_t get_or_allocate(Store& s, const TileKey& k, uint32_t job, uint8_t kind_) {
         auto it = s.slot_of.find(k);
@@ -228,11 +234,19 @@ struct bt_preprocessor {
                         for (uint32_t x = lo[0]; x < hi[0]; ++x)
                             for (uint32_t y = lo[1]; y < hi[1]; ++y)
                                 if (y < y0 || y >= y1) get_or_allocate(s, TileKey{d.side, lod, x, y}, ji, kReplica);
-                    } else {  // ghost rows that receive the halo strips of the adjacent ranks
+                    } else if (!spherical()) {  // ghost rows that receive the halo strips of the adjacent ranks
                         for (uint32_t x = lo[0]; x < hi[0]; ++x) {
                             if (y0 > lo[1]) get_or_allocate(s, TileKey{d.side, lod, x, y0 - 1}, ji, kGhost);
                             if (y1 < hi[1]) get_or_allocate(s, TileKey{d.side, lod, x, y1}, ji, kGhost);
                         }
+                    } else {  // cube: every neighbour (same face or across a face edge) of an owned tile that another rank owns
+                        for (uint32_t x = lo[0]; x < hi[0]; ++x)
+                            for (uint32_t y = std::max(lo[1], y0); y < std::min(hi[1], y1); ++y)
+                                for (int k = 0; k < 8; ++k) {
+                                    const TileKey self{d.side, lod, x, y};
+                                    const TileKey nb = neighbour_coordinate(self, (int32_t)x + kNeighbourOffsets[k][0], (int32_t)y + kNeighbourOffsets[k][1], true);
+                                    if (!(nb == kInvalidTile) && owner_of_row(lod, nb.y) != shard.rank) get_or_allocate(s, nb, ji, kGhost);
+                                }
                     }
                 }
             }
@@ -306,7 +320,6 @@ struct bt_preprocessor {
             if (tasks.size() > first) P.levels.push_back(Level{(uint32_t)lod, Range{first, (uint32_t)tasks.size() - first}});
         }
         // stitch: every LOD in one launch (reads only neighbour CENTRES, all final after the downsample phase)
-        static const int32_t kOffsets[8][2] = {{0, -1}, {1, 0}, {0, 1}, {-1, 0}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};  // coordinate.rs:209-218
         const uint32_t stitch_first = (uint32_t)tasks.size();
         for (uint32_t di = 0; di < j.datasets.size(); ++di) {
             const bt_dataset& d = j.datasets[di];
@@ -316,7 +329,7 @@ struct bt_preprocessor {
                 for (size_t i = f; i < tasks.size(); ++i) {
                     const TileKey self{tasks[i].tile.side, tasks[i].tile.lod, tasks[i].tile.x, tasks[i].tile.y};
                     for (int k = 0; k < 8; ++k) {  // TileCoordinate::neighbours — coordinate.rs:208-225
-                        const TileKey nb = neighbour_coordinate(self, (int32_t)self.x + kOffsets[k][0], (int32_t)self.y + kOffsets[k][1], spherical());
+                        const TileKey nb = neighbour_coordinate(self, (int32_t)self.x + kNeighbourOffsets[k][0], (int32_t)self.y + kNeighbourOffsets[k][1], spherical());
                         tasks[i].dep[k] = get_tile(s, nb, ji);
                         tasks[i].dep_side[k] = nb.side;
                     }
@@ -390,16 +403,22 @@ struct bt_preprocessor {
         const bt_dataset& d = j.datasets[0];
         const uint32_t C = s.cfg.texture_size - 2 * s.cfg.border_size;
         uint64_t bytes = 0;
-        for (uint32_t lod = std::max(d.lod_begin, root_lod + 1); lod < d.lod_end; ++lod)
-            bytes += 2ull * (1u << lod) * s.cfg.border_size * C * s.px;
+        for (uint32_t lod = std::max(d.lod_begin, root_lod + 1); lod < d.lod_end; ++lod) {
+            if (!spherical()) bytes += 2ull * (1u << lod) * s.cfg.border_size * C * s.px;
+            else bytes += (uint64_t)j.datasets.size() * cube_strips_per_side(lod) * s.cfg.border_size * C * s.px;
+        }
         return bytes;
     }
     uint64_t roots_bytes(const Job& j) const {
         if (shard.world == 1) return 0;
         const bt_dataset& d = j.datasets[0];
         if (d.lod_begin > root_lod) return 0;  // no level above the shard boundary is requested... but root tiles still needed by nobody
-        return (uint64_t)(1u << root_lod) * stores[j.attachment].tile_bytes;  // one row of the root level
+        return (uint64_t)j.datasets.size() * (1u << root_lod) * stores[j.attachment].tile_bytes;  // one row of the root level per dataset (cube face)
     }
+    // cube halo: per LOD and face a rank sends the outward strips of its band-boundary and face-edge tiles, in this order:
+    // [top strips of row y0, x ascending][bottom strips of row y1-1][left strips of column 0, y ascending][right strips of
+    // column n-1]; every strip is border_size x center_size pixels, so an entry's offset is its index times one strip size.
+    uint64_t cube_strips_per_side(uint32_t lod) const { const uint64_t n = 1ull << lod; return 2 * n + 2 * (n / shard.world); }
 };
 
 extern "C" {
@@ -410,10 +429,6 @@ bt_status bt_preprocessor_create(bt_context* ctx, uint32_t kind, const bt_attach
     if (kind != BT_KIND_PLANAR && kind != BT_KIND_SPHERICAL) return BT_ERR_INVALID_ARG;
     if (shard.world == 0 || shard.rank >= shard.world || (shard.world & (shard.world - 1)) != 0) {
         BT_SET_ERROR(ctx, "bt_preprocessor_create: shard world must be a power of two and rank < world");
-        return BT_ERR_INVALID_ARG;
-    }
-    if (shard.world > 1 && kind == BT_KIND_SPHERICAL) {
-        BT_SET_ERROR(ctx, "bt_preprocessor_create: sharding a spherical (cross-face stitched) pyramid is not supported yet");
         return BT_ERR_INVALID_ARG;
     }
     bt_preprocessor* p = new bt_preprocessor();
@@ -456,7 +471,10 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
     Job j;
     j.attachment = datasets[0].attachment_index;
     if (j.attachment >= p->stores.size()) { BT_SET_ERROR(ctx, "add_datasets: attachment_index %u out of range", j.attachment); return BT_ERR_INVALID_ARG; }
-    if (p->shard.world > 1 && count != 1) { BT_SET_ERROR(ctx, "add_datasets: sharded preprocessing takes one dataset per job"); return BT_ERR_INVALID_ARG; }
+    if (p->shard.world > 1 && count != (p->spherical() ? 6u : 1u)) {
+        BT_SET_ERROR(ctx, "add_datasets: sharded preprocessing takes one dataset per job (planar) or the six cube faces of one attachment (spherical)");
+        return BT_ERR_INVALID_ARG;
+    }
     uint32_t side_mask = 0;
     for (uint32_t i = 0; i < count; ++i) {
         const bt_dataset& d = datasets[i];
@@ -487,6 +505,12 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
             }
         }
     }
+    if (p->shard.world > 1)
+        for (uint32_t i = 1; i < count; ++i)
+            if (datasets[i].lod_begin != datasets[0].lod_begin || datasets[i].lod_end != datasets[0].lod_end) {
+                BT_SET_ERROR(ctx, "add_datasets: the six faces of a sharded job must share one lod_range");
+                return BT_ERR_INVALID_ARG;
+            }
     if (!p->plan_only()) BT_CUDA(ctx, cudaSetDevice(ctx->device));
     const Store& s = p->stores[j.attachment];
     for (uint32_t i = 0; i < count; ++i) {
@@ -562,15 +586,16 @@ static void exchange_plan(const bt_preprocessor* p, const Job& j, uint32_t kind,
     const bt_dataset& d = j.datasets[0];
     const uint32_t T = s.cfg.texture_size, B = s.cfg.border_size, C = T - 2 * B;
     const uint32_t rank = p->shard.rank, world = p->shard.world;
-    if (kind == 1) {  // one row of the root level per rank, tiles x-major
+    if (kind == 1) {  // one row of the root level per rank and dataset (cube face), tiles x-major
         const uint64_t per_rank = p->roots_bytes(j);
         if (per_rank == 0) return;
         const uint32_t n = 1u << p->root_lod;
         for (uint32_t r = 0; r < world; ++r) {
             if (unpack ? r == rank : r != rank) continue;
-            for (uint32_t x = 0; x < n; ++x)
-                out.push_back(bt_exchange_copy{bt_tile{d.side, p->root_lod, x, r}, 0u, 0u, T * T, r,
-                                               (unpack ? (uint64_t)r * per_rank : 0ull) + (uint64_t)x * s.tile_bytes});
+            for (uint32_t di = 0; di < j.datasets.size(); ++di)
+                for (uint32_t x = 0; x < n; ++x)
+                    out.push_back(bt_exchange_copy{bt_tile{j.datasets[di].side, p->root_lod, x, r}, 0u, 0u, T * T, r,
+                                                   (unpack ? (uint64_t)r * per_rank : 0ull) + ((uint64_t)di * n + x) * s.tile_bytes});
         }
         return;
     }
@@ -578,6 +603,52 @@ static void exchange_plan(const bt_preprocessor* p, const Job& j, uint32_t kind,
     if (per_rank == 0) return;
     const uint64_t row_bytes = (uint64_t)C * s.px;
     uint64_t offset = 0;
+    if (p->spherical()) {
+        // cube: strips of band-boundary and face-edge tiles (layout: bt_preprocessor::cube_strips_per_side)
+        const uint64_t strip = (uint64_t)B * row_bytes;
+        uint32_t dataset_of_side[6] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t di = 0; di < j.datasets.size(); ++di) dataset_of_side[j.datasets[di].side] = di;
+        // emits the row segments of strip `which` (0 top, 1 bottom, 2 left, 3 right) of `tile`, stored at `at` in the buffer
+        auto emit = [&](const TileKey& t, uint32_t which, uint32_t src_rank, uint64_t at) {
+            const bt_tile bt{t.side, t.lod, t.x, t.y};
+            if (which < 2)
+                for (uint32_t b = 0; b < B; ++b) out.push_back(bt_exchange_copy{bt, (which == 0 ? B : C) + b, B, C, src_rank, at + (uint64_t)b * row_bytes});
+            else
+                for (uint32_t i = 0; i < C; ++i) out.push_back(bt_exchange_copy{bt, B + i, which == 2 ? B : C, B, src_rank, at + (uint64_t)i * B * s.px});
+        };
+        for (uint32_t lod = std::max(d.lod_begin, p->root_lod + 1); lod < d.lod_end; ++lod) {
+            const uint32_t n = 1u << lod, h = n / world;
+            const uint64_t per_side = p->cube_strips_per_side(lod);
+            if (!unpack) {
+                const uint32_t y0 = rank * h, y1 = y0 + h;
+                for (uint32_t di = 0; di < j.datasets.size(); ++di) {
+                    const uint32_t side = j.datasets[di].side;
+                    const uint64_t base = offset + (uint64_t)di * per_side * strip;
+                    for (uint32_t x = 0; x < n; ++x) {
+                        emit(TileKey{side, lod, x, y0}, 0, rank, base + (uint64_t)x * strip);
+                        emit(TileKey{side, lod, x, y1 - 1}, 1, rank, base + (uint64_t)(n + x) * strip);
+                    }
+                    for (uint32_t y = y0; y < y1; ++y) {
+                        emit(TileKey{side, lod, 0, y}, 2, rank, base + (uint64_t)(2 * n + (y - y0)) * strip);
+                        emit(TileKey{side, lod, n - 1, y}, 3, rank, base + (uint64_t)(2 * n + h + (y - y0)) * strip);
+                    }
+                }
+            } else {
+                for (uint32_t slot = 0; slot < s.keys.size(); ++slot) {   // every ghost tile of this LOD: all strips its owner sends
+                    const TileKey& g = s.keys[slot];
+                    if (s.kind[slot] != kGhost || g.lod != lod) continue;
+                    const uint32_t q = p->owner_of_row(lod, g.y), qy0 = q * h;
+                    const uint64_t base = (uint64_t)q * per_rank + offset + (uint64_t)dataset_of_side[g.side] * per_side * strip;
+                    if (g.y == qy0) emit(g, 0, q, base + (uint64_t)g.x * strip);
+                    if (g.y == qy0 + h - 1) emit(g, 1, q, base + (uint64_t)(n + g.x) * strip);
+                    if (g.x == 0) emit(g, 2, q, base + (uint64_t)(2 * n + (g.y - qy0)) * strip);
+                    if (g.x == n - 1) emit(g, 3, q, base + (uint64_t)(2 * n + h + (g.y - qy0)) * strip);
+                }
+            }
+            offset += (uint64_t)j.datasets.size() * per_side * strip;
+        }
+        return;
+    }
     for (uint32_t lod = std::max(d.lod_begin, p->root_lod + 1); lod < d.lod_end; ++lod) {
         const uint32_t n = 1u << lod;
         uint32_t y0, y1;
@@ -601,6 +672,8 @@ static void exchange_plan(const bt_preprocessor* p, const Job& j, uint32_t kind,
     }
 }
 
+constexpr uint64_t kCopyChunk = 8192;
+
 static bt_status run_exchange(bt_preprocessor* p, const Job& j, uint32_t kind, bool unpack, unsigned char* buffer, cudaStream_t stream) {
     Store& s = p->stores[j.attachment];
     std::vector<bt_exchange_copy> plan;
@@ -612,7 +685,10 @@ static bt_status run_exchange(bt_preprocessor* p, const Job& j, uint32_t kind, b
                               ((size_t)c.tile_row * s.cfg.texture_size + c.tile_col) * s.px;
         unsigned char* buf = buffer + c.buffer_offset;
         const uint64_t bytes = (uint64_t)c.pixels * s.px;
-        copies.push_back(unpack ? RowCopy{buf, tile, bytes} : RowCopy{tile, buf, bytes});
+        for (uint64_t o = 0; o < bytes; o += kCopyChunk) {   // one warp copies one chunk (whole root tiles are split)
+            const uint64_t nb = std::min<uint64_t>(kCopyChunk, bytes - o);
+            copies.push_back(unpack ? RowCopy{buf + o, tile + o, nb} : RowCopy{tile + o, buf + o, nb});
+        }
     }
     BT_CUDA(p->ctx, cudaStreamSynchronize(stream));  // an earlier launch may still read d_copies
     bt_status st = p->upload(&p->d_copies, &p->d_copies_cap, copies, stream);
@@ -679,7 +755,7 @@ static bt_status exchange_entry(bt_preprocessor* p, uint32_t kind, bool unpack, 
     }
     if (unpack && kind == 1) {
         if (bytes) {  // the levels above the shard boundary: every rank computes them (21 tiles at world = 8)
-            bt_status st = p->run_levels((uint32_t)ji, p->root_lod, j.datasets[0].lod_begin, false, (cudaStream_t)stream);
+            bt_status st = p->run_levels((uint32_t)ji, p->root_lod, j.datasets[0].lod_begin, false, (cudaStream_t)stream);   // (all datasets of a sharded job share one lod_range)
             if (st != BT_OK) return st;
         }
         j.roots_done = true;

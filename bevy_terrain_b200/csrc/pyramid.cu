@@ -522,23 +522,25 @@ extern "C" cudaError_t bt_launch_selftest(const float* x, float* log2_out, uint3
 // row copies of the multi-GPU halo / root exchange (pack into / unpack from the NCCL buffers)
 // ------------------------------------------------------------------------------------------------
 namespace btd {
-__global__ void row_copy_kernel(const RowCopy* __restrict__ copies) {
-    const RowCopy c = copies[blockIdx.x];
+// one warp per copy: the planar halo has few long rows (C pixels), the cube halo also many short ones (border_size pixels)
+__global__ void row_copy_kernel(const RowCopy* __restrict__ copies, uint32_t n_copies) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (w >= n_copies) return;
+    const RowCopy c = copies[w];
     const uint16_t* s = static_cast<const uint16_t*>(c.src);
     uint16_t* d = static_cast<uint16_t*>(c.dst);
-    const uint64_t n = c.bytes / 2;
     if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0 && (c.bytes & 15u) == 0) {
         const uint4* s4 = reinterpret_cast<const uint4*>(s);
         uint4* d4 = reinterpret_cast<uint4*>(d);
-        for (uint64_t i = threadIdx.x; i < c.bytes / 16; i += blockDim.x) d4[i] = s4[i];
+        for (uint64_t i = lane; i < c.bytes / 16; i += 32) d4[i] = s4[i];
     } else {
-        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        for (uint64_t i = lane; i < c.bytes / 2; i += 32) d[i] = s[i];
     }
 }
 }  // namespace btd
 
 extern "C" cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    btd::row_copy_kernel<<<n, 256, 0, stream>>>(copies);
+    btd::row_copy_kernel<<<(n + 7u) / 8u, 256, 0, stream>>>(copies, n);
     return cudaGetLastError();
 }

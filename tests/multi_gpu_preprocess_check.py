@@ -74,9 +74,33 @@ def main():
             pre.close()
             if windowed:
                 ctx.free(dptr)
+    # ---- cube: six faces of one attachment per job; every rank owns the same row band of each face, ghosts across face edges
+    Ts, Ls, Ss = 32, 4, 160
+    for fmt, afmt in ((F.BT_FORMAT_R16, api.AttachmentFormat.R16), (F.BT_FORMAT_RGBA8, api.AttachmentFormat.Rgba8)):
+        if (1 << (Ls - 1)) < world:
+            continue
+        faces = [O.synth_source(fmt, Ss, Ss, seed=900 + 31 * side, holes=True) for side in range(6)]
+        truth = O.Pyramid(F.BT_KIND_SPHERICAL, fmt, Ts, B, Ls)
+        truth.add_datasets([O.make_dataset(faces[side], side=side, lod_range=(0, Ls)) for side in range(6)])
+        truth.run()
+        cfg = api.TerrainConfig(lod_count=Ls, model=api.TerrainModel.sphere((0, 0, 0), 1.0, 0.0, 1.0))
+        cfg.add_attachment(api.AttachmentConfig(name="a", texture_size=Ts, border_size=B, format=afmt))
+        pre = api.Preprocessor(ctx, cfg, rank=rank, world=world)
+        pre.preprocess_spherical(api.SphericalDataset(faces=faces, lod_range=range(0, Ls)))
+        sharded_run(pre, world)
+        torch.cuda.synchronize()
+        mine = [tuple(int(v) for v in t) for t in pre.tiles()]
+        for tc in mine:
+            got, exp = pre.get_tile(0, tc), truth.tile(*tc)
+            assert np.array_equal(got, exp), f"rank {rank} fmt {fmt} cube: tile {tc} differs ({int((got != exp).sum())} texels)"
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        union = [t for lst in gathered for t in lst]
+        assert len(union) == len(set(union)) == 6 * (4 ** Ls - 1) // 3, (len(union), len(set(union)))
+        pre.close()
     dist.barrier()
     if rank == 0:
-        print(f"MULTI_GPU_PREPROCESS_OK world={world}")
+        print(f"MULTI_GPU_PREPROCESS_OK world={world} (planar + cube)")
     ctx.close()
     dist.destroy_process_group()
 

@@ -34,16 +34,18 @@ def _free_port():
     return p
 
 
-def _plan(lib, rank, world, fmt):
+def _plan(lib, rank, world, fmt, kind=F.BT_KIND_PLANAR):
     att = (F.AttachmentConfig * 1)(F.AttachmentConfig(T, B, 1, fmt))
     h = C.c_void_p()
-    assert lib.bt_preprocessor_create(None, F.BT_KIND_PLANAR, att, 1, L, F.Shard(rank, world), C.byref(h)) == F.BT_OK
-    d = F.Dataset()
-    d.attachment_index, d.side = 0, 0
-    d.top_left[:] = [0.0, 0.0]
-    d.bottom_right[:] = [1.0, 1.0]
-    d.lod_begin, d.lod_end, d.width, d.height = 0, L, SRC, SRC
-    assert lib.bt_preprocessor_add_datasets(h, C.byref(d), 1) == F.BT_OK
+    assert lib.bt_preprocessor_create(None, kind, att, 1, L, F.Shard(rank, world), C.byref(h)) == F.BT_OK
+    sides = 6 if kind == F.BT_KIND_SPHERICAL else 1
+    ds = (F.Dataset * sides)()
+    for side, d in enumerate(ds):
+        d.attachment_index, d.side = 0, side
+        d.top_left[:] = [0.0, 0.0]
+        d.bottom_right[:] = [1.0, 1.0]
+        d.lod_begin, d.lod_end, d.width, d.height = 0, L, SRC, SRC
+    assert lib.bt_preprocessor_add_datasets(h, ds, sides) == F.BT_OK
     assert lib.bt_preprocessor_plan(h) == F.BT_OK
     return h
 
@@ -56,7 +58,7 @@ def _exchange_plan(lib, h, kind, unpack):
     return buf[: n.value]
 
 
-def _worker(rank, world, port, fmt, out_dir):
+def _worker(rank, world, port, fmt, out_dir, kind=F.BT_KIND_PLANAR):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -65,16 +67,18 @@ def _worker(rank, world, port, fmt, out_dir):
         OL = O.lib()
         px = 2 if fmt == F.BT_FORMAT_R16 else 4
         dt, shape = (np.uint16, (T, T)) if fmt == F.BT_FORMAT_R16 else (np.uint8, (T, T, 4))
-        src = O.synth_source(fmt, SRC, SRC, seed=77, holes=True)
+        spherical = kind == F.BT_KIND_SPHERICAL
+        sides = 6 if spherical else 1
+        srcs = [O.synth_source(fmt, SRC, SRC, seed=77 + 13 * side, holes=True) for side in range(sides)]
         # truth: single-rank oracle pyramid; `pre`: the same after split+downsample only
-        truth = O.Pyramid(F.BT_KIND_PLANAR, fmt, T, B, L)
-        truth.add_datasets([O.make_dataset(src, lod_range=(0, L))])
+        truth = O.Pyramid(kind, fmt, T, B, L)
+        truth.add_datasets([O.make_dataset(srcs[side], side=side, lod_range=(0, L)) for side in range(sides)])
         truth.run()
-        pre = O.Pyramid(F.BT_KIND_PLANAR, fmt, T, B, L)
-        pre.add_datasets([O.make_dataset(src, lod_range=(0, L))])
+        pre = O.Pyramid(kind, fmt, T, B, L)
+        pre.add_datasets([O.make_dataset(srcs[side], side=side, lod_range=(0, L)) for side in range(sides)])
         pre.run(phases=1)
 
-        h = _plan(lib, rank, world, fmt)
+        h = _plan(lib, rank, world, fmt, kind)
         n = F.u32()
         lib.bt_preprocessor_plan_tiles(h, 0, None, None, 0, C.byref(n))
         tiles = (F.Tile * n.value)()
@@ -112,14 +116,15 @@ def _worker(rank, world, port, fmt, out_dir):
         rb, hb = F.u64(), F.u64()
         lib.bt_preprocessor_roots_bytes(h, C.byref(rb))
         lib.bt_preprocessor_halo_bytes(h, C.byref(hb))
-        assert rb.value == (1 << root_lod) * T * T * px
+        assert rb.value == sides * (1 << root_lod) * T * T * px
         exchange(1, rb.value)
         # the levels above the shard boundary, computed redundantly on every rank from the gathered root level
         for lod in range(root_lod - 1, -1, -1):
-            for x in range(1 << lod):
-                for y in range(1 << lod):
-                    child = (C.c_void_p * 4)(*[store[(0, lod + 1, 2 * x + c % 2, 2 * y + c // 2)].ctypes.data for c in range(4)])
-                    OL.bto_downsample_tile_raw(fmt, T, B, store[(0, lod, x, y)].ctypes.data, child)
+            for side in range(sides):
+                for x in range(1 << lod):
+                    for y in range(1 << lod):
+                        child = (C.c_void_p * 4)(*[store[(side, lod + 1, 2 * x + c % 2, 2 * y + c // 2)].ctypes.data for c in range(4)])
+                        OL.bto_downsample_tile_raw(fmt, T, B, store[(side, lod, x, y)].ctypes.data, child)
         exchange(0, hb.value)
         # stitch what this rank stitches on the GPU: its owned rows (and every tile of the redundant top levels)
         for key, k in kind_of.items():
@@ -127,7 +132,7 @@ def _worker(rank, world, port, fmt, out_dir):
                 continue
             nb = (F.Tile * 8)()
             t = F.Tile(*key)
-            OL.bto_tile_neighbours(C.byref(t), 0, nb)
+            OL.bto_tile_neighbours(C.byref(t), int(spherical), nb)
             ptrs = (C.c_void_p * 8)()
             for i in range(8):
                 nk = (nb[i].side, nb[i].lod, nb[i].x, nb[i].y)
@@ -153,10 +158,12 @@ def _worker(rank, world, port, fmt, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fmt,world", [(F.BT_FORMAT_R16, 2), (F.BT_FORMAT_RGBA8, 2), (F.BT_FORMAT_R16, 4)])
-def test_sharded_preprocess_exchange_gloo(fmt, world, tmp_path):
-    """world 2: the sub-root level is LOD 1; world 4: LOD 2, two redundant top levels, interior ranks with halos on both sides"""
-    mp.spawn(_worker, args=(world, _free_port(), fmt, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("fmt,world,kind", [(F.BT_FORMAT_R16, 2, F.BT_KIND_PLANAR), (F.BT_FORMAT_RGBA8, 2, F.BT_KIND_PLANAR), (F.BT_FORMAT_R16, 4, F.BT_KIND_PLANAR),
+                                            (F.BT_FORMAT_R16, 2, F.BT_KIND_SPHERICAL), (F.BT_FORMAT_RGBA8, 4, F.BT_KIND_SPHERICAL)])
+def test_sharded_preprocess_exchange_gloo(fmt, world, kind, tmp_path):
+    """world 2: the sub-root level is LOD 1; world 4: LOD 2, two redundant top levels, interior ranks with halos on both sides;
+    spherical: six faces, every rank owns the same row band of each face, ghosts across face edges (rotated neighbours)"""
+    mp.spawn(_worker, args=(world, _free_port(), fmt, str(tmp_path), kind), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
 
