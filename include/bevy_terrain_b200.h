@@ -393,7 +393,9 @@ void      bt_preprocessor_destroy(bt_preprocessor* p);
  * task list; successive calls for one attachment overlay in call order (split.wgsl:36-42
  * fall-through).  count > 1 (e.g. the 6 cube faces): Preprocessor::preprocess_spherical ordering
  * (:314-343) — split/downsample ALL datasets, barrier, then per LOD per dataset stitch, so that
- * cross-face neighbours exist when the stitch tasks resolve them.                             */
+ * cross-face neighbours exist when the stitch tasks resolve them.
+ * Sharded preprocessors (shard.world > 1) take full-coverage datasets: one per job (planar) or the six cube
+ * faces of one attachment with a common lod_range (spherical).                                */
 bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* datasets, uint32_t count);
 /* optional: allocate the device pyramid store of all pending jobs now (keeps cudaMalloc out of run_*) */
 bt_status bt_preprocessor_reserve(bt_preprocessor* p, void* stream);
