@@ -26,8 +26,11 @@ constexpr uint32_t SELECT_SMEM_TILES = 4096;  // per frontier buffer (2 x 64 KiB
 // compute_subdivision_coordinate + approximate_view_distance + should_be_divided
 // (functions.wgsl:133-154,117-131; refine_tiles.wgsl:17-22).  HIGH_PRECISION is compiled out in the
 // prepass (tiling_prepass.rs:61-78 only sets SPHERICAL/TEST*).
+// `planar_normal`: normal_local_to_world of a planar terrain does not depend on the tile (normalize(normal_matrix * +Y)); the
+// caller evaluates it once per thread, which takes a 40-instruction dependent chain (sqrt, reciprocal, three quotients) out of
+// every level of this latency-bound kernel.  Same operations on the same operands, so the same bits.
 template <bool SPHERICAL>
-__device__ __forceinline__ bool should_be_divided(const ViewUniforms& U, const bt_tile& tile) {
+__device__ __forceinline__ bool should_be_divided(const ViewUniforms& U, const bt_tile& tile, const Vec3& planar_normal) {
     const bt_side_parameter& p = U.approximation.sides[tile.side];
     Coord v{tile.side, U.approximation.origin_lod, (uint32_t)p.view_xy[0], (uint32_t)p.view_xy[1], p.view_uv[0], p.view_uv[1]};
     change_lod(v, tile.lod);
@@ -39,7 +42,7 @@ __device__ __forceinline__ bool should_be_divided(const ViewUniforms& U, const b
     Coord c{tile.side, tile.lod, tile.x, tile.y, u, w};
     Vec3 lp = local_position<SPHERICAL>(c);
     Vec3 wp = position_local_to_world(U.mesh, lp);
-    Vec3 wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+    Vec3 wn = SPHERICAL ? normal_local_to_world<SPHERICAL>(U.mesh, lp) : planar_normal;
     float h = U.approximation.approximate_height;
     const float* e = U.culling.world_position;
     Vec3 q{(wp.x + h * wn.x) - e[0], (wp.y + h * wn.y) - e[1], (wp.z + h * wn.z) - e[2]};
@@ -108,6 +111,7 @@ select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restri
     mbar_wait_cta(&S.bar, 0);
 
     const ViewUniforms& U = S.U;
+    const Vec3 planar_normal = SPHERICAL ? Vec3{0.0f, 0.0f, 0.0f} : normal_local_to_world<false>(U.mesh, Vec3{0.0f, 0.0f, 0.0f});
     const uint32_t refinement_count = U.view_config.refinement_count;
     bt_tile* cur = S.frontier[0];
     uint32_t n_cur = n_roots;
@@ -134,7 +138,7 @@ select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restri
             if (valid) {
                 tile = cur[i];
                 if ((flags & BT_FLAG_FRUSTUM_CULL) && tile_outside_frustum<SPHERICAL>(U, tile)) valid = false;  // culled: neither refined nor emitted
-                else divide = should_be_divided<SPHERICAL>(U, tile);
+                else divide = should_be_divided<SPHERICAL>(U, tile, planar_normal);
             }
             const uint32_t div_mask = __ballot_sync(0xffffffffu, valid && divide);
             const uint32_t fin_mask = __ballot_sync(0xffffffffu, valid && !divide);
