@@ -187,3 +187,74 @@ def test_shard_plan_partitions_rows_for_world_1_2_4_8():
             assert hb.value == exp
             lib.bt_preprocessor_destroy(h)
         assert len(owned) == len(set(owned)) == (4 ** L - 1) // 3, (world, len(owned))
+
+
+def test_cube_shard_plan_partitions_all_six_faces():
+    """plan-only preprocessor (no GPU): for world 1..8 the owned tiles of all ranks partition the six-face pyramid, every ghost
+    lies above the root level and is a neighbour (possibly across a face edge) of an owned tile, and the unpack plan of every
+    rank covers exactly its ghost tiles"""
+    from tests import oracle as O
+    lib, OL = F.load_library(), O.lib()
+    for world in (1, 2, 4, 8):
+        owned_all = []
+        root = int(np.log2(world))
+        for rank in range(world):
+            h = _plan(lib, rank, world, F.BT_FORMAT_R16, F.BT_KIND_SPHERICAL)
+            n = F.u32()
+            lib.bt_preprocessor_plan_tiles(h, 0, None, None, 0, C.byref(n))
+            tiles, kinds = (F.Tile * n.value)(), (F.u32 * n.value)()
+            lib.bt_preprocessor_plan_tiles(h, 0, tiles, kinds, n.value, C.byref(n))
+            keys = [(t.side, t.lod, t.x, t.y) for t in tiles]
+            owned = {k for k, kd in zip(keys, kinds) if kd == 0}
+            ghosts = {k for k, kd in zip(keys, kinds) if kd == 1}
+            owned_all += sorted(owned)
+            if world == 1:
+                assert not ghosts
+            neighbours_of_owned = set()
+            for k in owned:
+                nb = (F.Tile * 8)()
+                t = F.Tile(*k)
+                OL.bto_tile_neighbours(C.byref(t), 1, nb)
+                neighbours_of_owned |= {(b.side, b.lod, b.x, b.y) for b in nb if b.side != 0xFFFFFFFF}
+            for g in ghosts:
+                assert g[1] > root and g in neighbours_of_owned and g not in owned
+            # what stitch will read but this rank does not own must be a ghost (above the root level) or a replica
+            missing = {k for k in neighbours_of_owned if k not in owned and k[1] > root} - ghosts
+            assert not missing, (world, rank, sorted(missing)[:4])
+            unpacked = {(c.tile.side, c.tile.lod, c.tile.x, c.tile.y) for c in _exchange_plan(lib, h, 0, 1)}
+            assert unpacked == ghosts
+            hb = F.u64()
+            lib.bt_preprocessor_halo_bytes(h, C.byref(hb))
+            packed = sum(c.pixels for c in _exchange_plan(lib, h, 0, 0)) * 2
+            assert packed == hb.value
+            lib.bt_preprocessor_destroy(h)
+        assert len(owned_all) == len(set(owned_all)) == 6 * (4 ** L - 1) // 3, (world, len(owned_all))
+
+
+def test_sharded_job_argument_errors():
+    lib = F.load_library()
+    att = (F.AttachmentConfig * 1)(F.AttachmentConfig(T, B, 1, F.BT_FORMAT_R16))
+    h = C.c_void_p()
+    assert lib.bt_preprocessor_create(None, F.BT_KIND_PLANAR, att, 1, L, F.Shard(0, 3), C.byref(h)) == F.BT_ERR_INVALID_ARG   # not a power of two
+    assert lib.bt_preprocessor_create(None, F.BT_KIND_PLANAR, att, 1, L, F.Shard(2, 2), C.byref(h)) == F.BT_ERR_INVALID_ARG   # rank >= world
+
+    def dataset(side, lod_end=L):
+        d = F.Dataset()
+        d.attachment_index, d.side = 0, side
+        d.top_left[:] = [0.0, 0.0]
+        d.bottom_right[:] = [1.0, 1.0]
+        d.lod_begin, d.lod_end, d.width, d.height = 0, lod_end, SRC, SRC
+        return d
+
+    assert lib.bt_preprocessor_create(None, F.BT_KIND_SPHERICAL, att, 1, L, F.Shard(0, 2), C.byref(h)) == F.BT_OK
+    five = (F.Dataset * 5)(*[dataset(s) for s in range(5)])
+    assert lib.bt_preprocessor_add_datasets(h, five, 5) == F.BT_ERR_INVALID_ARG            # a sharded cube job needs all six faces
+    mixed = (F.Dataset * 6)(*[dataset(s, L if s else L - 1) for s in range(6)])
+    assert lib.bt_preprocessor_add_datasets(h, mixed, 6) == F.BT_ERR_INVALID_ARG           # ... with one lod_range
+    twice = (F.Dataset * 6)(*[dataset(min(s, 4)) for s in range(6)])
+    assert lib.bt_preprocessor_add_datasets(h, twice, 6) == F.BT_ERR_INVALID_ARG           # ... on distinct sides
+    lib.bt_preprocessor_destroy(h)
+    assert lib.bt_preprocessor_create(None, F.BT_KIND_PLANAR, att, 1, L, F.Shard(0, 2), C.byref(h)) == F.BT_OK
+    two = (F.Dataset * 2)(dataset(0), dataset(0))
+    assert lib.bt_preprocessor_add_datasets(h, two, 2) == F.BT_ERR_INVALID_ARG             # sharded planar: one dataset per job
+    lib.bt_preprocessor_destroy(h)
