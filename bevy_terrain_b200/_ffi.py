@@ -18,7 +18,7 @@ u32, i32, f32, f64, u64 = C.c_uint32, C.c_int32, C.c_float, C.c_double, C.c_uint
 # status codes
 BT_OK, BT_ERR_INVALID_ARG, BT_ERR_CAPACITY, BT_ERR_CUDA, BT_ERR_NCCL, BT_ERR_IO, BT_ERR_OUT_OF_MEMORY, BT_ERR_NOT_FOUND = range(8)
 BT_FORMAT_RGBA8, BT_FORMAT_R16 = 0, 1
-BT_KIND_PLANAR, BT_KIND_SPHERICAL = 0, 1
+BT_KIND_PLANAR, BT_KIND_SPHERICAL, BT_KIND_ELLIPSOIDAL = 0, 1, 2
 BT_FLAG_MORPH, BT_FLAG_BLEND, BT_FLAG_HIGH_PRECISION, BT_FLAG_NORMALS, BT_FLAG_FRUSTUM_CULL = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 6
 
 
@@ -190,6 +190,7 @@ def _declare(lib: C.CDLL) -> None:
         "bt_view_device_ptrs": (i32, [vp, P(vp), P(vp)]),
         "bt_terrain_model_planar": (None, [P(f64), f64, f32, f32, P(TerrainModel)]),
         "bt_terrain_model_sphere": (None, [P(f64), f64, f32, f32, P(TerrainModel)]),
+        "bt_terrain_model_ellipsoid": (None, [P(f64), f64, f64, f32, f32, P(TerrainModel)]),
         "bt_terrain_view_config_default": (None, [P(TerrainViewConfig)]),
         "bt_terrain_model_scale": (f64, [P(TerrainModel)]),
         "bt_terrain_model_mesh_transform": (None, [P(TerrainModel), P(MeshTransform)]),

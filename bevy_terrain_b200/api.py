@@ -120,6 +120,13 @@ class TerrainModel:
         F.load_library().bt_terrain_model_sphere((F.f64 * 3)(*position), radius, min_height, max_height, C.byref(m))
         return TerrainModel(m)
 
+    @staticmethod
+    def ellipsoid(position: Sequence[float], major_axis: float, minor_axis: float, min_height: float, max_height: float) -> "TerrainModel":
+        """TerrainModel::ellipsoid (terrain_model.rs:106-128): polar (minor) axis along world y."""
+        m = F.TerrainModel()
+        F.load_library().bt_terrain_model_ellipsoid((F.f64 * 3)(*position), major_axis, minor_axis, min_height, max_height, C.byref(m))
+        return TerrainModel(m)
+
     def is_spherical(self) -> bool:
         return self.c.kind != F.BT_KIND_PLANAR
 

@@ -40,8 +40,107 @@ inline D3 inverse_transform_point(const bt_terrain_model& m, D3 p) {
     return {(p.x - m.position[0]) / m.scale[0], (p.y - m.position[1]) / m.scale[1], (p.z - m.position[2]) / m.scale[2]};
 }
 
-// TerrainModel::position_world_to_local — terrain_model.rs:145-168 (planar / sphere)
+// ---- closest point on an axis-aligned ellipsoid (src/math/ellipsoid.rs; the algorithm of D. Eberly, "Distance from a Point to
+// an Ellipse, an Ellipsoid, or a Hyperellipsoid", Geometric Tools): work in the first octant with semi-axes e0 >= e1 >= e2, find
+// the root t of  sum_i (r_i z_i / (t + r_i))^2 = 1  by bisection (r_i = e_i^2 / e_last^2, z_i = y_i / e_i), then
+// x_i = r_i y_i / (t + r_i).  The iteration count and the termination tests follow the reference so that the f64 results agree.
+constexpr int kEllipsoidIterations = 1074;   // ellipsoid.rs:8-10: after that many halvings s0 == s1
+
+template <int N>
+double ellipsoid_root(const double (&r)[N], const double (&z)[N], double g) {
+    double n[N], nn = 0.0;
+    for (int i = 0; i < N; ++i) { n[i] = r[i] * z[i]; nn += n[i] * n[i]; }
+    double s0 = z[N - 1] - 1.0, s1 = g < 0.0 ? 0.0 : std::sqrt(nn) - 1.0, s = 0.0;
+    for (int it = 0; it < kEllipsoidIterations; ++it) {
+        s = (s0 + s1) / 2.0;
+        if (s == s0 || s == s1) break;
+        double q = 0.0;
+        for (int i = 0; i < N; ++i) { const double ratio = n[i] / (s + r[i]); q += ratio * ratio; }
+        const double gg = q - 1.0;
+        if (gg < 0.0) s1 = s; else if (gg > 0.0) s0 = s; else break;
+    }
+    return s;
+}
+
+// ellipse with semi-axes e0 >= e1, query (y0, y1) in the first quadrant
+void project_point_ellipse(double e0, double e1, double y0, double y1, double out[2]) {
+    if (y1 > 0.0) {
+        if (y0 > 0.0) {
+            const double z[2] = {y0 / e0, y1 / e1};
+            const double g = (z[0] * z[0] + z[1] * z[1]) - 1.0;
+            if (g != 0.0) {
+                const double r[2] = {(e0 * e0) / (e1 * e1), 1.0};
+                const double t = ellipsoid_root<2>(r, z, g);
+                out[0] = r[0] * y0 / (t + r[0]);
+                out[1] = r[1] * y1 / (t + r[1]);
+            } else { out[0] = y0; out[1] = y1; }
+        } else { out[0] = 0.0; out[1] = e1; }
+    } else {
+        const double numer0 = e0 * y0, denom0 = e0 * e0 - e1 * e1;
+        if (numer0 < denom0) {
+            const double xde0 = numer0 / denom0;
+            out[0] = e0 * xde0;
+            out[1] = e1 * std::sqrt(1.0 - xde0 * xde0);
+        } else { out[0] = e0; out[1] = 0.0; }
+    }
+}
+
+inline double signum(double v) { return std::isnan(v) ? v : (std::signbit(v) ? -1.0 : 1.0); }   // f64::signum: signum(+-0) = +-1
+
+// project_point_ellipsoid(e, y) — ellipsoid.rs:12-63; e = (e0, e1, e2) descending, the query is swizzled (x, z, y) so that the
+// terrain's polar axis (world y, the minor axis) lands in the last slot
+D3 project_point_ellipsoid(const double e[3], D3 query) {
+    const double sign[3] = {signum(query.x), signum(query.y), signum(query.z)};
+    const double y[3] = {std::fabs(query.x), std::fabs(query.z), std::fabs(query.y)};
+    double x[3];
+    if (y[2] > 0.0) {
+        if (y[1] > 0.0) {
+            if (y[0] > 0.0) {
+                const double z[3] = {y[0] / e[0], y[1] / e[1], y[2] / e[2]};
+                const double g = ((z[0] * z[0] + z[1] * z[1]) + z[2] * z[2]) - 1.0;
+                if (g != 0.0) {
+                    const double r[3] = {(e[0] * e[0]) / (e[2] * e[2]), (e[1] * e[1]) / (e[2] * e[2]), 1.0};
+                    const double t = ellipsoid_root<3>(r, z, g);
+                    for (int i = 0; i < 3; ++i) x[i] = r[i] * y[i] / (t + r[i]);
+                } else { x[0] = y[0]; x[1] = y[1]; x[2] = y[2]; }
+            } else {
+                double p[2];
+                project_point_ellipse(e[1], e[2], y[1], y[2], p);
+                x[0] = 0.0; x[1] = p[0]; x[2] = p[1];
+            }
+        } else if (y[0] > 0.0) {
+            double p[2];
+            project_point_ellipse(e[0], e[2], y[0], y[2], p);
+            x[0] = p[0]; x[1] = 0.0; x[2] = p[1];
+        } else { x[0] = 0.0; x[1] = 0.0; x[2] = e[2]; }
+    } else {
+        const double denom0 = e[0] * e[0] - e[2] * e[2], denom1 = e[1] * e[1] - e[2] * e[2];
+        const double numer0 = e[0] * y[0], numer1 = e[1] * y[1];
+        bool done = false;
+        if (numer0 < denom0 && numer1 < denom1) {
+            const double xde0 = numer0 / denom0, xde1 = numer1 / denom1;
+            const double discr = (1.0 - xde0 * xde0) - xde1 * xde1;
+            if (discr > 0.0) { x[0] = e[0] * xde0; x[1] = e[1] * xde1; x[2] = e[2] * std::sqrt(discr); done = true; }
+        }
+        if (!done) {
+            double p[2];
+            project_point_ellipse(e[0], e[1], y[0], y[1], p);
+            x[0] = p[0]; x[1] = p[1]; x[2] = 0.0;
+        }
+    }
+    return {sign[0] * x[0], sign[1] * x[2], sign[2] * x[1]};   // swizzle back: (x, z, y)
+}
+
+// TerrainModel::position_world_to_local — terrain_model.rs:145-168
 D3 position_world_to_local(const bt_terrain_model& m, D3 world) {
+    if (m.kind == BT_KIND_ELLIPSOIDAL) {
+        // ellipsoid_from_world = inverse(rotation * translation) with the identity rotation: subtract the position
+        const D3 rel{world.x - m.position[0], world.y - m.position[1], world.z - m.position[2]};
+        const double e[3] = {m.scale[0], m.scale[0], m.scale[1]};   // (major, major, minor)
+        // (literal reference behaviour: local_from_world is applied to the point in the ELLIPSOID frame, terrain_model.rs:163-166,
+        //  i.e. the translation is subtracted twice — invisible for the reference's own use, an ellipsoid at the origin)
+        return normalized(inverse_transform_point(m, project_point_ellipsoid(e, rel)));
+    }
     D3 l = inverse_transform_point(m, world);
     if (m.kind == BT_KIND_PLANAR) return {l.x, 0.0 * l.y, l.z};
     return normalized(l);
@@ -169,6 +268,15 @@ void bt_terrain_model_sphere(const double position[3], double radius, float min_
     out->max_height = max_height;
 }
 
+void bt_terrain_model_ellipsoid(const double position[3], double major_axis, double minor_axis, float min_height, float max_height,
+                                bt_terrain_model* out) {   // terrain_model.rs:106-128: scale = (major, minor, major), identity rotation
+    std::memset(out, 0, sizeof(*out));
+    out->kind = BT_KIND_ELLIPSOIDAL;
+    for (int k = 0; k < 3; ++k) { out->position[k] = position[k]; out->scale[k] = k == 1 ? minor_axis : major_axis; }
+    out->min_height = min_height;
+    out->max_height = max_height;
+}
+
 void bt_terrain_view_config_default(bt_terrain_view_config* out) {  // terrain_view.rs:47-64
     std::memset(out, 0, sizeof(*out));
     out->tree_size = 8;
@@ -186,6 +294,7 @@ void bt_terrain_view_config_default(bt_terrain_view_config* out) {  // terrain_v
 }
 
 double bt_terrain_model_scale(const bt_terrain_model* model) {  // terrain_model.rs:183-193
+    if (model->kind == BT_KIND_ELLIPSOIDAL) return (model->scale[0] + model->scale[1]) / 2.0;   // (major + minor) / 2
     return model->kind == BT_KIND_PLANAR ? model->scale[0] / 2.0 : model->scale[0];
 }
 

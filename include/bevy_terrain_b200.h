@@ -150,7 +150,8 @@ typedef struct bt_vertex {
 enum { BT_FORMAT_RGBA8 = 0, BT_FORMAT_R16 = 1 };
 
 /* TerrainKind — src/math/terrain_model.rs:23-36 */
-enum { BT_KIND_PLANAR = 0, BT_KIND_SPHERICAL = 1 };
+enum { BT_KIND_PLANAR = 0, BT_KIND_SPHERICAL = 1,
+       BT_KIND_ELLIPSOIDAL = 2 /* host-side model only (bt_terrain_model): terrains, views and preprocessors are SPHERICAL */ };
 
 /* shader-def flags (src/render/terrain_material.rs:73-228, tiling_prepass.rs:28-79) */
 enum {
@@ -295,12 +296,12 @@ bt_status bt_view_device_ptrs(bt_view* view, bt_tile** final_tiles, bt_indirect*
 /* host-side f64 producers of the per-frame inputs (no GPU needed)                              */
 /* ------------------------------------------------------------------------------------------ */
 
-/* TerrainModel — src/math/terrain_model.rs:40-104 (planar / sphere; ellipsoid is out of scope) */
+/* TerrainModel — src/math/terrain_model.rs:40-128 (planar / sphere / ellipsoid) */
 typedef struct bt_terrain_model {
     uint32_t kind;             /* BT_KIND_* */
     uint32_t _pad;
     double   position[3];
-    double   scale[3];         /* side_length (planar) or radius (sphere), splatted */
+    double   scale[3];         /* side_length (planar) or radius (sphere), splatted; (major, minor, major) for an ellipsoid */
     float    min_height, max_height;
 } bt_terrain_model;
 
@@ -318,6 +319,10 @@ void bt_terrain_model_planar(const double position[3], double side_length, float
                              float max_height, bt_terrain_model* out);   /* terrain_model.rs:84-93  */
 void bt_terrain_model_sphere(const double position[3], double radius, float min_height,
                              float max_height, bt_terrain_model* out);   /* terrain_model.rs:95-104 */
+/* TerrainModel::ellipsoid (terrain_model.rs:106-128): scale (major, minor, major), the polar (minor) axis is world y;
+ * position_world_to_local projects onto the ellipsoid first (src/math/ellipsoid.rs); scale() = (major + minor) / 2     */
+void bt_terrain_model_ellipsoid(const double position[3], double major_axis, double minor_axis, float min_height,
+                                float max_height, bt_terrain_model* out);
 void bt_terrain_view_config_default(bt_terrain_view_config* out);       /* terrain_view.rs:47-64   */
 /* TerrainModel::scale (terrain_model.rs:183-193) */
 double bt_terrain_model_scale(const bt_terrain_model* model);

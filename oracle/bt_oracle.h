@@ -97,6 +97,8 @@ void bto_generate_mipmaps(uint32_t format, uint32_t texture_size, uint32_t mip_l
 /* ---- f64 host math ---- */
 void bto_model_approximation(const bt_terrain_model* model, const double view_world_position[3],
                              uint32_t origin_lod, float approximate_height, bt_model_approximation* out);
+/* src/math/ellipsoid.rs:12-63 with e = (major, major, minor) */
+void bto_project_point_ellipsoid(double major_axis, double minor_axis, const double query[3], double out[3]);
 void bto_coordinate_from_world_position(const bt_terrain_model* model, const double world[3],
                                         uint32_t* side, double uv[2]);
 void bto_coordinate_world_position(const bt_terrain_model* model, uint32_t side, const double uv[2],

@@ -3,8 +3,8 @@
  * TEST INFRASTRUCTURE ONLY (see bt_oracle.h).  PARITY UNPINNED (no reference tests exist).
  *
  * Restates src/math/coordinate.rs:69-151, src/math/terrain_model.rs:14-21,131-193,263-360 and
- * src/terrain_data/tile_tree.rs:175-221.  Only the planar and sphere models (identity rotation,
- * as every TerrainModel constructor produces: terrain_model.rs:84-128) are covered.
+ * src/terrain_data/tile_tree.rs:175-221 and src/math/ellipsoid.rs (closest point on an ellipsoid).  Planar, sphere and
+ * ellipsoid models with the identity rotation, as every TerrainModel constructor produces (terrain_model.rs:84-128).
  */
 #include "bt_oracle.h"
 
@@ -31,8 +31,106 @@ static void normalize3(double v[3]) {
     v[0] /= l; v[1] /= l; v[2] /= l;
 }
 
+/* ---- src/math/ellipsoid.rs: closest point on an axis-aligned ellipse / ellipsoid (first quadrant / octant, semi-axes in
+ * descending order), Eberly's bisection on  F(t) = sum (r_i z_i / (t + r_i))^2 - 1  ------------------------------------ */
+#define BTO_ELLIPSOID_MAX_ITERATIONS 1074 /* ellipsoid.rs:10 */
+
+/* get_root_2d / get_root_3d — ellipsoid.rs:92-142: dims = 2 or 3 */
+static double ellipsoid_get_root(int dims, const double r[3], const double z[3], double g) {
+    double n[3] = {0.0, 0.0, 0.0}, len2 = 0.0, s0, s1, s = 0.0;
+    for (int i = 0; i < dims; ++i) { n[i] = r[i] * z[i]; len2 += n[i] * n[i]; }
+    s0 = z[dims - 1] - 1.0;
+    s1 = g < 0.0 ? 0.0 : sqrt(len2) - 1.0;
+    for (int iteration = 0; iteration < BTO_ELLIPSOID_MAX_ITERATIONS; ++iteration) {
+        double sum = 0.0, gi;
+        s = (s0 + s1) / 2.0;
+        if (s == s0 || s == s1) break;
+        for (int i = 0; i < dims; ++i) { double ratio = n[i] / (s + r[i]); sum += ratio * ratio; }
+        gi = sum - 1.0;
+        if (gi < 0.0) s1 = s;
+        else if (gi > 0.0) s0 = s;
+        else break;
+    }
+    return s;
+}
+
+/* project_point_ellipse — ellipsoid.rs:65-90 */
+static void ellipse_project(double ea, double eb, double ya, double yb, double* xa, double* xb) {
+    if (yb > 0.0) {
+        if (ya > 0.0) {
+            double z[3] = {ya / ea, yb / eb, 0.0};
+            double g = (z[0] * z[0] + z[1] * z[1]) - 1.0;
+            if (g != 0.0) {
+                double r[3] = {(ea * ea) / (eb * eb), 1.0, 0.0};
+                double t = ellipsoid_get_root(2, r, z, g);
+                *xa = r[0] * ya / (t + r[0]);
+                *xb = r[1] * yb / (t + r[1]);
+            } else { *xa = ya; *xb = yb; }
+        } else { *xa = 0.0; *xb = eb; }
+    } else {
+        double numer0 = ea * ya, denom0 = ea * ea - eb * eb;
+        if (numer0 < denom0) {
+            double xde0 = numer0 / denom0;
+            *xa = ea * xde0;
+            *xb = eb * sqrt(1.0 - xde0 * xde0);
+        } else { *xa = ea; *xb = 0.0; }
+    }
+}
+
+static double f64_signum(double v) { return v != v ? v : (signbit(v) ? -1.0 : 1.0); }
+
+/* project_point_ellipsoid — ellipsoid.rs:12-63; e = (major, major, minor); the query's y and z are exchanged on the way in and
+ * on the way out (`y.xzy()`, `x.xzy()`) because the terrain's minor axis is world y */
+static void ellipsoid_project(const double e[3], const double query[3], double out[3]) {
+    const double sx = f64_signum(query[0]), sy = f64_signum(query[1]), sz = f64_signum(query[2]);
+    const double y[3] = {fabs(query[0]), fabs(query[2]), fabs(query[1])};
+    double x[3];
+    if (y[2] > 0.0) {
+        if (y[1] > 0.0) {
+            if (y[0] > 0.0) {
+                double z[3] = {y[0] / e[0], y[1] / e[1], y[2] / e[2]};
+                double g = ((z[0] * z[0] + z[1] * z[1]) + z[2] * z[2]) - 1.0;
+                if (g != 0.0) {
+                    double r[3] = {(e[0] * e[0]) / (e[2] * e[2]), (e[1] * e[1]) / (e[2] * e[2]), 1.0};
+                    double t = ellipsoid_get_root(3, r, z, g);
+                    for (int i = 0; i < 3; ++i) x[i] = r[i] * y[i] / (t + r[i]);
+                } else { x[0] = y[0]; x[1] = y[1]; x[2] = y[2]; }
+            } else { x[0] = 0.0; ellipse_project(e[1], e[2], y[1], y[2], &x[1], &x[2]); }
+        } else if (y[0] > 0.0) { x[1] = 0.0; ellipse_project(e[0], e[2], y[0], y[2], &x[0], &x[2]); }
+        else { x[0] = 0.0; x[1] = 0.0; x[2] = e[2]; }
+    } else {
+        double denom0 = e[0] * e[0] - e[2] * e[2], denom1 = e[1] * e[1] - e[2] * e[2];
+        double numer0 = e[0] * y[0], numer1 = e[1] * y[1];
+        int have = 0;
+        if (numer0 < denom0 && numer1 < denom1) {
+            double xde0 = numer0 / denom0, xde1 = numer1 / denom1;
+            double discr = (1.0 - xde0 * xde0) - xde1 * xde1;
+            if (discr > 0.0) { x[0] = e[0] * xde0; x[1] = e[1] * xde1; x[2] = e[2] * sqrt(discr); have = 1; }
+        }
+        if (!have) { x[2] = 0.0; ellipse_project(e[0], e[1], y[0], y[1], &x[0], &x[1]); }
+    }
+    out[0] = sx * x[0];
+    out[1] = sy * x[2];
+    out[2] = sz * x[1];
+}
+
+void bto_project_point_ellipsoid(double major_axis, double minor_axis, const double query[3], double out[3]) {
+    const double e[3] = {major_axis, major_axis, minor_axis};
+    ellipsoid_project(e, query, out);
+}
+
 /* TerrainModel::position_world_to_local — terrain_model.rs:145-168 */
 static void position_world_to_local(const bt_terrain_model* m, const double world[3], double out[3]) {
+    if (m->kind == BT_KIND_ELLIPSOIDAL) {
+        /* ellipsoid_from_world = (rotation * translation)^-1 with the identity rotation; NOTE the reference then applies
+         * local_from_world to the point of the ELLIPSOID frame (terrain_model.rs:163-166): reproduced literally */
+        const double e[3] = {m->scale[0], m->scale[0], m->scale[1]};
+        double rel[3] = {world[0] - m->position[0], world[1] - m->position[1], world[2] - m->position[2]}, surface[3];
+        ellipsoid_project(e, rel, surface);
+        local_from_world_point(m, surface, out);
+        normalize3(out);
+        return;
+    }
     local_from_world_point(m, world, out);
     if (m->kind == BT_KIND_PLANAR) { out[1] = 0.0 * out[1]; }
     else normalize3(out);

@@ -19,6 +19,7 @@ pub const BT_FORMAT_RGBA8: u32 = 0; // AttachmentFormat::id(), src/terrain_data/
 pub const BT_FORMAT_R16: u32 = 1;
 pub const BT_KIND_PLANAR: u32 = 0;
 pub const BT_KIND_SPHERICAL: u32 = 1;
+pub const BT_KIND_ELLIPSOIDAL: u32 = 2; // host-side model only (bt_terrain_model)
 pub const BT_FLAG_MORPH: u32 = 1 << 1;
 pub const BT_FLAG_BLEND: u32 = 1 << 2;
 pub const BT_FLAG_HIGH_PRECISION: u32 = 1 << 3;
@@ -161,6 +162,7 @@ extern "C" {
     pub fn bt_view_device_ptrs(view: *mut bt_view, final_tiles: *mut *mut bt_tile, indirect: *mut *mut bt_indirect) -> bt_status;
     pub fn bt_terrain_model_planar(position: *const f64, side_length: f64, min_height: f32, max_height: f32, out: *mut bt_terrain_model);
     pub fn bt_terrain_model_sphere(position: *const f64, radius: f64, min_height: f32, max_height: f32, out: *mut bt_terrain_model);
+    pub fn bt_terrain_model_ellipsoid(position: *const f64, major_axis: f64, minor_axis: f64, min_height: f32, max_height: f32, out: *mut bt_terrain_model);
     pub fn bt_terrain_view_config_default(out: *mut bt_terrain_view_config);
     pub fn bt_terrain_model_scale(model: *const bt_terrain_model) -> f64;
     pub fn bt_terrain_model_mesh_transform(model: *const bt_terrain_model, out: *mut bt_mesh_transform);

@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         "bto_generate_mipmaps": (None, [u32, u32, u32, vp, vp]),
         "bto_model_approximation": (None, [P(F.TerrainModel), P(f64), u32, f32, P(F.ModelApproximation)]),
         "bto_coordinate_from_world_position": (None, [P(F.TerrainModel), P(f64), P(u32), P(f64)]),
+        "bto_project_point_ellipsoid": (None, [f64, f64, P(f64), P(f64)]),
         "bto_coordinate_world_position": (None, [P(F.TerrainModel), u32, P(f64), f32, P(f64)]),
         "bto_tile_tree_origin": (None, [u32, u32, P(f64), P(u32)]),
         "bto_project_to_side": (None, [P(F.TerrainModel), u32, P(f64), u32, P(f64)]),
@@ -93,18 +94,21 @@ def lib() -> C.CDLL:
 # host-side model helpers (restating src/math/terrain_model.rs constructors; oracle side)
 # ------------------------------------------------------------------------------------------------
 
-def terrain_model(kind: int, position, size: float, min_height: float, max_height: float) -> F.TerrainModel:
-    """TerrainModel::planar(position, side_length, ..) / ::sphere(position, radius, ..) (terrain_model.rs:84-104)."""
+def terrain_model(kind: int, position, size: float, min_height: float, max_height: float, minor_axis: float | None = None) -> F.TerrainModel:
+    """TerrainModel::planar(position, side_length, ..) / ::sphere(position, radius, ..) / ::ellipsoid(position, major, minor, ..)
+    (terrain_model.rs:84-128)."""
     m = F.TerrainModel()
     m.kind = kind
     m.position[:] = list(position)
-    m.scale[:] = [size, size, size]
+    m.scale[:] = [size, size if minor_axis is None else minor_axis, size]
     m.min_height, m.max_height = min_height, max_height
     return m
 
 
 def model_scale(m: F.TerrainModel) -> float:
     """TerrainModel::scale (terrain_model.rs:183-193)."""
+    if m.kind == F.BT_KIND_ELLIPSOIDAL:
+        return (m.scale[0] + m.scale[1]) / 2.0
     return m.scale[0] / 2.0 if m.kind == F.BT_KIND_PLANAR else m.scale[0]
 
 

@@ -19,10 +19,12 @@ from tests.clipmap_ref import ClipmapRef
 class Scene:
     def __init__(self, kind="planar", lod_count=4, T=64, B=2, src=256, grid_size=16, atlas_size=None, seed=0x5EED0001,
                  holes=False, **view_overrides):
-        self.kind = F.BT_KIND_PLANAR if kind == "planar" else F.BT_KIND_SPHERICAL
+        self.kind = F.BT_KIND_PLANAR if kind == "planar" else F.BT_KIND_SPHERICAL     # what terrains / pyramids / kernels see
         self.spherical = self.kind == F.BT_KIND_SPHERICAL
         self.lod_count, self.T, self.B, self.src_size = lod_count, T, B, src
-        if self.spherical:   # examples/spherical.rs:5-9 constants
+        if kind == "ellipsoid":   # examples/spherical.rs:5-9: MAJOR_AXES / MINOR_AXES (WGS84), an ellipsoid is "spherical" on the GPU
+            self.model = O.terrain_model(F.BT_KIND_ELLIPSOIDAL, (0.0, 0.0, 0.0), 6378137.0, -12000.0, 9000.0, minor_axis=6356752.314245)
+        elif self.spherical:      # examples/spherical.rs:5-9 constants
             self.model = O.terrain_model(self.kind, (0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0)
         else:                # examples/planar.rs:6-9,53
             self.model = O.terrain_model(self.kind, (0.0, -100.0, 0.0), 2000.0, 0.0, 500.0)
@@ -106,7 +108,9 @@ class Scene:
     def terrain_config(self):
         """TerrainConfig for the product API with the same parameters."""
         from bevy_terrain_b200 import api
-        if self.spherical:
+        if self.model.kind == F.BT_KIND_ELLIPSOIDAL:
+            model = api.TerrainModel.ellipsoid((0.0, 0.0, 0.0), 6378137.0, 6356752.314245, -12000.0, 9000.0)
+        elif self.spherical:
             model = api.TerrainModel.sphere((0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0)
         else:
             model = api.TerrainModel.planar((0.0, -100.0, 0.0), 2000.0, 0.0, 500.0)

@@ -89,6 +89,40 @@ def test_vertices_spherical_bit_exact(ctx, flags):
         _assert_vertices_equal(verts, exp)
 
 
+def test_vertices_ellipsoid_bit_exact(ctx):
+    """TerrainModel::ellipsoid: a "spherical" terrain whose mesh transform has the scale (major, minor, major); the host-side model
+    (ellipsoid projection of the view, Taylor coefficients, clipmap) comes from the product's C++ through the ABI"""
+    from bevy_terrain_b200 import api
+    scene = Scene("ellipsoid", lod_count=3, T=32, B=2, src=64, grid_size=16)
+    a = 6378137.0
+    d = np.array([0.3, 0.9, -0.4]); d /= np.linalg.norm(d)
+    positions = [tuple(d * (a + 400000.0)), tuple(np.array([-1.0, 0.01, 0.02]) * (a + 30000.0))]
+    flags = ALL | F.BT_FLAG_HIGH_PRECISION
+    atlas = api.TileAtlas(ctx, scene.terrain_config())
+    tree = api.TileTree(atlas, scene.cfg)
+    try:
+        tree.add_existing_tiles(np.array(sorted(scene.existing), dtype=np.uint32))
+        for pos in positions:
+            loads = scene.move_view(pos)
+            got_loads = tree.compute_requests(pos)            # the product's clipmap (ellipsoid model) against the reference twin
+            assert [(tuple(int(v) for v in t), i) for t, i in got_loads] == loads
+            for tc, idx in loads:
+                atlas.upload_tile(0, idx, scene.atlas[idx])
+                tree.mark_loaded(tc)
+            tree.adjust_to_tile_atlas()
+            tree.set_approximate_height(scene.approximate_height)
+            tree.prepare()                                     # product-side model approximation + table
+            assert bytes(tree.frame.approximation) == bytes(scene.approx)
+            tree.select_tiles()
+            tiles, ind = tree.readback()
+            exp_tiles, _, _ = scene.oracle_select()
+            assert np.array_equal(tiles, exp_tiles)
+            tree.gen_vertices(flags)
+            _assert_vertices_equal(tree.download_vertices(0, ind.vertex_count), scene.oracle_vertices(tiles, flags))
+    finally:
+        tree.close(); atlas.close()
+
+
 def test_vertices_high_precision_path_is_taken(ctx):
     """close to the surface the Taylor path (compute_relative_position) must engage and still match"""
     scene = Scene("spherical", lod_count=3, T=32, B=2, src=64, grid_size=16, precision_threshold_distance=0.01)

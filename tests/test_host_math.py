@@ -14,7 +14,10 @@ from tests.scene import planar_view_positions, spherical_view_positions
 def _models():
     from bevy_terrain_b200 import api
     return [(api.TerrainModel.planar((0.0, -100.0, 0.0), 2000.0, 0.0, 500.0), O.terrain_model(F.BT_KIND_PLANAR, (0.0, -100.0, 0.0), 2000.0, 0.0, 500.0), planar_view_positions(6)),
-            (api.TerrainModel.sphere((0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0), O.terrain_model(F.BT_KIND_SPHERICAL, (0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0), spherical_view_positions())]
+            (api.TerrainModel.sphere((0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0), O.terrain_model(F.BT_KIND_SPHERICAL, (0.0, 0.0, 0.0), 6371000.0, -12000.0, 9000.0), spherical_view_positions()),
+            # WGS84-shaped ellipsoid (examples/spherical.rs:5-9 has MAJOR_AXES / MINOR_AXES of this size)
+            (api.TerrainModel.ellipsoid((0.0, 0.0, 0.0), 6378137.0, 6356752.314245, -12000.0, 9000.0),
+             O.terrain_model(F.BT_KIND_ELLIPSOIDAL, (0.0, 0.0, 0.0), 6378137.0, -12000.0, 9000.0, minor_axis=6356752.314245), spherical_view_positions())]
 
 
 def test_constructors_and_uniforms_match():
@@ -61,7 +64,7 @@ def test_taylor_approximation_reproduces_f64_positions():
         assert err < 0.5, err   # metres, on a 6371 km sphere, ~2 km from the view
 
 
-@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("which", [0, 1, 2])
 def test_tile_tree_matches_python_reference_over_a_camera_path(which):
     lib = F.load_library()
     prod, orc, positions = _models()[which]
@@ -108,3 +111,65 @@ def test_from_world_position_round_trip():
         L.bto_coordinate_world_position(C.byref(orc), side.value, uv, 0.0, back)
         assert np.allclose(back[:], p, atol=1e-6)
         assert 0.0 <= uv[0] <= 1.0 and 0.0 <= uv[1] <= 1.0
+
+
+# ---- ellipsoid model (src/math/ellipsoid.rs) ---------------------------------------------------------------------------------
+def _project_numpy(major, minor, q):
+    """independent formulation of the closest point on the ellipsoid x^2/a^2 + y^2/b^2 + z^2/a^2 = 1 (b = polar axis along y):
+    Newton on the Lagrange multiplier  sum (e_i q_i / (e_i^2 + t))^2 = 1,  x_i = e_i^2 q_i / (e_i^2 + t)"""
+    e = np.array([major, minor, major], dtype=np.float64)
+    q = np.asarray(q, dtype=np.float64)
+    t = 0.0 if np.sum((q / e) ** 2) <= 1.0 else np.linalg.norm(q) * e.min() - e.min() ** 2
+    lo = -e.min() ** 2 + 1e-9
+    for _ in range(200):
+        f = np.sum((e * q / (e * e + t)) ** 2) - 1.0
+        df = -2.0 * np.sum((e * q) ** 2 / (e * e + t) ** 3)
+        step = f / df
+        t_new = max(t - step, (t + lo) / 2.0)
+        if abs(t_new - t) <= 1e-15 * max(1.0, abs(t)):
+            t = t_new
+            break
+        t = t_new
+    return e * e * q / (e * e + t)
+
+
+def test_ellipsoid_projection_is_the_closest_surface_point():
+    L = O.lib()
+    major, minor = 6378137.0, 6356752.314245
+    rng = np.random.default_rng(12)
+    queries = [rng.normal(size=3) * s for s in (major * 0.3, major, major * 1.001, major * 4.0) for _ in range(60)]
+    queries += [np.array(v, dtype=np.float64) for v in ((major * 2, 0.0, 0.0), (0.0, minor * 3, 0.0), (0.0, 0.0, -major * 1.5), (1.0, 2.0, 3.0),
+                                                         (major * 0.5, 0.0, major * 0.5), (0.0, -minor * 0.9, major * 0.2))]
+    for q in queries:
+        out = (C.c_double * 3)()
+        L.bto_project_point_ellipsoid(major, minor, (C.c_double * 3)(*q), out)
+        x = np.array(out[:])
+        assert abs((x[0] / major) ** 2 + (x[1] / minor) ** 2 + (x[2] / major) ** 2 - 1.0) < 5e-9           # on the surface (queries near the centre are ill-conditioned)
+        grad = np.array([x[0] / major ** 2, x[1] / minor ** 2, x[2] / major ** 2])
+        d = q - x
+        if np.linalg.norm(d) > 1e-3:                                                                     # q - x is parallel to the normal
+            assert np.linalg.norm(np.cross(d / np.linalg.norm(d), grad / np.linalg.norm(grad))) < 1e-8
+        if np.sum((q / np.array([major, minor, major])) ** 2) > 1e-2:      # (deep inside, the closest point is not unique enough for Newton)
+            assert np.linalg.norm(x - _project_numpy(major, minor, q)) < 1e-4 * max(1.0, np.linalg.norm(d) / major)   # == the twin
+
+
+def test_ellipsoid_model_local_positions_and_scale():
+    from bevy_terrain_b200 import api
+    L = O.lib()
+    major, minor = 6378137.0, 6356752.314245
+    orc = O.terrain_model(F.BT_KIND_ELLIPSOIDAL, (0.0, 0.0, 0.0), major, -12000.0, 9000.0, minor_axis=minor)
+    prod = api.TerrainModel.ellipsoid((0.0, 0.0, 0.0), major, minor, -12000.0, 9000.0)
+    assert bytes(prod.c) == bytes(orc) and prod.is_spherical()
+    assert prod.scale() == O.model_scale(orc) == (major + minor) / 2.0
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        p = d * major * rng.uniform(1.0, 1.5)
+        side = C.c_uint32(); uv = (C.c_double * 2)()
+        L.bto_coordinate_from_world_position(C.byref(orc), (C.c_double * 3)(*p), C.byref(side), uv)
+        back = (C.c_double * 3)()
+        L.bto_coordinate_world_position(C.byref(orc), side.value, uv, 0.0, back)       # the surface point below p
+        b = np.array(back[:])
+        assert abs((b[0] / major) ** 2 + (b[1] / minor) ** 2 + (b[2] / major) ** 2 - 1.0) < 1e-9
+        foot = _project_numpy(major, minor, p)
+        assert np.linalg.norm(b - foot) < 1e-3         # metres: it is the foot point of p on the ellipsoid

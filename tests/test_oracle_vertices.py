@@ -87,3 +87,25 @@ def test_cube_face_edge_vertices_agree_across_faces():
         assert (dist[same] < 4.0).all(), dist[same].max()      # ... and it agrees to a few ulps of 6.4e6 (0.5 m each)
         shared += int(same.sum())
     assert shared > 40
+
+
+def test_ellipsoidal_terrain_vertices_lie_on_the_ellipsoid_shell():
+    """TerrainModel::ellipsoid (terrain_model.rs:106-128): the mesh transform carries the non-uniform scale (major, minor, major),
+    so every generated vertex sits between the ellipsoid displaced by min_height and by max_height along its normal"""
+    g = 16
+    scene = Scene("ellipsoid", lod_count=3, T=32, B=2, src=64, grid_size=g)
+    a, b = 6378137.0, 6356752.314245
+    d = np.array([0.3, 0.9, -0.4]); d /= np.linalg.norm(d)          # high latitude: the flattening matters
+    scene.move_view(tuple(d * (a + 400000.0)))
+    tiles, ind, _ = scene.oracle_select()
+    assert len({int(t[0]) for t in tiles}) >= 2
+    v = scene.oracle_vertices(tiles, F.BT_FLAG_NORMALS | F.BT_FLAG_MORPH | F.BT_FLAG_BLEND)
+    p = v["position"][:, :3].astype(np.float64)
+    # height above the ellipsoid along the (approximately radial) normal: solve |p / (a+h, b+h, a+h)| = 1 to first order
+    level = np.sqrt((p[:, 0] / a) ** 2 + (p[:, 1] / b) ** 2 + (p[:, 2] / a) ** 2)
+    h = (level - 1.0) * np.linalg.norm(p, axis=1) / level
+    assert h.min() > -12000.0 - 50.0 and h.max() < 9000.0 + 50.0
+    # the same frame on the SPHERE of the mean radius differs visibly near the pole (sanity: the ellipsoid is not ignored)
+    polar = np.abs(p[:, 1]) > 0.95 * np.linalg.norm(p, axis=1)
+    if polar.any():
+        assert np.linalg.norm(p[polar], axis=1).max() < b + 9000.0 + 3000.0     # polar radius, not the 6 371 km mean
