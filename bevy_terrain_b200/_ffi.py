@@ -115,6 +115,10 @@ class TileLoad(C.Structure):
     _fields_ = [("tile", Tile), ("atlas_index", u32), ("_pad", u32 * 3)]
 
 
+class Image(C.Structure):  # a decoded source image (bt_image_load)
+    _fields_ = [("width", u32), ("height", u32), ("format", u32), ("_pad", u32), ("pixels", C.c_void_p)]
+
+
 class TileLookup(C.Structure):  # tile_tree.rs:67-83
     _fields_ = [("atlas_index", u32), ("atlas_lod", u32), ("atlas_uv", f32 * 2)]
 
@@ -177,6 +181,8 @@ def _declare(lib: C.CDLL) -> None:
         "bt_atlas_download_tile": (i32, [vp, u32, u32, vp, C.c_size_t]),
         "bt_atlas_load_tile_file": (i32, [vp, u32, u32, C.c_char_p, P(Tile), vp]),
         "bt_tile_config_load": (i32, [C.c_char_p, P(Tile), u32, P(u32)]),
+        "bt_image_load": (i32, [C.c_char_p, P(Image), C.c_char_p, C.c_size_t]),
+        "bt_image_free": (None, [P(Image)]),
         "bt_atlas_device_ptr": (i32, [vp, u32, P(vp)]),
         "bt_view_create": (i32, [vp, P(ViewDesc), P(vp)]),
         "bt_view_destroy": (None, [vp]),

@@ -17,6 +17,7 @@ marshals structs.  There is no Python/CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import enum
 from dataclasses import dataclass, field
 from typing import Iterable, Sequence
@@ -386,10 +387,28 @@ class TileTree:
             self._tree = C.c_void_p()
 
 
+def load_image(path: str) -> np.ndarray:
+    """Decode a PNG / TIFF source image through the library (bt_image_load): (H, W) uint16 for 16-bit gray, (H, W, 4) uint8 for colour."""
+    lib = F.load_library()
+    img, err = F.Image(), C.create_string_buffer(512)
+    st = lib.bt_image_load(os.fsencode(path), C.byref(img), err, len(err))
+    if st != F.BT_OK:
+        raise F.BtError(st, err.value.decode(errors="replace"))
+    try:
+        if img.format == F.BT_FORMAT_R16:
+            a = np.ctypeslib.as_array(C.cast(img.pixels, C.POINTER(C.c_uint16)), shape=(img.height, img.width)).copy()
+        else:
+            a = np.ctypeslib.as_array(C.cast(img.pixels, C.POINTER(C.c_uint8)), shape=(img.height, img.width, 4)).copy()
+    finally:
+        lib.bt_image_free(C.byref(img))
+    return a
+
+
 @dataclass
-class PreprocessDataset:  # preprocessor.rs:36-55 — `pixels` replaces `path` (decoders are out of scope)
+class PreprocessDataset:  # preprocessor.rs:36-55 — `path` (decoded by the library's PNG / TIFF readers) or decoded `pixels`
     attachment_index: int = 0
-    pixels: np.ndarray | None = None      # host image (H,W) uint16 or (H,W,4) uint8 ...
+    path: str | None = None               # source image file, as in the reference ...
+    pixels: np.ndarray | None = None      # ... or a host image (H,W) uint16 / (H,W,4) uint8 ...
     device_pixels: int = 0                # ... or a device pointer with width/height
     width: int = 0
     height: int = 0
@@ -406,6 +425,8 @@ class PreprocessDataset:  # preprocessor.rs:36-55 — `pixels` replaces `path` (
         d.top_left[:] = [float(v) for v in self.top_left]
         d.bottom_right[:] = [float(v) for v in self.bottom_right]
         d.lod_begin, d.lod_end = self.lod_range.start, self.lod_range.stop
+        if self.pixels is None and self.path is not None and not self.device_pixels:
+            self.pixels = load_image(self.path)
         if self.pixels is not None:
             self.pixels = np.ascontiguousarray(self.pixels)
             d.height, d.width = self.pixels.shape[0], self.pixels.shape[1]

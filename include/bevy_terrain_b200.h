@@ -454,6 +454,14 @@ bt_status bt_generate_mipmaps(bt_context* ctx, uint32_t format, uint32_t texture
  * reference; see DESIGN.md "synthetic inputs")                                                */
 bt_status bt_synth_source(bt_context* ctx, uint32_t format, uint32_t width, uint32_t height,
                           uint32_t x0, uint32_t y0, uint32_t seed, uint32_t holes, void* device_out, void* stream);
+/* Source-image decoders for preprocessor inputs (host only; PreprocessDataset::path in the reference is an asset path that
+ * Bevy's ImageLoader / src/formats/tiff.rs decode): PNG 16-bit gray -> BT_FORMAT_R16, PNG 8-bit RGB / RGBA -> BT_FORMAT_RGBA8,
+ * TIFF 16-bit gray (strips or tiles; none / LZW / Deflate; predictor 1 or 2; II or MM) -> R16 with the sample bytes kept as they
+ * are (tiff.rs casts every integer result to R16Unorm texels), TIFF 8-bit RGB / RGBA -> Rgba8.  `pixels` is malloc'ed; release
+ * it with bt_image_free.  On failure returns BT_ERR_IO and writes a message into `error` (may be NULL).                      */
+typedef struct bt_image { uint32_t width, height, format /* BT_FORMAT_* */, _pad; void* pixels; } bt_image;
+bt_status bt_image_load(const char* path, bt_image* out, char* error, size_t error_capacity);
+void      bt_image_free(bt_image* image);
 /* numerics self-test (all counters must be 0): mismatches[0]/[1] = 16-/8-bit unorm values whose fast exact decode
  * (scalar and packed-f32 forms) differs from the IEEE division it replaces, plus ([1]) values whose round-down pack
  * differs from floor(0.5 + M*clamp(v,0,1)); mismatches[2] = operand pairs whose branch-free exact division differs from

@@ -133,6 +133,9 @@ pub struct bt_tile_load { pub tile: bt_tile, pub atlas_index: u32, pub _pad: [u3
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)]
 pub struct bt_exchange_copy { pub tile: bt_tile, pub tile_row: u32, pub tile_col: u32, pub pixels: u32, pub src_rank: u32, pub buffer_offset: u64 }
 
+/// a decoded source image (`bt_image_load`): `pixels` is malloc'ed by the library, release it with `bt_image_free`
+#[repr(C)] pub struct bt_image { pub width: u32, pub height: u32, pub format: u32, pub _pad: u32, pub pixels: *mut c_void }
+
 // Every entry point of include/bevy_terrain_b200.h, generated by tools/gen_rust_ffi.py (argument names as in the header).
 #[link(name = "bevy_terrain_b200")]
 extern "C" {
@@ -200,6 +203,8 @@ extern "C" {
     pub fn bt_culling_planes(clip_from_world: *const f32, planes: *mut f32);
     pub fn bt_generate_mipmaps(ctx: *mut bt_context, format: u32, texture_size: u32, mip_level_count: u32, device_mip0: *const c_void, device_mips_out: *mut c_void, stream: *mut c_void) -> bt_status;
     pub fn bt_synth_source(ctx: *mut bt_context, format: u32, width: u32, height: u32, x0: u32, y0: u32, seed: u32, holes: u32, device_out: *mut c_void, stream: *mut c_void) -> bt_status;
+    pub fn bt_image_load(path: *const c_char, out: *mut bt_image, error: *mut c_char, error_capacity: usize) -> bt_status;
+    pub fn bt_image_free(image: *mut bt_image);
     pub fn bt_selftest_numerics(ctx: *mut bt_context, x: *const f32, log2_out: *mut f32, n: u32, mismatches: *mut u32) -> bt_status;
     pub fn bt_device_alloc(ctx: *mut bt_context, bytes: usize, out: *mut *mut c_void) -> bt_status;
     pub fn bt_device_free(ctx: *mut bt_context, ptr: *mut c_void) -> bt_status;
