@@ -62,6 +62,12 @@ std::vector<unsigned char> inflate_all(const unsigned char* src, size_t n, size_
     return out;
 }
 
+// Deflate expands at most ~1032 : 1 and TIFF-LZW less: a header that asks for more than that is corrupt (and would make the
+// decoder allocate gigabytes for a few bytes of input)
+size_t plausible_output(size_t compressed_bytes) { return compressed_bytes * 1100 + (1u << 16); }
+
+constexpr uint32_t kMaxSide = 1u << 17;   // 131072: far above any terrain source, keeps size arithmetic and allocations sane
+
 struct Decoded {
     uint32_t width = 0, height = 0, format = BT_FORMAT_R16;
     std::vector<unsigned char> pixels;   // R16: host-endian u16; Rgba8: r, g, b, a
@@ -103,6 +109,7 @@ Decoded decode_png(const std::vector<unsigned char>& file) {
         at += 12 + (size_t)len;
     }
     if (w == 0 || h == 0) fail("PNG: missing IHDR");
+    if (w > kMaxSide || h > kMaxSide) fail("PNG: %u x %u exceeds the supported image size", w, h);
     int channels;
     Decoded out;
     if (colour == 0 && depth == 16) { channels = 1; out.format = BT_FORMAT_R16; }
@@ -110,6 +117,7 @@ Decoded decode_png(const std::vector<unsigned char>& file) {
     else if (colour == 6 && depth == 8) { channels = 4; out.format = BT_FORMAT_RGBA8; }
     else fail("PNG: colour type %d with %d bits is not a terrain source format (16-bit gray, 8-bit RGB / RGBA)", colour, depth);
     const size_t bpp = (size_t)channels * depth / 8, row = (size_t)w * bpp;
+    if ((row + 1) * h > plausible_output(idat.size())) fail("PNG: %u x %u pixels cannot come from %zu compressed bytes", w, h, idat.size());
     std::vector<unsigned char> raw = inflate_all(idat.data(), idat.size(), (row + 1) * h);
     if (raw.size() != (row + 1) * h) fail("PNG: image data has %zu bytes, expected %zu", raw.size(), (row + 1) * h);
     std::vector<unsigned char> img(row * h);
@@ -224,6 +232,7 @@ Decoded decode_tiff(const std::vector<unsigned char>& file) {
         const uint32_t type = t.u16(entry + 2), count = t.u32(entry + 4);
         const size_t size = type == 3 ? 2 : (type == 4 ? 4 : (type == 1 ? 1 : 0));
         if (!size) fail("TIFF: unsupported field type %u", type);
+        if ((size_t)count * size > file.size()) fail("TIFF: field with %u values in a %zu-byte file", count, file.size());
         const size_t base = (size_t)count * size <= 4 ? entry + 8 : t.u32(entry + 8);
         out.resize(count);
         for (uint32_t i = 0; i < count; ++i)
@@ -251,6 +260,8 @@ Decoded decode_tiff(const std::vector<unsigned char>& file) {
         }
     }
     if (!width || !height || offsets.empty() || offsets.size() != counts.size()) fail("TIFF: missing dimensions or strip / tile tables");
+    if (width > kMaxSide || height > kMaxSide) fail("TIFF: %u x %u exceeds the supported image size", width, height);
+    if (rows_per_strip == 0 || ((tile_w != 0) != (tile_h != 0)) || tile_w > kMaxSide || tile_h > kMaxSide) fail("TIFF: bad strip / tile geometry");
     if (planar != 1) fail("TIFF: planar sample layout is not supported");
     if (predictor != 1 && predictor != 2) fail("TIFF: predictor %u is not supported", predictor);
     Decoded out;
@@ -263,6 +274,7 @@ Decoded decode_tiff(const std::vector<unsigned char>& file) {
     const uint32_t bw = tiled ? tile_w : width, bh = tiled ? tile_h : std::min(rows_per_strip, height);
     const uint32_t across = (width + bw - 1) / bw, down = (height + bh - 1) / bh;
     if ((size_t)across * down != offsets.size()) fail("TIFF: %zu strips / tiles, expected %u", offsets.size(), across * down);
+    if ((size_t)width * height * bpp > plausible_output(file.size())) fail("TIFF: %u x %u pixels cannot come from a %zu-byte file", width, height, file.size());
     out.width = width; out.height = height;
     out.pixels.assign((size_t)width * height * (out.format == BT_FORMAT_R16 ? 2 : 4), 0);
     for (uint32_t by = 0; by < down; ++by)

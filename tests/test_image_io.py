@@ -236,3 +236,32 @@ def test_decoder_errors_are_reported(tmp_path):
     (tmp_path / "bad.png").write_bytes(bytes(data))
     with pytest.raises(F.BtError):
         api.load_image(str(tmp_path / "bad.png"))
+
+
+def test_truncated_and_corrupted_files_fail_cleanly(tmp_path):
+    """untrusted input: every truncation / byte flip must end in BT_ERR_IO or in a decoded image, never in a crash"""
+    g = _gray(40, 40, 30)
+    write_png(tmp_path / "a.png", g)
+    write_tiff(tmp_path / "a.tif", g, compression=5, predictor=2, rows_per_strip=7)
+    write_tiff(tmp_path / "b.tif", _colour(24, 24, 3, 31), compression=8, tile=(16, 16), big=True)
+    rng = np.random.default_rng(99)
+    outcomes = {"ok": 0, "error": 0}
+    for name in ("a.png", "a.tif", "b.tif"):
+        data = (tmp_path / name).read_bytes()
+        variants = [data[:n] for n in rng.integers(0, len(data), 40)]
+        for _ in range(120):
+            b = bytearray(data)
+            for at in rng.integers(0, len(data), rng.integers(1, 4)):
+                b[at] = rng.integers(0, 256)
+            variants.append(bytes(b))
+        for i, v in enumerate(variants):
+            p = tmp_path / f"v{i}_{name}"
+            p.write_bytes(v)
+            try:
+                img = api.load_image(str(p))
+                assert img.ndim in (2, 3)
+                outcomes["ok"] += 1
+            except F.BtError as e:
+                assert e.status == F.BT_ERR_IO
+                outcomes["error"] += 1
+    assert outcomes["error"] > 100          # truncations and most flips are detected (CRC, sizes, code tables)
