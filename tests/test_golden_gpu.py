@@ -2,7 +2,6 @@
 import numpy as np
 import pytest
 
-from bevy_terrain_b200 import _ffi as F
 from tests.golden_util import GoldenFrame, load
 
 pytestmark = pytest.mark.gpu

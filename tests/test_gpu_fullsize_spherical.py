@@ -2,7 +2,6 @@
 10 LODs of which the dataset resolves LODs 0..4 (8192 / 508 = 16 tiles per face side), texture 512, grid 64.
 The scalar oracle cannot recompute all of it, so: size-independent properties of the pyramid and of the vertex stream, and a
 bit-exact comparison with the oracle on whole sampled tiles using the product's own inputs (atlas + table downloaded)."""
-import ctypes as C
 
 import numpy as np
 import pytest

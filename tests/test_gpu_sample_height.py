@@ -1,14 +1,10 @@
 """TileTree::approximate_height chain: host lookup (bt_tile_tree_sample_lookup) + device texels (bt_atlas_sample) against a
 numpy restatement of sample_attachment / compute_blend / lookup_tile / AttachmentData::sample
 (terrain_data/mod.rs:221-307, tile_tree.rs:223-266, tile_atlas.rs:249-258)."""
-import ctypes as C
-import math
 
 import numpy as np
 import pytest
 
-from bevy_terrain_b200 import _ffi as F
-from tests import oracle as O
 from tests.scene import Scene
 
 pytestmark = pytest.mark.gpu

@@ -7,7 +7,6 @@ the CUDA path is bit-identical to it (tests/test_gpu_vertices.py), so the proper
 import numpy as np
 
 from bevy_terrain_b200 import _ffi as F
-from tests import oracle as O
 from tests.scene import Scene
 
 

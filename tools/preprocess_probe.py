@@ -24,7 +24,6 @@ def main():
     args = ap.parse_args()
     import numpy as np
     import torch
-    import bevy_terrain_b200 as bt
     from bevy_terrain_b200 import _ffi as F, api
     ctx = api.Context(0)
     S, L = args.source, args.lods
