@@ -37,7 +37,46 @@ impl AttachmentConfig {
     }
 }
 
-/// `PreprocessDataset` (src/preprocess/preprocessor.rs:36-55); the caller decodes `path` with the `image`/`tiff` crates as the reference does.
+/// `TerrainModel` (src/math/terrain_model.rs:40-128): the plain-data model every host-math entry point takes.
+#[derive(Clone, Copy)] pub struct TerrainModel(pub ffi::bt_terrain_model);
+impl TerrainModel {
+    pub fn planar(position: [f64; 3], side_length: f64, min_height: f32, max_height: f32) -> Self {
+        let mut m = ffi::bt_terrain_model::default();
+        unsafe { ffi::bt_terrain_model_planar(position.as_ptr(), side_length, min_height, max_height, &mut m) };
+        Self(m)
+    }
+    pub fn sphere(position: [f64; 3], radius: f64, min_height: f32, max_height: f32) -> Self {
+        let mut m = ffi::bt_terrain_model::default();
+        unsafe { ffi::bt_terrain_model_sphere(position.as_ptr(), radius, min_height, max_height, &mut m) };
+        Self(m)
+    }
+    pub fn ellipsoid(position: [f64; 3], major_axis: f64, minor_axis: f64, min_height: f32, max_height: f32) -> Self {
+        let mut m = ffi::bt_terrain_model::default();
+        unsafe { ffi::bt_terrain_model_ellipsoid(position.as_ptr(), major_axis, minor_axis, min_height, max_height, &mut m) };
+        Self(m)
+    }
+    pub fn is_spherical(&self) -> bool { self.0.kind != ffi::BT_KIND_PLANAR }
+    pub fn scale(&self) -> f64 { unsafe { ffi::bt_terrain_model_scale(&self.0) } }
+}
+
+/// A decoded source image (`PreprocessDataset::path` of the reference): PNG / TIFF through `bt_image_load`.
+pub struct SourceImage { pub width: u32, pub height: u32, pub format: AttachmentFormat, pub pixels: Vec<u8> }
+impl SourceImage {
+    pub fn load(path: &str) -> Result<Self> {
+        let c_path = CString::new(path)?;
+        let mut image = ffi::bt_image { width: 0, height: 0, format: 0, _pad: 0, pixels: ptr::null_mut() };
+        let mut error = [0 as std::os::raw::c_char; 256];
+        let st = unsafe { ffi::bt_image_load(c_path.as_ptr(), &mut image, error.as_mut_ptr(), error.len()) };
+        if st != ffi::BT_OK { return Err(anyhow!("{}", unsafe { CStr::from_ptr(error.as_ptr()) }.to_string_lossy())); }
+        let (format, px) = if image.format == ffi::BT_FORMAT_R16 { (AttachmentFormat::R16, 2) } else { (AttachmentFormat::Rgba8, 4) };
+        let bytes = image.width as usize * image.height as usize * px;
+        let pixels = unsafe { std::slice::from_raw_parts(image.pixels as *const u8, bytes) }.to_vec();
+        unsafe { ffi::bt_image_free(&mut image) };
+        Ok(Self { width: image.width, height: image.height, format, pixels })
+    }
+}
+
+/// `PreprocessDataset` (src/preprocess/preprocessor.rs:36-55); `pixels` come from `SourceImage::load(path)` or from the `image`/`tiff` crates as in the reference.
 pub struct PreprocessDataset<'a> {
     pub attachment_index: u32, pub pixels: &'a [u8], pub width: u32, pub height: u32, pub side: u32,
     pub top_left: [f32; 2], pub bottom_right: [f32; 2], pub lod_range: Range<u32>,
