@@ -375,7 +375,7 @@ def oracle_vertex_inputs(h, flags):
     vi.attachments[0].scale = float(c / np.float32(h["T"]))
     vi.attachments[0].offset = float(np.float32(h["B"]) / np.float32(h["T"]))
     vi.view_world_position[:] = [float(np.float32(v)) for v in h["pos"]]
-    vi.spherical, vi.texture_size = 0, h["T"]
+    vi.spherical, vi.texture_size, vi.atlas_size = 0, h["T"], len(h["atlas"])
     vi.tile_tree = h["entries"].ctypes.data_as(C.POINTER(F.TileTreeEntry))
     vi.height_atlas = h["atlas"].ctypes.data
     vi.tiles = h["tiles"].ctypes.data_as(C.POINTER(F.Tile))

@@ -96,7 +96,7 @@ class VertexBuffer(C.Structure):
 
 
 class ViewDesc(C.Structure):
-    _fields_ = [("geometry_tile_count", u32), ("tree_size", u32), ("grid_size", u32), ("_pad", u32), ("max_vertices", u64)]
+    _fields_ = [("geometry_tile_count", u32), ("tree_size", u32), ("grid_size", u32), ("readback_tile_capacity", u32), ("max_vertices", u64)]
 
 
 class TerrainModel(C.Structure):  # terrain_model.rs:40-104
@@ -203,6 +203,9 @@ def _declare(lib: C.CDLL) -> None:
         "bt_view_config_uniform_from": (None, [P(TerrainViewConfig), P(TerrainModel), P(ViewConfigUniform)]),
         "bt_model_approximation_compute": (i32, [P(TerrainModel), P(f64), u32, f32, P(ModelApproximation)]),
         "bt_tile_tree_create": (i32, [P(TerrainModel), P(TerrainViewConfig), u32, u32, P(vp)]),
+        "bt_atlas_state_create": (i32, [u32, P(vp)]),
+        "bt_atlas_state_destroy": (None, [vp]),
+        "bt_tile_tree_create_shared": (i32, [P(TerrainModel), P(TerrainViewConfig), u32, vp, P(vp)]),
         "bt_tile_tree_destroy": (None, [vp]),
         "bt_tile_tree_add_existing": (i32, [vp, P(Tile), u32]),
         "bt_tile_tree_update": (i32, [vp, P(f64), P(TileLoad), u32, P(u32)]),

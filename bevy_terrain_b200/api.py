@@ -187,6 +187,9 @@ class TileAtlas:
         d.transform = self.model.mesh_transform()
         self._h = C.c_void_p()
         ctx.check(ctx.lib.bt_terrain_create(ctx._h, C.byref(d), C.byref(self._h)))
+        # TileAtlasState is per terrain: every TileTree (view) of this atlas shares it (tile_atlas.rs:272-300)
+        self._state = C.c_void_p()
+        ctx.check(ctx.lib.bt_atlas_state_create(config.atlas_size, C.byref(self._state)))
 
     @staticmethod
     def new(ctx: Context, config: TerrainConfig) -> "TileAtlas":
@@ -218,6 +221,9 @@ class TileAtlas:
         return p.value
 
     def close(self) -> None:
+        if self._state:
+            self.ctx.lib.bt_atlas_state_destroy(self._state)
+            self._state = C.c_void_p()
         if self._h:
             self.ctx.lib.bt_terrain_destroy(self._h)
             self._h = C.c_void_p()
@@ -238,7 +244,7 @@ class TileTree:
         self.side_count = 6 if self.model.is_spherical() else 1
         self.entry_count = self.side_count * self.lod_count * view_config.tree_size ** 2
         self._tree = C.c_void_p()
-        self.ctx.check(lib.bt_tile_tree_create(C.byref(self.model.c), C.byref(view_config), self.lod_count, tile_atlas.atlas_size, C.byref(self._tree)))
+        self.ctx.check(lib.bt_tile_tree_create_shared(C.byref(self.model.c), C.byref(view_config), self.lod_count, tile_atlas._state, C.byref(self._tree)))
         vd = F.ViewDesc(geometry_tile_count=view_config.geometry_tile_count, tree_size=view_config.tree_size,
                         grid_size=view_config.grid_size, max_vertices=max_vertices)
         self._view = C.c_void_p()

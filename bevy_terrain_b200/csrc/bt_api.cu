@@ -303,6 +303,15 @@ bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out)
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_readback, sizeof(btd::SelectStatus) + sizeof(bt_indirect) + sizeof(btd::GenStatus), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->staging_free, cudaEventDisableTiming);
+    // everything bt_view_run_frame needs is created HERE: no allocation on the per-frame path (SURVEY 8b ownership rule)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->select_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->copy_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        const uint32_t want = desc->readback_tile_capacity ? desc->readback_tile_capacity : 65536u;
+        v->h_tiles_cap = want < desc->geometry_tile_count ? want : desc->geometry_tile_count;
+        e = cudaHostAlloc((void**)&v->h_tiles, (size_t)v->h_tiles_cap * sizeof(bt_tile), cudaHostAllocDefault);
+    }
     if (e == cudaSuccess && desc->max_vertices) {
         e = cudaMalloc((void**)&v->d_vertices, desc->max_vertices * sizeof(bt_vertex));
         v->vertex_capacity = desc->max_vertices;
@@ -359,6 +368,7 @@ bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) {
     U.spherical = t->desc.kind == BT_KIND_SPHERICAL;
     U.texture_size = t->desc.attachments[0].texture_size;
     U.tile_tree_entries = v->tile_tree_entries;
+    U.atlas_size = t->desc.atlas_size;
     U.approximation = f->approximation;
     U.culling = f->culling;
     // TerrainConfigUniform::from_tile_atlas — terrain_bind_group.rs:84-93
@@ -459,18 +469,8 @@ bt_status bt_view_run_frame(bt_view* v, const bt_view_frame* frame, uint32_t sel
     if (v->desc.max_vertices == 0) { ctx->set_error("bt_view_run_frame: needs a view created with max_vertices (no blocking growth on the frame path)"); return BT_ERR_INVALID_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!v->copy_stream) {
-        BT_CUDA(ctx, cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
-        BT_CUDA(ctx, cudaEventCreateWithFlags(&v->select_done, cudaEventDisableTiming));
-        BT_CUDA(ctx, cudaEventCreateWithFlags(&v->copy_done, cudaEventDisableTiming));
-    }
-    const uint32_t want = tiles ? (capacity < v->desc.geometry_tile_count ? capacity : v->desc.geometry_tile_count) : 0u;
-    if (want > v->h_tiles_cap) {
-        if (v->h_tiles) BT_CUDA(ctx, cudaFreeHost(v->h_tiles));
-        v->h_tiles = nullptr;
-        BT_CUDA(ctx, cudaHostAlloc((void**)&v->h_tiles, (size_t)want * sizeof(bt_tile), cudaHostAllocDefault));
-        v->h_tiles_cap = want;
-    }
+    // the pinned read-back buffer was sized by bt_view_create (bt_view_desc.readback_tile_capacity): nothing is allocated here
+    const uint32_t want = tiles ? (capacity < v->h_tiles_cap ? capacity : v->h_tiles_cap) : 0u;
     bt_status st = bt_view_update(v, frame, stream);
     if (st != BT_OK) return st;
     st = bt_select_tiles(v, select_flags, stream);

@@ -6,7 +6,7 @@
 // blended as src/shaders/render/fragment.wgsl:99-107).
 //
 // Design (B200):
-//   * persistent CTAs (one per SM, warp-specialised: 23 compute warps + 1 TMA store warp) stride over work items
+//   * persistent CTAs (one per SM, warp-specialised: 19 compute warps + 1 TMA store warp) stride over work items
 //     = (tile, block of CB column strips); image hand-over by mbarriers, no CTA-wide barrier in steady state
 //   * the reference's triangle-strip index stream visits every grid vertex ~2x (8448 strip
 //     vertices for 65x65 = 4225 unique ones at grid 64, compute_tile_uv functions.wgsl:64-71);
@@ -81,6 +81,7 @@ struct FrameConsts {
     Vec3  planar_normal;       // normal_local_to_world for the planar model: a constant (functions.wgsl:14-24)
     float lod_cap;             // f32(lod_count) - 0.00001 (functions.wgsl:52)
     uint32_t tree_size, tree_mask, lod_count;  // tree_mask = tree_size - 1 when tree_size is a power of two, else 0
+    uint32_t last_layer;       // atlas_size - 1: texture-array indices clamp to it
 };
 
 template <bool SPHERICAL>
@@ -106,6 +107,7 @@ __device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) 
     F.tree_size = U.view_config.tree_size;
     F.tree_mask = (F.tree_size & (F.tree_size - 1u)) == 0u ? F.tree_size - 1u : 0u;
     F.lod_count = U.terrain_config.lod_count;
+    F.last_layer = U.atlas_size ? U.atlas_size - 1u : 0u;
     return F;
 }
 
@@ -341,7 +343,9 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     const int tile_texels = F.T * F.T;
     const bool normals = (flags & BT_FLAG_NORMALS) != 0u;
     const AtlasTile ta = lookup_tile(F, tile_tree, c, blend_lod);
-    const uint16_t* layer_a = atlas + (size_t)ta.index * tile_texels;
+    // An INVALID entry (0xFFFFFFFF: no tile loaded yet for this slot) samples like the reference does: WGSL clamps the
+    // texture-array index to the last layer (textureSampleLevel array_index), so the frame keeps rendering.
+    const uint16_t* layer_a = atlas + (size_t)min(ta.index, F.last_layer) * tile_texels;
     const float ua = ta.c.u * F.a_scale + F.a_offset, va = ta.c.v * F.a_scale + F.a_offset;  // attachment_uv
     float height;
     Vec3 nrm = wn;
@@ -354,7 +358,7 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     }
     if (blend_ratio > 0.0f) {
         const AtlasTile tb = lookup_tile(F, tile_tree, c, blend_lod - 1u);
-        const uint16_t* layer_b = atlas + (size_t)tb.index * tile_texels;
+        const uint16_t* layer_b = atlas + (size_t)min(tb.index, F.last_layer) * tile_texels;
         const float ub = tb.c.u * F.a_scale + F.a_offset, vb = tb.c.v * F.a_scale + F.a_offset;
         if (normals) {  // fragment.wgsl:103-107
             const FiveTaps taps = sample_five(F, layer_b, ub, vb);

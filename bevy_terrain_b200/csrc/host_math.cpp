@@ -413,26 +413,21 @@ struct TreeSlot { TileKey coordinate = kInvalidTile; bool requested = false; };
 
 }  // namespace
 
-struct bt_tile_tree {
-    bt_terrain_model model;
-    bt_terrain_view_config cfg;
-    uint32_t lod_count, atlas_size, side_count;
-    double load_distance;  // pre-multiplied by the model scale (tile_tree.rs:148)
-    float approximate_height;
-    D3 view_world_position{0, 0, 0};
-    std::vector<TreeSlot> tiles;            // [side][lod][x % tree][y % tree]
-    std::vector<uint32_t> origins;          // [side][lod] uvec2
-    // TileAtlasState — tile_atlas.rs:272-300
+// TileAtlasState — tile_atlas.rs:272-300.  Per TERRAIN in the reference and shared by every view's TileTree: slot allocation,
+// the LRU of unused slots, the set of tiles that exist on disk and the load queue.  Several bt_tile_tree handles created with
+// bt_tile_tree_create_shared reference one state; bt_tile_tree_create makes a private one (single-view terrains).
+struct bt_atlas_state {
+    uint32_t atlas_size = 0;
+    uint32_t users = 0;            // trees referencing this state (a private state dies with its tree)
+    bool owned_by_tree = false;
     std::unordered_map<TileKey, AtlasTileState, TileKeyHash> tile_states;
     std::deque<std::pair<TileKey, uint32_t>> unused_tiles;  // (coordinate, atlas_index), LRU order
     std::unordered_set<TileKey, TileKeyHash> existing_tiles;
     std::vector<bt_tile_load> pending_loads;
 
-    size_t slot_index(uint32_t side, uint32_t lod, uint32_t x, uint32_t y) const {
-        const uint32_t ts = cfg.tree_size;
-        return (((size_t)side * lod_count + lod) * ts + x % ts) * ts + y % ts;
+    explicit bt_atlas_state(uint32_t n) : atlas_size(n) {
+        for (uint32_t i = 0; i < n; ++i) unused_tiles.emplace_back(kInvalidTile, i);  // TileAtlasState::new — tile_atlas.rs:302-325
     }
-
     // TileAtlasState::allocate_tile — tile_atlas.rs:383-389
     bool allocate_tile(uint32_t* atlas_index) {
         if (unused_tiles.empty()) return false;  // reference: expect("Atlas out of indices")
@@ -483,6 +478,24 @@ struct bt_tile_tree {
     }
 };
 
+struct bt_tile_tree {
+    bt_terrain_model model;
+    bt_terrain_view_config cfg;
+    uint32_t lod_count, atlas_size, side_count;
+    double load_distance;  // pre-multiplied by the model scale (tile_tree.rs:148)
+    float approximate_height;
+    D3 view_world_position{0, 0, 0};
+    std::vector<TreeSlot> tiles;            // [side][lod][x % tree][y % tree]
+    std::vector<uint32_t> origins;          // [side][lod] uvec2
+    bt_atlas_state* state = nullptr;        // the terrain's TileAtlasState (shared by all views of the terrain)
+
+    size_t slot_index(uint32_t side, uint32_t lod, uint32_t x, uint32_t y) const {
+        const uint32_t ts = cfg.tree_size;
+        return (((size_t)side * lod_count + lod) * ts + x % ts) * ts + y % ts;
+    }
+    bt_tile_tree_entry best_tile(TileKey k) const { return state->best_tile(k); }
+};
+
 namespace {
 
 // TileTree::compute_tree_xy — tile_tree.rs:175-178
@@ -522,10 +535,35 @@ double compute_tile_distance(const bt_tile_tree& t, const TileKey& tile, Coordin
 
 extern "C" {
 
+bt_status bt_atlas_state_create(uint32_t atlas_size, bt_atlas_state** out) {
+    if (!out || atlas_size == 0) return BT_ERR_INVALID_ARG;
+    *out = new bt_atlas_state(atlas_size);
+    return BT_OK;
+}
+
+void bt_atlas_state_destroy(bt_atlas_state* state) {
+    if (!state) return;
+    if (state->users == 0) delete state;
+    else state->owned_by_tree = true;   // still referenced: the last tree that goes away frees it
+}
+
 bt_status bt_tile_tree_create(const bt_terrain_model* model, const bt_terrain_view_config* cfg, uint32_t lod_count,
                               uint32_t atlas_size, bt_tile_tree** out) {
-    if (!model || !cfg || !out || lod_count == 0 || lod_count > 31 || cfg->tree_size == 0) return BT_ERR_INVALID_ARG;
+    if (!out || atlas_size == 0) return BT_ERR_INVALID_ARG;
+    bt_atlas_state* state = new bt_atlas_state(atlas_size);
+    state->owned_by_tree = true;
+    const bt_status st = bt_tile_tree_create_shared(model, cfg, lod_count, state, out);
+    if (st != BT_OK) delete state;
+    return st;
+}
+
+bt_status bt_tile_tree_create_shared(const bt_terrain_model* model, const bt_terrain_view_config* cfg, uint32_t lod_count,
+                                     bt_atlas_state* state, bt_tile_tree** out) {
+    if (!model || !cfg || !out || !state || lod_count == 0 || lod_count > 31 || cfg->tree_size == 0) return BT_ERR_INVALID_ARG;
+    const uint32_t atlas_size = state->atlas_size;
     bt_tile_tree* t = new bt_tile_tree();
+    t->state = state;
+    state->users += 1;
     t->model = *model;
     t->cfg = *cfg;
     t->lod_count = lod_count;
@@ -535,16 +573,23 @@ bt_status bt_tile_tree_create(const bt_terrain_model* model, const bt_terrain_vi
     t->approximate_height = (model->min_height + model->max_height) / 2.0f;  // tile_tree.rs:155
     t->tiles.resize((size_t)t->side_count * lod_count * cfg->tree_size * cfg->tree_size);
     t->origins.assign((size_t)t->side_count * lod_count * 2, 0u);
-    for (uint32_t i = 0; i < atlas_size; ++i) t->unused_tiles.emplace_back(kInvalidTile, i);  // TileAtlasState::new — tile_atlas.rs:302-325
     *out = t;
     return BT_OK;
 }
 
-void bt_tile_tree_destroy(bt_tile_tree* tree) { delete tree; }
+void bt_tile_tree_destroy(bt_tile_tree* tree) {
+    if (!tree) return;
+    bt_atlas_state* st = tree->state;
+    // the view's outstanding requests go back to the shared state (a despawned view releases its tiles)
+    for (TreeSlot& slot : tree->tiles) if (slot.requested) st->release_tile(slot.coordinate);
+    if (st->users) st->users -= 1;
+    if (st->owned_by_tree && st->users == 0) delete st;
+    delete tree;
+}
 
 bt_status bt_tile_tree_add_existing(bt_tile_tree* tree, const bt_tile* tiles, uint32_t count) {
     if (!tree || (!tiles && count)) return BT_ERR_INVALID_ARG;
-    for (uint32_t i = 0; i < count; ++i) tree->existing_tiles.insert(TileKey{tiles[i].side, tiles[i].lod, tiles[i].x, tiles[i].y});
+    for (uint32_t i = 0; i < count; ++i) tree->state->existing_tiles.insert(TileKey{tiles[i].side, tiles[i].lod, tiles[i].x, tiles[i].y});
     return BT_OK;
 }
 
@@ -623,21 +668,22 @@ bt_status bt_tile_tree_update(bt_tile_tree* tree, const double view_world_positi
             }
         }
     }
-    for (const TileKey& k : released) t.release_tile(k);
+    bt_atlas_state& as = *t.state;
+    for (const TileKey& k : released) as.release_tile(k);
     bt_status st = BT_OK;
-    for (const TileKey& k : requested) if (!t.request_tile(k)) st = BT_ERR_CAPACITY;  // atlas out of indices
-    const uint32_t n = (uint32_t)t.pending_loads.size();
+    for (const TileKey& k : requested) if (!as.request_tile(k)) st = BT_ERR_CAPACITY;  // atlas out of indices
+    const uint32_t n = (uint32_t)as.pending_loads.size();   // the terrain's load queue: requests of every view that shares the state
     if (count) *count = n;
-    if (loads) for (uint32_t i = 0; i < n && i < cap; ++i) loads[i] = t.pending_loads[i];
-    if (loads && cap >= n) t.pending_loads.clear();
+    if (loads) for (uint32_t i = 0; i < n && i < cap; ++i) loads[i] = as.pending_loads[i];
+    if (loads && cap >= n) as.pending_loads.clear();
     return st;
 }
 
 // TileAtlasState::loaded_tile_attachment once per attachment collapses to one call per tile
 bt_status bt_tile_tree_mark_loaded(bt_tile_tree* tree, const bt_tile* tile) {
     if (!tree || !tile) return BT_ERR_INVALID_ARG;
-    auto it = tree->tile_states.find(TileKey{tile->side, tile->lod, tile->x, tile->y});
-    if (it == tree->tile_states.end()) return BT_ERR_NOT_FOUND;
+    auto it = tree->state->tile_states.find(TileKey{tile->side, tile->lod, tile->x, tile->y});
+    if (it == tree->state->tile_states.end()) return BT_ERR_NOT_FOUND;
     it->second.loaded = true;
     return BT_OK;
 }

@@ -40,7 +40,7 @@ std::vector<unsigned char> read_file(const char* path) {
 }
 
 std::vector<unsigned char> inflate_all(const unsigned char* src, size_t n, size_t expected) {
-    std::vector<unsigned char> out(expected ? expected : 1);
+    std::vector<unsigned char> out(expected ? std::min<size_t>(expected, std::max<size_t>(n * 4, 1u << 16)) : 1);   // grows on demand up to `expected`
     z_stream z{};
     if (inflateInit(&z) != Z_OK) fail("zlib: inflateInit failed");
     z.next_in = const_cast<unsigned char*>(src);
@@ -284,6 +284,11 @@ Decoded decode_tiff(const std::vector<unsigned char>& file) {
             const unsigned char* src = &file[offsets[index]];
             const uint32_t rows = tiled ? bh : std::min(bh, height - by * bh);   // tiles are always full size, the last strip is short
             const size_t expected = (size_t)bw * rows * bpp;
+            // bound the block BEFORE anything is allocated for it: a tiny crafted file must not make the decoder reserve
+            // gigabytes (tile_w / tile_h / rows_per_strip are attacker-controlled up to kMaxSide each)
+            if (compression == 1 ? counts[index] < expected : expected > plausible_output(counts[index]))
+                fail("TIFF: strip / tile %zu: %zu stored bytes cannot hold %zu decoded bytes", index, (size_t)counts[index], expected);
+            if (tiled && ((size_t)tile_w > 2 * (size_t)width + 16 || (size_t)tile_h > 2 * (size_t)height + 16)) fail("TIFF: tile %u x %u is larger than the image", tile_w, tile_h);
             std::vector<unsigned char> block;
             if (compression == 1) block.assign(src, src + counts[index]);
             else if (compression == 8 || compression == 32946) block = inflate_all(src, counts[index], expected);

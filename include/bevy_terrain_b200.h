@@ -14,7 +14,8 @@
  *
  * Conventions
  *   - every function returns a bt_status (0 = BT_OK); nothing throws/unwinds across the ABI
- *   - opaque handles own all device memory; host inputs are copied during the call
+ *   - opaque handles own all device memory; host input STRUCTS are copied during the call (bulk texel
+ *     uploads are stream-ordered copies from the caller's buffer: see bt_atlas_upload_tile)
  *   - `stream` arguments are a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
  *     per-frame calls are stream-ordered and non-blocking except the *_readback calls
  *   - no allocation on the per-frame path after bt_view_create
@@ -225,7 +226,9 @@ bt_status   bt_context_synchronize(bt_context* ctx);
 /* ------------------------------------------------------------------------------------------ */
 bt_status bt_terrain_create(bt_context* ctx, const bt_terrain_desc* desc, bt_terrain** out);
 void      bt_terrain_destroy(bt_terrain* terrain);
-/* = GpuTileAtlas::upload_tiles (gpu_tile_atlas.rs:309-336): host texels (mip 0, row-major) -> slot */
+/* = GpuTileAtlas::upload_tiles (gpu_tile_atlas.rs:309-336): host texels (mip 0, row-major) -> slot.
+ * The copy is issued asynchronously on `stream` straight from `texels`: with PINNED host memory the buffer must stay valid
+ * and unmodified until the stream has reached the copy (pageable memory is staged by the driver before the call returns). */
 bt_status bt_atlas_upload_tile(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index,
                                const void* texels, size_t bytes, void* stream);
 /* device-to-device variant (tile produced by bt_preprocessor stays on the GPU) */
@@ -255,7 +258,8 @@ typedef struct bt_view_desc {
     uint32_t geometry_tile_count;  /* capacity of final_tiles / temporary_tiles (ref default 1e6) */
     uint32_t tree_size;
     uint32_t grid_size;
-    uint32_t _pad;
+    uint32_t readback_tile_capacity; /* tiles bt_view_run_frame can return per call (pinned host buffer, allocated by
+                                        bt_view_create); 0 = min(geometry_tile_count, 65536)                        */
     uint64_t max_vertices;         /* vertex buffer capacity in vertices; 0 = grow on demand in bt_gen_vertices */
 } bt_view_desc;
 
@@ -277,7 +281,10 @@ bt_status bt_gen_vertices(bt_view* view, uint32_t flags, void* stream, bt_vertex
 /* One frame in one call = bt_view_update + bt_select_tiles + bt_gen_vertices + read-back of the tile list and indirect
  * record (Prepare + TilingPrepassNode::run + the draw's vertex stage of the reference's frame).  The read-back overlaps
  * gen_vertices on an internal copy stream; on return the tile list is on the host, the vertex buffer is (being) written
- * on the device, stream-ordered on `stream`.  Needs a view created with max_vertices > 0.                          */
+ * on the device, stream-ordered on `stream`.  Needs a view created with max_vertices > 0.  Allocates nothing: the copy
+ * stream, events and pinned buffers belong to the view (bt_view_create); at most readback_tile_capacity tiles are
+ * returned (*count still receives the true number).  The 1.5 GB vertex stream is NOT copied back: like the reference's
+ * draw, its consumer reads it on the device.                                                                       */
 bt_status bt_view_run_frame(bt_view* view, const bt_view_frame* frame, uint32_t select_flags, uint32_t gen_flags, void* stream,
                         bt_tile* tiles, uint32_t capacity, uint32_t* count, bt_indirect* indirect, bt_vertex_buffer* vertices);
 /* blocking D2H of final_tiles + indirect (the reference never reads these back; the draw
@@ -341,6 +348,15 @@ bt_status bt_model_approximation_compute(const bt_terrain_model* model, const do
  * async file I/O: tiles the tree requests are reported to the caller, who uploads them and
  * marks them loaded.                                                                          */
 typedef struct bt_tile_tree bt_tile_tree;
+/* TileAtlasState (tile_atlas.rs:272-300) is per TERRAIN in the reference and shared by the TileTree of every view:
+ * slot allocation, the LRU of unused slots, existing tiles, the load queue.  Views of one terrain must share one state
+ * (bt_tile_tree_create_shared), otherwise each tree would hand out atlas indices 0..atlas_size-1 on its own and the views
+ * would overwrite each other's slots.  bt_tile_tree_create makes a private state for single-view terrains.           */
+typedef struct bt_atlas_state bt_atlas_state;
+bt_status bt_atlas_state_create(uint32_t atlas_size, bt_atlas_state** out);
+void      bt_atlas_state_destroy(bt_atlas_state* state);     /* freed once the last tree that references it is gone */
+bt_status bt_tile_tree_create_shared(const bt_terrain_model* model, const bt_terrain_view_config* cfg,
+                                     uint32_t lod_count, bt_atlas_state* state, bt_tile_tree** out);
 bt_status bt_tile_tree_create(const bt_terrain_model* model, const bt_terrain_view_config* cfg,
                               uint32_t lod_count, uint32_t atlas_size, bt_tile_tree** out);
 void      bt_tile_tree_destroy(bt_tile_tree* tree);

@@ -345,6 +345,8 @@ static atlas_tile lookup_tile(const bto_vertex_inputs* in, coord c, uint32_t ble
 /* sample_height — attachments.wgsl:7-10,12-24,45-49 */
 static float sample_height_uv(const bto_vertex_inputs* in, uint32_t atlas_index, float u, float v) {
     uint32_t T = in->texture_size;
+    /* textureSampleLevel clamps array_index to [0, layers-1] (WGSL): an INVALID entry (0xFFFFFFFF) reads the last layer */
+    if (in->atlas_size && atlas_index > in->atlas_size - 1u) atlas_index = in->atlas_size - 1u;
     const uint16_t* layer = in->height_atlas + (size_t)atlas_index * T * T;
     float s = sample_r16_layer(layer, T, u, v);
     return o_mix(in->terrain_config.min_height, in->terrain_config.max_height, s);

@@ -54,7 +54,7 @@ typedef struct bto_vertex_inputs {
     float                     view_world_position[3];
     int32_t                   spherical;
     uint32_t                  texture_size;      /* of attachment 0 (height, R16) */
-    uint32_t                  _pad;
+    uint32_t                  atlas_size;        /* layers in height_atlas; array indices clamp to atlas_size-1 (0 = unchecked) */
     const bt_tile_tree_entry* tile_tree;
     const uint16_t*           height_atlas;      /* [atlas_index][T][T] */
     const bt_tile*            tiles;

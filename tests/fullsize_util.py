@@ -28,7 +28,7 @@ def oracle_inputs(ctx, cfg, atlas, tree, tiles, flags, pos, spherical: bool, T: 
     vi.attachments[0].size, vi.attachments[0].scale, vi.attachments[0].offset = float(Cn), float(np.float32(Cn) / np.float32(T)), float(np.float32(B) / np.float32(T))
     vi.mesh = cfg.model.mesh_transform()
     vi.view_world_position[:] = [float(np.float32(p)) for p in pos]
-    vi.spherical, vi.texture_size = int(spherical), T
+    vi.spherical, vi.texture_size, vi.atlas_size = int(spherical), T, cfg.atlas_size
     entries = np.frombuffer(tree.entries, dtype=np.uint32).reshape(-1, 2).copy()
     vi.tile_tree = entries.ctypes.data_as(C.POINTER(F.TileTreeEntry))
     vi.height_atlas = host_atlas.ctypes.data

@@ -50,6 +50,7 @@ class GoldenFrame:
         vi.attachments[0].offset = float(np.float32(self.B) / np.float32(self.T))
         vi.view_world_position[:] = [float(np.float32(v)) for v in self.view_pos]
         vi.spherical, vi.texture_size = int(self.spherical), self.T
+        vi.atlas_size = len(self.atlas)
         vi.tile_tree = self.entries.ctypes.data_as(C.POINTER(F.TileTreeEntry))
         vi.height_atlas = self.atlas.ctypes.data
         vi.tiles = self.tiles.ctypes.data_as(C.POINTER(F.Tile))

@@ -29,7 +29,7 @@ class VertexInputs(C.Structure):
     _fields_ = [("view_config", F.ViewConfigUniform), ("approximation", F.ModelApproximation),
                 ("terrain_config", F.TerrainConfigUniform), ("attachments", F.AttachmentUniform * 8),
                 ("mesh", F.MeshTransform), ("view_world_position", f32 * 3), ("spherical", i32),
-                ("texture_size", u32), ("_pad", u32), ("tile_tree", C.POINTER(F.TileTreeEntry)),
+                ("texture_size", u32), ("atlas_size", u32), ("tile_tree", C.POINTER(F.TileTreeEntry)),
                 ("height_atlas", C.c_void_p), ("tiles", C.POINTER(F.Tile)), ("tile_count", u32), ("flags", u32)]
 
 

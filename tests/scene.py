@@ -81,6 +81,7 @@ class Scene:
         vi.mesh = self.mesh
         vi.view_world_position[:] = [float(np.float32(v)) for v in self.view_pos]
         vi.spherical, vi.texture_size = int(self.spherical), self.T
+        vi.atlas_size = len(self.atlas)
         self._tiles_keep = np.ascontiguousarray(tiles, dtype=np.uint32)
         vi.tile_tree = self.entries.ctypes.data_as(C.POINTER(F.TileTreeEntry))
         vi.height_atlas = self.atlas.ctypes.data

@@ -191,3 +191,45 @@ def test_run_frame_equals_separate_calls(ctx):
             assert np.array_equal(tiles_f, exp_tiles)
     finally:
         tree.close(); atlas.close()
+
+
+def test_vertices_before_any_tile_is_loaded(ctx):
+    """The first frames of the streaming loop: no tile has been marked loaded yet, so every tile-tree entry is INVALID
+    ({0xFFFFFFFF, 0xFFFFFFFF}, tile_tree.rs:51-65).  The reference keeps rendering (WGSL clamps the texture-array index to the
+    last layer); the kernel must do the same — no fault, same bits as the oracle — and the context must stay usable."""
+    from bevy_terrain_b200 import api
+    scene = Scene("planar", lod_count=4, T=64, B=2, src=256, grid_size=16)
+    pos = planar_view_positions(1)[0]
+    scene.move_view(pos)
+    atlas = api.TileAtlas(ctx, scene.terrain_config())
+    tree = api.TileTree(atlas, scene.cfg)
+    try:
+        # upload real texels to the LAST layer so the clamped read is visible in the result, but leave the table INVALID
+        last = scene.atlas_size - 1
+        rng = np.random.default_rng(9)
+        texels = rng.integers(1, 65535, size=(scene.T, scene.T), dtype=np.uint16)
+        atlas.upload_tile(0, last, texels)
+        frame = scene.view_frame()
+        invalid = np.full((len(scene.entries), 2), 0xFFFFFFFF, dtype=np.uint32)
+        import ctypes as C
+        frame.tile_tree = invalid.ctypes.data_as(C.POINTER(F.TileTreeEntry))
+        tree.prepare(frame=frame)
+        tree.select_tiles()
+        tiles, ind = tree.readback()
+        for flags in (F.BT_FLAG_NORMALS, ALL):
+            tree.gen_vertices(flags)
+            verts = tree.download_vertices(0, ind.vertex_count)
+            host = scene.atlas.copy()
+            saved_atlas, saved_entries = scene.atlas, scene.entries
+            try:
+                host[:] = 0
+                host[last] = texels
+                scene.atlas, scene.entries = host, invalid
+                exp = scene.oracle_vertices(tiles, flags)
+            finally:
+                scene.atlas, scene.entries = saved_atlas, saved_entries
+            _assert_vertices_equal(verts, exp)
+        ctx.synchronize()     # no sticky CUDA error
+    finally:
+        tree.close()
+        atlas.close()

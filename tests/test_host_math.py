@@ -173,3 +173,57 @@ def test_ellipsoid_model_local_positions_and_scale():
         assert abs((b[0] / major) ** 2 + (b[1] / minor) ** 2 + (b[2] / major) ** 2 - 1.0) < 1e-9
         foot = _project_numpy(major, minor, p)
         assert np.linalg.norm(b - foot) < 1e-3         # metres: it is the foot point of p on the ellipsoid
+
+
+def test_two_views_of_one_terrain_share_the_atlas_state():
+    """TileAtlasState is per terrain (tile_atlas.rs:272-300): two TileTrees (views) created on one bt_atlas_state never get the
+    same atlas slot for different tiles, a tile requested by both is loaded once, and it stays resident until both released it."""
+    lib = F.load_library()
+    prod, orc, positions = _models()[0]
+    lod_count, atlas_size = 5, 300
+    cfg = O.default_view_config()
+    existing = np.array([(0, l, x, y) for l in range(lod_count) for x in range(1 << l) for y in range(1 << l)], dtype=np.uint32)
+    state, a, b = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert lib.bt_atlas_state_create(atlas_size, C.byref(state)) == F.BT_OK
+    assert lib.bt_tile_tree_create_shared(C.byref(prod.c), C.byref(cfg), lod_count, state, C.byref(a)) == F.BT_OK
+    assert lib.bt_tile_tree_create_shared(C.byref(prod.c), C.byref(cfg), lod_count, state, C.byref(b)) == F.BT_OK
+    assert lib.bt_tile_tree_add_existing(a, existing.ctypes.data_as(C.POINTER(F.Tile)), len(existing)) == F.BT_OK   # shared: visible to b too
+    slot_of = {}
+    n_entries = lod_count * cfg.tree_size ** 2
+
+    def update(tree, pos):
+        buf = (F.TileLoad * atlas_size)(); n = F.u32()
+        assert lib.bt_tile_tree_update(tree, (F.f64 * 3)(*pos), buf, atlas_size, C.byref(n)) == F.BT_OK
+        for l in buf[: n.value]:
+            key = (l.tile.side, l.tile.lod, l.tile.x, l.tile.y)
+            assert key not in slot_of, "a tile both views want is loaded once"
+            slot_of[key] = l.atlas_index
+            assert lib.bt_tile_tree_mark_loaded(tree, C.byref(l.tile)) == F.BT_OK
+        return n.value
+
+    try:
+        pa, pb = positions[0], positions[-1]
+        assert update(a, pa) > 0
+        update(b, pb)
+        assert len(set(slot_of.values())) == len(slot_of), "two views must never be handed the same atlas slot"
+        ent_a = (F.TileTreeEntry * n_entries)(); ent_b = (F.TileTreeEntry * n_entries)()
+        assert lib.bt_tile_tree_entries(a, ent_a, n_entries, None, 0) == F.BT_OK
+        assert lib.bt_tile_tree_entries(b, ent_b, n_entries, None, 0) == F.BT_OK
+        ea, eb = (np.frombuffer(e, dtype=np.uint32).reshape(-1, 2) for e in (ent_a, ent_b))
+        assert ea[0, 0] != 0xFFFFFFFF and eb[0, 0] == ea[0, 0]       # the root tile: one slot, seen by both views
+        valid_b = int((eb[:, 0] != 0xFFFFFFFF).sum())
+        assert valid_b > lod_count
+        # moving view b onto view a's position requests nothing new: the tiles are resident through view a
+        before = len(slot_of)
+        update(b, pa)
+        assert len(slot_of) == before
+        # destroying view a releases its requests; b still holds the same tiles, so they must not be recycled
+        lib.bt_tile_tree_destroy(a); a = C.c_void_p()
+        update(b, pa)
+        assert lib.bt_tile_tree_entries(b, ent_b, n_entries, None, 0) == F.BT_OK
+        after = np.frombuffer(ent_b, dtype=np.uint32).reshape(-1, 2)
+        assert int((after[:, 0] != 0xFFFFFFFF).sum()) >= valid_b and after[0, 0] == ea[0, 0]
+    finally:
+        if a: lib.bt_tile_tree_destroy(a)
+        lib.bt_tile_tree_destroy(b)
+        lib.bt_atlas_state_destroy(state)
