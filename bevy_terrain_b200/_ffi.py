@@ -235,6 +235,15 @@ def _declare(lib: C.CDLL) -> None:
         "bt_preprocessor_tile_device_ptr": (i32, [vp, u32, P(Tile), P(vp)]),
         "bt_preprocessor_get_tile": (i32, [vp, u32, P(Tile), vp, C.c_size_t]),
         "bt_preprocessor_save": (i32, [vp, u32, C.c_char_p]),
+        "bt_preprocessor_hash": (i32, [vp, u32, P(u64), vp]),
+        "bt_comm_unique_id": (i32, [vp, C.c_size_t]),
+        "bt_comm_create": (i32, [vp, u32, u32, vp, C.c_size_t, P(vp)]),
+        "bt_comm_destroy": (None, [vp]),
+        "bt_comm_info": (i32, [vp, P(u32), P(u32), P(i32), P(u32)]),
+        "bt_comm_barrier": (i32, [vp, vp]),
+        "bt_comm_all_reduce_sum_u64": (i32, [vp, P(u64), u32, vp]),
+        "bt_comm_load_error": (C.c_char_p, []),
+        "bt_preprocessor_run_sharded": (i32, [vp, vp, vp]),
         "bt_culling_planes": (None, [P(f32), P(f32 * 4)]),
         "bt_generate_mipmaps": (i32, [vp, u32, u32, u32, vp, vp, vp]),
         "bt_synth_source": (i32, [vp, u32, u32, u32, u32, u32, u32, u32, vp, vp]),

@@ -77,6 +77,58 @@ class Context:
             self._h = C.c_void_p()
 
 
+class Comm:
+    """bt_comm: the multi-GPU communicator of the sharded preprocessor (NCCL over NVLink, one process per GPU).
+
+    Bootstrap like any NCCL program: rank 0 creates the 128-byte unique id (`Comm.unique_id()`), the host distributes it
+    (`broadcast` is any callable bytes -> bytes that returns rank 0's value on every rank, e.g. a torch.distributed or MPI
+    broadcast), then every rank constructs the communicator (collective)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: bytes):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        ctx.check(ctx.lib.bt_comm_create(ctx._h, rank, world, buf, 128, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = F.load_library()
+        buf = C.create_string_buffer(128)
+        st = lib.bt_comm_unique_id(buf, 128)
+        if st != F.BT_OK:
+            raise F.BtError(st, "bt_comm_unique_id: " + (lib.bt_comm_load_error() or b"").decode())
+        return buf.raw
+
+    @staticmethod
+    def from_torch_distributed(ctx: Context) -> "Comm":
+        """convenience bootstrap for hosts that already run torch.distributed: the unique id travels as a broadcast tensor"""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        raw = Comm.unique_id() if rank == 0 else bytes(128)
+        t = torch.tensor(list(raw), dtype=torch.uint8, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, 0)
+        return Comm(ctx, rank, world, bytes(t.cpu().tolist()))
+
+    def info(self) -> dict:
+        r, w, v, p = F.u32(), F.u32(), F.i32(), F.u32()
+        self.ctx.check(self.ctx.lib.bt_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v), C.byref(p)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value, "peer_access": bool(p.value)}
+
+    def barrier(self, stream: int = 0) -> None:
+        self.ctx.check(self.ctx.lib.bt_comm_barrier(self._h, C.c_void_p(stream)))
+
+    def all_reduce_sum_u64(self, values, stream: int = 0) -> list:
+        arr = (F.u64 * len(values))(*[int(v) & 0xFFFFFFFFFFFFFFFF for v in values])
+        self.ctx.check(self.ctx.lib.bt_comm_all_reduce_sum_u64(self._h, arr, len(values), C.c_void_p(stream)))
+        return list(arr)
+
+    def close(self) -> None:
+        if self._h:
+            self.ctx.lib.bt_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 class AttachmentFormat(enum.IntEnum):  # terrain_data/mod.rs:38-57 (ids)
     Rgba8 = F.BT_FORMAT_RGBA8
     R16 = F.BT_FORMAT_R16
@@ -501,7 +553,12 @@ class Preprocessor:
         self.ctx.check(self.ctx.lib.bt_preprocessor_run(self._h, C.c_void_p(stream)))
         return self
 
-    # phase API (multi-GPU hosts run the collectives in between)
+    def run_sharded(self, comm: "Comm", stream: int = 0) -> "Preprocessor":
+        """the whole sharded job in the library: kernels + ONE grouped NCCL all-gather per wave, overlapped with the interior stitch"""
+        self.ctx.check(self.ctx.lib.bt_preprocessor_run_sharded(self._h, comm._h, C.c_void_p(stream)))
+        return self
+
+    # phase API (hosts that run their own collective between the phases; also what the CPU gloo tests drive)
     def run_split_downsample(self, stream: int = 0) -> None:
         self.ctx.check(self.ctx.lib.bt_preprocessor_run_split_downsample(self._h, C.c_void_p(stream)))
 
@@ -550,6 +607,12 @@ class Preprocessor:
         t = F.Tile(*[int(v) for v in tile])
         self.ctx.check(self.ctx.lib.bt_preprocessor_get_tile(self._h, attachment, C.byref(t), out.ctypes.data, out.nbytes))
         return out
+
+    def content_hash(self, attachment: int = 0, stream: int = 0) -> int:
+        """order-independent 64-bit hash of this rank's output tiles (sum over ranks == single-GPU hash iff byte-identical)"""
+        h = F.u64()
+        self.ctx.check(self.ctx.lib.bt_preprocessor_hash(self._h, attachment, C.byref(h), C.c_void_p(stream)))
+        return h.value
 
     def save(self, attachment: int, directory: str) -> None:
         self.ctx.check(self.ctx.lib.bt_preprocessor_save(self._h, attachment, directory.encode()))

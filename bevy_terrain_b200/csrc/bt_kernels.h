@@ -43,6 +43,8 @@ struct RowCopy {
     uint64_t bytes;   // multiple of 2
 };
 
+struct TileHashTask { uint64_t key; uint32_t slot, _pad; };   // key = hash of (attachment-independent) tile coordinate
+
 struct DatasetDevice {
     const void* pixels;     // device pointer to source row `row_begin`, row-major
     uint32_t width, height; // of the WHOLE image

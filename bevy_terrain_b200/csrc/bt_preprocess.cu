@@ -18,6 +18,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "bt_comm.h"
 #include "bt_kernels.h"
 #include "bt_runtime.h"
 
@@ -66,9 +67,18 @@ struct JobPlan {  // all task tables of one job, concatenated: [split | downsamp
     std::vector<PyramidTask> tasks;
     std::vector<DatasetDevice> datasets;
     Range split, stitch;
+    uint32_t stitch_local = 0;   // the first stitch_local tasks of `stitch` need nothing from another rank (run while the exchange is in flight)
     std::vector<Level> levels;
     PyramidTask* d_tasks = nullptr;
     DatasetDevice* d_datasets = nullptr;
+};
+
+// device-resident copy tables + buffer segments of one job's exchange (kind 0 = halo strips, 1 = sub-root tiles), built once
+struct ExchangeTables {
+    RowCopy* d_copies = nullptr;          // [pack kind 0 | pack kind 1 | unpack kind 0 | unpack kind 1]
+    uint32_t pack_begin[2] = {0, 0}, pack_count[2] = {0, 0}, unpack_begin[2] = {0, 0}, unpack_count[2] = {0, 0};
+    uint64_t send_off[2] = {0, 0}, recv_off[2] = {0, 0}, bytes[2] = {0, 0};
+    bool built = false;
 };
 
 struct Job {
@@ -76,6 +86,7 @@ struct Job {
     std::vector<bt_dataset> datasets;
     std::vector<void*> owned_pixels;  // device copies of host-provided sources
     JobPlan plan;
+    ExchangeTables xt;
     bool prepared = false, split_done = false, roots_done = false, halo_done = false, stitched = false;
 };
 
@@ -127,6 +138,8 @@ struct bt_preprocessor {
     std::vector<Job> jobs;
     // scratch device buffers (grown on demand)
     RowCopy* d_copies = nullptr; size_t d_copies_cap = 0;
+    // exchange buffers of the in-library sharded run (bt_preprocessor_run_sharded): all pending jobs' segments back to back
+    unsigned char* d_send = nullptr; unsigned char* d_recv = nullptr; uint64_t send_cap = 0, recv_cap = 0;
 
     bool spherical() const { return kind == BT_KIND_SPHERICAL; }
     bool plan_only() const { return ctx == nullptr; }  // created without a context: host-side planning only
@@ -337,6 +350,18 @@ struct bt_preprocessor {
             }
         }
         P.stitch = Range{stitch_first, (uint32_t)tasks.size() - stitch_first};
+        // sharded: tasks that read nothing another rank produces (no ghost / replica neighbour, not one of the replicated top
+        // levels) go first, so that bt_preprocessor_run_sharded can stitch them while the exchange is still in flight
+        P.stitch_local = P.stitch.count;
+        if (shard.world > 1) {
+            auto local = [&](const PyramidTask& t) {
+                if (t.tile.lod < root_lod) return false;
+                for (int k = 0; k < 8; ++k) if (t.dep[k] != kInvalid && s.kind[t.dep[k]] != kOwned) return false;
+                return true;
+            };
+            const auto mid = std::stable_partition(tasks.begin() + stitch_first, tasks.end(), local);
+            P.stitch_local = (uint32_t)(mid - (tasks.begin() + stitch_first));
+        }
         j.prepared = true;
         if (plan_only()) return BT_OK;
         // device copies (one allocation + one copy per job)
@@ -380,12 +405,15 @@ struct bt_preprocessor {
         return st;
     }
 
-    bt_status run_stitch_job(uint32_t ji, cudaStream_t stream) {
+    // part 0 = the tasks that need nothing from another rank, 1 = the rest, 2 = all
+    bt_status run_stitch_job(uint32_t ji, cudaStream_t stream, int part = 2) {
         Job& j = jobs[ji];
         Store& s = stores[j.attachment];
         const JobPlan& P = j.plan;
-        BT_CUDA(ctx, bt_launch_stitch(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + P.stitch.begin, P.stitch.count, stream));
-        j.stitched = true;
+        const uint32_t first = part == 1 ? P.stitch_local : 0u;
+        const uint32_t count = part == 0 ? P.stitch_local : P.stitch.count - first;
+        BT_CUDA(ctx, bt_launch_stitch(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + P.stitch.begin + first, count, stream));
+        if (part != 0) j.stitched = true;
         return BT_OK;
     }
 
@@ -460,8 +488,10 @@ void bt_preprocessor_destroy(bt_preprocessor* p) {
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (Store& s : p->stores) if (s.arena) cudaFree(s.arena);
-    for (Job& j : p->jobs) { for (void* px : j.owned_pixels) cudaFree(px); cudaFree(j.plan.d_tasks); cudaFree(j.plan.d_datasets); }
+    for (Job& j : p->jobs) { for (void* px : j.owned_pixels) cudaFree(px); cudaFree(j.plan.d_tasks); cudaFree(j.plan.d_datasets); cudaFree(j.xt.d_copies); }
     cudaFree(p->d_copies);
+    cudaFree(p->d_send);
+    cudaFree(p->d_recv);
     delete p;
 }
 
@@ -531,6 +561,9 @@ bt_status bt_preprocessor_add_datasets(bt_preprocessor* p, const bt_dataset* dat
     return BT_OK;
 }
 
+static std::vector<uint32_t> next_wave(const bt_preprocessor* p);
+static bt_status build_exchange_tables(bt_preprocessor* p, const std::vector<uint32_t>& wave, cudaStream_t stream);
+
 // Allocates (and first-use-initialises) the device pyramid store for every pending job, so that a subsequent
 // run contains no cudaMalloc.  Optional: run_* do the same lazily.
 bt_status bt_preprocessor_reserve(bt_preprocessor* p, void* stream) {
@@ -541,6 +574,10 @@ bt_status bt_preprocessor_reserve(bt_preprocessor* p, void* stream) {
         if (p->jobs[ji].stitched) continue;
         bt_status st = p->prepare_job((uint32_t)ji, (cudaStream_t)stream);
         if (st != BT_OK) return st;
+    }
+    if (p->shard.world > 1) {   // the exchange buffers and copy tables of the first wave (bt_preprocessor_run_sharded)
+        const std::vector<uint32_t> wave = next_wave(p);
+        if (!wave.empty()) { bt_status st = build_exchange_tables(p, wave, (cudaStream_t)stream); if (st != BT_OK) return st; }
     }
     return BT_OK;
 }
@@ -697,6 +734,130 @@ static bt_status run_exchange(bt_preprocessor* p, const Job& j, uint32_t kind, b
     return BT_OK;
 }
 
+// ---- in-library sharded run: split/downsample -> pack -> ONE grouped NCCL all-gather on the communicator's stream, overlapped
+// with the stitch of every tile that needs no remote data -> unpack -> replicated top levels -> boundary stitch -----------------
+static bt_status build_exchange_tables(bt_preprocessor* p, const std::vector<uint32_t>& wave, cudaStream_t stream) {
+    bt_context* ctx = p->ctx;
+    bool all_built = true;
+    for (uint32_t ji : wave) all_built = all_built && p->jobs[ji].xt.built;
+    if (all_built) return BT_OK;
+    // buffer segments: per job [halo | roots], back to back; the gathered buffer holds world x the same segments
+    uint64_t send_total = 0;
+    for (uint32_t ji : wave) {
+        Job& j = p->jobs[ji];
+        j.xt.bytes[0] = p->halo_bytes(j);
+        j.xt.bytes[1] = p->roots_bytes(j);
+        for (int k = 0; k < 2; ++k) { j.xt.send_off[k] = send_total; j.xt.recv_off[k] = send_total * p->shard.world; send_total += (j.xt.bytes[k] + 255) & ~255ull; }
+    }
+    BT_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (send_total > p->send_cap) {
+        if (p->d_send) BT_CUDA(ctx, cudaFree(p->d_send));
+        if (p->d_recv) BT_CUDA(ctx, cudaFree(p->d_recv));
+        p->d_send = p->d_recv = nullptr;
+        BT_CUDA(ctx, cudaMalloc((void**)&p->d_send, send_total));
+        BT_CUDA(ctx, cudaMalloc((void**)&p->d_recv, send_total * p->shard.world));
+        p->send_cap = send_total;
+        p->recv_cap = send_total * p->shard.world;
+    }
+    for (uint32_t ji : wave) {
+        Job& j = p->jobs[ji];
+        Store& s = p->stores[j.attachment];
+        std::vector<RowCopy> copies;
+        for (int unpack = 0; unpack < 2; ++unpack)
+            for (uint32_t kind = 0; kind < 2; ++kind) {
+                std::vector<bt_exchange_copy> plan;
+                exchange_plan(p, j, kind, unpack != 0, plan);
+                const uint32_t begin = (uint32_t)copies.size();
+                unsigned char* buffer = unpack ? p->d_recv + j.xt.recv_off[kind] : p->d_send + j.xt.send_off[kind];
+                for (const bt_exchange_copy& c : plan) {
+                    unsigned char* tile = s.arena + (size_t)s.slot_of.at(TileKey{c.tile.side, c.tile.lod, c.tile.x, c.tile.y}) * s.tile_bytes +
+                                          ((size_t)c.tile_row * s.cfg.texture_size + c.tile_col) * s.px;
+                    unsigned char* buf = buffer + c.buffer_offset;
+                    const uint64_t bytes = (uint64_t)c.pixels * s.px;
+                    for (uint64_t o = 0; o < bytes; o += kCopyChunk) {
+                        const uint64_t nb = std::min<uint64_t>(kCopyChunk, bytes - o);
+                        copies.push_back(unpack ? RowCopy{buf + o, tile + o, nb} : RowCopy{tile + o, buf + o, nb});
+                    }
+                }
+                (unpack ? j.xt.unpack_begin : j.xt.pack_begin)[kind] = begin;
+                (unpack ? j.xt.unpack_count : j.xt.pack_count)[kind] = (uint32_t)copies.size() - begin;
+            }
+        if (j.xt.d_copies) { BT_CUDA(ctx, cudaFree(j.xt.d_copies)); j.xt.d_copies = nullptr; }
+        BT_CUDA(ctx, cudaMalloc((void**)&j.xt.d_copies, std::max<size_t>(copies.size(), 1) * sizeof(RowCopy)));
+        if (!copies.empty()) BT_CUDA(ctx, cudaMemcpy(j.xt.d_copies, copies.data(), copies.size() * sizeof(RowCopy), cudaMemcpyHostToDevice));
+        j.xt.built = true;
+    }
+    return BT_OK;
+}
+
+// pending jobs are processed in waves of jobs on DISTINCT attachments (successive datasets of one attachment overlay each other
+// and must stay ordered); config 5 (height + albedo) is one wave = one collective
+static std::vector<uint32_t> next_wave(const bt_preprocessor* p) {
+    std::vector<uint32_t> wave;
+    uint32_t seen = 0;
+    for (uint32_t ji = 0; ji < p->jobs.size(); ++ji) {
+        if (p->jobs[ji].stitched) continue;
+        const uint32_t bit = 1u << p->jobs[ji].attachment;
+        if (seen & bit) break;
+        seen |= bit;
+        wave.push_back(ji);
+    }
+    return wave;
+}
+
+bt_status bt_preprocessor_run_sharded(bt_preprocessor* p, bt_comm* comm, void* stream_) {
+    if (!p || p->plan_only() || !comm) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = p->ctx;
+    if (comm->world != p->shard.world || comm->rank != p->shard.rank || comm->ctx != ctx) {
+        BT_SET_ERROR(ctx, "bt_preprocessor_run_sharded: the communicator (rank %u of %u) does not match the preprocessor's shard (rank %u of %u)",
+                     comm->rank, comm->world, p->shard.rank, p->shard.world);
+        return BT_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (p->shard.world == 1) return bt_preprocessor_run(p, stream_);
+    for (;;) {
+        const std::vector<uint32_t> wave = next_wave(p);
+        if (wave.empty()) break;
+        bt_status st;
+        for (uint32_t ji : wave) if ((st = p->prepare_job(ji, stream)) != BT_OK) return st;
+        if ((st = build_exchange_tables(p, wave, stream)) != BT_OK) return st;
+        // 1. communication-free part: split + downsample of this rank's band, down to the shard boundary level
+        for (uint32_t ji : wave) if ((st = p->run_split_downsample_job(ji, stream)) != BT_OK) return st;
+        // 2. pack every job's sub-root tiles and border strips
+        std::vector<bt_comm_segment> segs;
+        for (uint32_t ji : wave) {
+            Job& j = p->jobs[ji];
+            for (int k = 0; k < 2; ++k) {
+                if (!j.xt.bytes[k]) continue;
+                BT_CUDA(ctx, bt_launch_row_copy(j.xt.d_copies + j.xt.pack_begin[k], j.xt.pack_count[k], stream));
+                segs.push_back(bt_comm_segment{p->d_send + j.xt.send_off[k], p->d_recv + j.xt.recv_off[k], (size_t)j.xt.bytes[k]});
+            }
+        }
+        // 3. ONE grouped collective for the whole wave, on the communicator's stream ...
+        BT_CUDA(ctx, cudaEventRecord(comm->ready, stream));
+        BT_CUDA(ctx, cudaStreamWaitEvent(comm->stream, comm->ready, 0));
+        if ((st = bt_comm_all_gather_group(comm, segs.data(), (uint32_t)segs.size(), comm->stream)) != BT_OK) return st;
+        BT_CUDA(ctx, cudaEventRecord(comm->done, comm->stream));
+        // 4. ... while the compute stream stitches every tile whose neighbours are all local
+        for (uint32_t ji : wave) if ((st = p->run_stitch_job(ji, stream, 0)) != BT_OK) return st;
+        // 5. behind the collective: unpack, the replicated top levels, and the boundary tiles' stitch
+        BT_CUDA(ctx, cudaStreamWaitEvent(stream, comm->done, 0));
+        for (uint32_t ji : wave) {
+            Job& j = p->jobs[ji];
+            if (j.xt.bytes[1]) {
+                BT_CUDA(ctx, bt_launch_row_copy(j.xt.d_copies + j.xt.unpack_begin[1], j.xt.unpack_count[1], stream));
+                if ((st = p->run_levels(ji, p->root_lod, j.datasets[0].lod_begin, false, stream)) != BT_OK) return st;
+            }
+            j.roots_done = true;
+            if (j.xt.bytes[0]) BT_CUDA(ctx, bt_launch_row_copy(j.xt.d_copies + j.xt.unpack_begin[0], j.xt.unpack_count[0], stream));
+            j.halo_done = true;
+            if ((st = p->run_stitch_job(ji, stream, 1)) != BT_OK) return st;
+        }
+    }
+    return BT_OK;
+}
+
 // host-side planning entry points (work on a plan-only preprocessor too)
 bt_status bt_preprocessor_plan(bt_preprocessor* p) {
     if (!p) return BT_ERR_INVALID_ARG;
@@ -815,6 +976,41 @@ bt_status bt_preprocessor_get_tile(bt_preprocessor* p, uint32_t attachment, cons
     if (bytes != p->stores[attachment].tile_bytes) { BT_SET_ERROR(p->ctx, "get_tile: expected %zu bytes", p->stores[attachment].tile_bytes); return BT_ERR_INVALID_ARG; }
     BT_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
     BT_CUDA(p->ctx, cudaMemcpy(host_out, dev, bytes, cudaMemcpyDeviceToHost));
+    return BT_OK;
+}
+
+// Order-independent 64-bit content hash of this rank's OUTPUT tiles (coordinate-keyed): the sum over ranks of a sharded run
+// equals the hash of the single-GPU pyramid iff every tile is byte-identical (up to 2^-64 collisions).  Blocking.
+bt_status bt_preprocessor_hash(bt_preprocessor* p, uint32_t attachment, uint64_t* out, void* stream) {
+    if (!p || p->plan_only() || !out || attachment >= p->stores.size()) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = p->ctx;
+    const Store& s = p->stores[attachment];
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<btd::TileHashTask> tasks;
+    for (uint32_t i = 0; i < s.keys.size(); ++i) {
+        if (!is_output(p, s, i)) continue;
+        const TileKey& k = s.keys[i];
+        uint64_t key = 0x9e3779b97f4a7c15ull;
+        for (uint32_t w : {k.side, k.lod, k.x, k.y}) { key ^= w; key *= 0x100000001b3ull; key ^= key >> 29; }
+        tasks.push_back(btd::TileHashTask{key, i, 0u});
+    }
+    *out = 0;
+    if (tasks.empty()) return BT_OK;
+    btd::TileHashTask* d_tasks = nullptr;
+    unsigned long long* d_out = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaMalloc((void**)&d_tasks, tasks.size() * sizeof(btd::TileHashTask)));
+    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(btd::TileHashTask), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = bt_launch_tile_hash(s.arena, s.tile_bytes, d_tasks, (uint32_t)tasks.size(), d_out, st);
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_tasks);
+    cudaFree(d_out);
+    BT_CUDA(ctx, e);
+    *out = (uint64_t)h;
     return BT_OK;
 }
 

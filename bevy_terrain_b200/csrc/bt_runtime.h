@@ -77,4 +77,6 @@ cudaError_t bt_launch_synth(uint32_t format, uint32_t width, uint32_t height, ui
                             uint32_t holes, void* out, cudaStream_t stream);
 cudaError_t bt_launch_selftest(const float* x, float* log2_out, uint32_t n, uint32_t* mismatches, cudaStream_t stream);
 cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream);
+cudaError_t bt_launch_tile_hash(const void* arena, uint64_t tile_bytes, const btd::TileHashTask* tasks, uint32_t n,
+                                unsigned long long* out, cudaStream_t stream);
 }

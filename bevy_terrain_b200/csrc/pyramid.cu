@@ -539,6 +539,46 @@ __global__ void row_copy_kernel(const RowCopy* __restrict__ copies, uint32_t n_c
 }
 }  // namespace btd
 
+// ------------------------------------------------------------------------------------------------
+// content hash of a set of tiles (order-independent 64-bit sum): lets a sharded run prove on the device that the union of
+// the ranks' tiles equals the single-GPU pyramid without moving 32 GiB to the host
+// ------------------------------------------------------------------------------------------------
+namespace btd {
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+__global__ void __launch_bounds__(256) tile_hash_kernel(const unsigned char* __restrict__ arena, uint64_t tile_bytes,
+                                                        const TileHashTask* __restrict__ tasks, unsigned long long* __restrict__ out) {
+    const TileHashTask t = tasks[blockIdx.x];
+    const uint4* w = reinterpret_cast<const uint4*>(arena + (size_t)t.slot * tile_bytes);
+    const uint32_t n = (uint32_t)(tile_bytes / 16);
+    uint64_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        const uint4 v = w[i];
+        const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        acc += mix64(lo + mix64(t.key + 2ull * i)) + mix64(hi + mix64(t.key + 2ull * i + 1ull));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ uint64_t part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t s = 0;
+        for (int k = 0; k < 8; ++k) s += part[k];
+        atomicAdd(out, (unsigned long long)s);
+    }
+}
+}  // namespace btd
+
+extern "C" cudaError_t bt_launch_tile_hash(const void* arena, uint64_t tile_bytes, const btd::TileHashTask* tasks, uint32_t n,
+                                           unsigned long long* out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (tile_bytes % 16) return cudaErrorInvalidValue;
+    btd::tile_hash_kernel<<<n, 256, 0, stream>>>(static_cast<const unsigned char*>(arena), tile_bytes, tasks, out);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     btd::row_copy_kernel<<<(n + 7u) / 8u, 256, 0, stream>>>(copies, n);

@@ -447,12 +447,34 @@ bt_status bt_preprocessor_halo_unpack(bt_preprocessor* p, const void* device_gat
 bt_status bt_preprocessor_roots_bytes(bt_preprocessor* p, uint64_t* send_bytes_per_rank);
 bt_status bt_preprocessor_roots_pack(bt_preprocessor* p, void* device_send, void* stream);
 bt_status bt_preprocessor_roots_unpack_and_finish(bt_preprocessor* p, const void* device_gathered, void* stream);
+/* ---- multi-GPU communicator (one process per GPU of one box; NCCL over NVLink / NVSwitch, loaded with dlopen at
+ * bt_comm_create so single-GPU hosts never touch it).  Bootstrap like any NCCL program: rank 0 calls bt_comm_unique_id and
+ * the host distributes the 128 bytes (MPI, a TCP store, a file ...), then every rank calls bt_comm_create (collective).     */
+#define BT_COMM_UNIQUE_ID_BYTES 128u
+#define BT_COMM_MAX_RANKS 8u
+typedef struct bt_comm bt_comm;
+bt_status   bt_comm_unique_id(void* out, size_t bytes);                     /* = ncclGetUniqueId */
+bt_status   bt_comm_create(bt_context* ctx, uint32_t rank, uint32_t world, const void* unique_id, size_t id_bytes, bt_comm** out);
+void        bt_comm_destroy(bt_comm* comm);
+bt_status   bt_comm_info(const bt_comm* comm, uint32_t* rank, uint32_t* world, int32_t* nccl_version, uint32_t* peer_access);
+bt_status   bt_comm_barrier(bt_comm* comm, void* stream);                   /* stream-ordered, all ranks */
+bt_status   bt_comm_all_reduce_sum_u64(bt_comm* comm, uint64_t* values, uint32_t count, void* stream);   /* host in/out, blocking */
+const char* bt_comm_load_error(void);                                       /* why libnccl could not be loaded, if it could not */
+/* The sharded preprocess in ONE call (replaces the Python-driven phase sequence): per wave of pending jobs
+ * split + downsample of this rank's band -> pack -> ONE grouped all-gather of all sub-root tiles and border strips on the
+ * communicator's stream, overlapped with the stitch of every tile whose neighbours are local -> unpack -> the replicated top
+ * levels -> stitch of the boundary tiles (stitch fused behind its collective).  Stream-ordered on `stream`;
+ * bt_preprocessor_reserve beforehand keeps every allocation and table upload out of it.  Returns BT_ERR_NCCL on transport errors. */
+bt_status   bt_preprocessor_run_sharded(bt_preprocessor* p, bt_comm* comm, void* stream);
 /* results */
 bt_status bt_preprocessor_tile_count(bt_preprocessor* p, uint32_t attachment, uint32_t* count);
 bt_status bt_preprocessor_list_tiles(bt_preprocessor* p, uint32_t attachment, bt_tile* tiles, uint32_t cap, uint32_t* count);
 /* device pointer of one tile's texels (texture_size^2 pixels, mip 0) */
 bt_status bt_preprocessor_tile_device_ptr(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void** out);
 bt_status bt_preprocessor_get_tile(bt_preprocessor* p, uint32_t attachment, const bt_tile* tile, void* host_out, size_t bytes);
+/* order-independent 64-bit content hash of this rank's output tiles of one attachment (coordinate-keyed, computed on the
+ * device): the wrapping sum over the ranks of a sharded run equals the hash of the single-GPU pyramid iff all tiles agree */
+bt_status bt_preprocessor_hash(bt_preprocessor* p, uint32_t attachment, uint64_t* out, void* stream);
 /* Save (tile_atlas.rs:77-116, formats/mod.rs:9-36): <dir>/<side>_<lod>_<x>_<y>.bin + config.tc */
 bt_status bt_preprocessor_save(bt_preprocessor* p, uint32_t attachment, const char* directory);
 
