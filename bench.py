@@ -64,11 +64,19 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 # host threads: decided HERE, not inherited (torch.distributed.run exports OMP_NUM_THREADS=1)
 # ------------------------------------------------------------------------------------------------
+_HOST_THREADS = None
+
+
 def host_threads() -> int:
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(1, os.cpu_count() or 1)
+    """the cores this process may run on, sampled ONCE at start-up: after libgomp has initialised with OMP_PROC_BIND the initial
+    thread is bound to a single place and sched_getaffinity would report 1"""
+    global _HOST_THREADS
+    if _HOST_THREADS is None:
+        try:
+            _HOST_THREADS = max(1, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            _HOST_THREADS = max(1, os.cpu_count() or 1)
+    return _HOST_THREADS
 
 
 def pin_openmp_env():

@@ -33,9 +33,21 @@ namespace btd {
 #endif
 constexpr uint32_t GEN_ROTATION = BT_GEN_ROTATION;
 constexpr int GEN_COMPUTE_WARPS = BT_GEN_COMPUTE_WARPS;  // compute warps per CTA (+ 1 store warp), one CTA per SM
-constexpr int GEN_THREADS = (GEN_COMPUTE_WARPS + 1) * 32;
+constexpr int GEN_THREADS = (GEN_COMPUTE_WARPS + 1) * 32;   // + the auxiliary warp (per-item tables, TMA stores)
 constexpr int GEN_CTAS_PER_SM = 1;
-constexpr int GEN_BUFFERS = 2;         // output images per CTA: compute of item i+1 overlaps the TMA stores of item i
+#ifndef BT_GEN_BUFFERS
+#define BT_GEN_BUFFERS 2
+#endif
+#ifndef BT_GEN_MAX_CB
+#define BT_GEN_MAX_CB 16
+#endif
+#ifndef BT_GEN_FULL_SLEEP_NS
+#define BT_GEN_FULL_SLEEP_NS 256
+#endif
+#ifndef BT_GEN_EMPTY_SLEEP_NS
+#define BT_GEN_EMPTY_SLEEP_NS 64
+#endif
+constexpr int GEN_BUFFERS = BT_GEN_BUFFERS;   // output images per CTA: compute of item i+1 overlaps the TMA stores of item i
 // Strips are laid out in the smem image with a stride that is 16 (mod 128) bytes: lanes of a warp write records of 32 different
 // strips, and with that stride each quarter-warp of a 128-bit store (and each half-warp of a 64-bit one) covers all 32 banks
 // once (the 40-byte records themselves are 8-byte aligned; the stride keeps every strip 16-byte aligned for the TMA).
@@ -59,6 +71,7 @@ struct GenParams {
     uint32_t magic_items;      // ceil(2^32 / items_per_tile): w / items_per_tile == umulhi(w, magic_items) (w < 2^32 / items_per_tile)
     uint32_t magic_cols;       // ceil(2^32 / (CB + 1)) for full-width items
     uint32_t magic_cols_ragged;  // the same for the narrower last item of a tile (g % CB strips), if any
+    uint32_t table_bytes;      // one slot of per-item tables: sizeof(ItemTables) + (g + 1) row entries, 128-byte multiple
 };
 
 struct Record {  // one bt_vertex as five 8-byte words
@@ -82,7 +95,28 @@ struct FrameConsts {
     float lod_cap;             // f32(lod_count) - 0.00001 (functions.wgsl:52)
     uint32_t tree_size, tree_mask, lod_count;  // tree_mask = tree_size - 1 when tree_size is a power of two, else 0
     uint32_t last_layer;       // atlas_size - 1: texture-array indices clamp to it
+    uint32_t morph_mant, blend_mant;   // mantissa thresholds of the certain-zero tests of the morph / blend ratio (ratio_is_certainly_zero)
 };
+
+// The morph and blend ratios are  inverse_mix(lod + range, lod, t) = saturate((t - (lod + range)) / (lod - (lod + range)))  with
+// t = log2_det(x); they are exactly 0 whenever t >= fl(lod + range).  For a positive normal x = m * 2^k (1 <= m < 2) the value
+// log2_det(x) differs from k + log2(m) by less than 1e-5 (a few ulp of a number < 64, tests/test_oracle_numerics.py), so
+//     k == lod  and  log2(m) >= range + 2e-4      (or k > lod, given range <= 0.99)
+// guarantees t >= fl(lod + range) without evaluating log2_det.  The threshold on the 23 mantissa bits of m is computed once per
+// thread; 0xFFFFFFFF disables the shortcut (range outside (0, 0.99]: every vertex takes the full evaluation).
+__device__ __forceinline__ uint32_t range_mantissa_threshold(float range) {
+    if (!(range > 0.0f) || range > 0.99f) return 0xFFFFFFFFu;
+    const float m = exp2f(range + 2e-4f);                        // in (1, 2); exp2f is accurate to 2 ulp, the 2e-4 margin covers it
+    const uint32_t t = (uint32_t)ceilf((m - 1.0f) * 8388608.0f) + 2u;
+    return t < 0x007fe000u ? t : 0xFFFFFFFFu;
+}
+// x = m * 2^k positive and normal?  Splits it into k and the mantissa bits.
+__device__ __forceinline__ bool split_normal(float x, int& k, uint32_t& mant) {
+    const uint32_t bits = __float_as_uint(x), expo = bits >> 23;   // sign + exponent
+    k = (int)expo - 127;
+    mant = bits & 0x007fffffu;
+    return (expo - 1u) < 253u;
+}
 
 template <bool SPHERICAL>
 __device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) {
@@ -108,6 +142,8 @@ __device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) 
     F.tree_mask = (F.tree_size & (F.tree_size - 1u)) == 0u ? F.tree_size - 1u : 0u;
     F.lod_count = U.terrain_config.lod_count;
     F.last_layer = U.atlas_size ? U.atlas_size - 1u : 0u;
+    F.morph_mant = range_mantissa_threshold(U.view_config.morph_range);
+    F.blend_mant = range_mantissa_threshold(U.view_config.blend_range);
     return F;
 }
 
@@ -247,18 +283,17 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
     return out;
 }
 
-// sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch); `pre` carries the shared taps
+// sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch); `pre` carries the shared taps, `distance_between_samples`
+// = side_length / (attachments[0].size * tile_count(tile.lod)) comes from the per-item LOD record (or the generic lookup)
 template <bool SPHERICAL>
-__device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16_t* __restrict__ layer, const AtlasTile& t,
-                                              float u, float v, Vec3 vertex_normal, const FiveTaps* pre = nullptr) {
-    const float pixels_per_side = F.size0 * tile_count(t.c.lod);
-    const float distance_between_samples = div_rn(F.side_length, pixels_per_side);
+__device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16_t* __restrict__ layer, uint32_t side,
+                                              float distance_between_samples, float u, float v, Vec3 vertex_normal, const FiveTaps& pre) {
     const float offset = F.normal_offset;
     float left, up, right, down;
-    if (pre && pre->ok) {
+    if (pre.ok) {
         // mix(min_h, max_h, s) = min_h * (1 - s) + max_h * s for two taps at a time; the sum of the two products stays scalar
         const float2 lo = make_float2(F.min_h, F.min_h), hi = make_float2(F.max_h, F.max_h), one = make_float2(1.0f, 1.0f);
-        const float2 s_lr = make_float2(pre->left, pre->right), s_ud = make_float2(pre->up, pre->down);
+        const float2 s_lr = make_float2(pre.left, pre.right), s_ud = make_float2(pre.up, pre.down);
         const float2 a_lr = __fmul2_rn(lo, __fadd2_rn(one, make_float2(-s_lr.x, -s_lr.y))), b_lr = __fmul2_rn(hi, s_lr);
         const float2 a_ud = __fmul2_rn(lo, __fadd2_rn(one, make_float2(-s_ud.x, -s_ud.y))), b_ud = __fmul2_rn(hi, s_ud);
         left = a_lr.x + b_lr.x;
@@ -275,7 +310,7 @@ __device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16
     Vec3 r;
     if (SPHERICAL) {
         Vec3 face_up;
-        switch (t.c.side) {
+        switch (side) {
             case 0: case 1: face_up = Vec3{0.0f, 1.0f, 0.0f}; break;
             case 2: case 3: face_up = Vec3{0.0f, 0.0f, -1.0f}; break;
             default: face_up = Vec3{-1.0f, 0.0f, 0.0f}; break;
@@ -291,82 +326,259 @@ __device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16
     return normalize3(r);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-item tables (shared memory), produced by the SETUP warp a few items ahead of the compute warps.
+//
+// Everything in vertex_info / lookup_tile that depends only on (tile, grid column), (tile, grid row) or
+// (tile, blend LOD) is evaluated ONCE per item with exactly the operations the per-vertex formula performs
+// (so the per-vertex result is bit-identical), instead of ~150 instructions per vertex:
+//   col[lx]  : coordinate u of the grid column and the column part of compute_local_position /
+//              position_local_to_world (functions.wgsl:73-96,26-29)
+//   row[gy]  : the same for grid rows
+//   lod[L]   : lookup_tile(coordinate, L) for every blend LOD L <= tile.lod: both coordinate_change_lod steps of
+//              functions.wgsl:232-246 collapse to  uv' = ((f1 + uv) * s1 + f2) * s2  with per-(item, L) constants — a step with
+//              delta 0 is encoded as f = 0, s = 1, which leaves uv unchanged bit for bit (uv >= +0) — plus the
+//              tile-tree entry's atlas layer and sample_normal's distance_between_samples.
+// Blend LODs above the tile's own LOD (a geometry tile coarser than the data it samples: lookups then differ
+// per vertex) and table entries with atlas_lod > lod take the generic per-vertex path.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEN_TABLE_SLOTS = 4;      // tables of up to 4 items in flight
+constexpr int GEN_TABLE_LEAD = 2;       // the auxiliary warp builds them this many items ahead of the item whose image it stores
+constexpr int GEN_MAX_COLS = 32;        // strips per item + 1 <= 17
+constexpr uint32_t LODREC_SLOW = 0x80000000u;
+
+struct alignas(16) LodRecord {
+    float f1x, f1y, f2x, f2y;           // offsets of the two change_lod steps
+    float s1, s2;                       // their scales (2^delta)
+    float dbs;                          // distance_between_samples of the resolved atlas tile
+    uint32_t layer;                     // min(atlas_index, atlas_size - 1) | LODREC_SLOW
+};
+
+struct alignas(16) ItemTables {
+    float4 col[GEN_MAX_COLS];
+    LodRecord lod[32];
+    uint4 tile;                         // side, lod, x, y
+    // float4 row[grid_size + 1] follows
+};
+
+template <bool SPHERICAL>
+__device__ __forceinline__ float4 axis_terms(const ViewUniforms& U, const FrameConsts& F, uint32_t tile_xy, float inv_tc, uint32_t g_index, int axis) {
+    // compute_tile_uv — functions.wgsl:64-71 (x / g == x * (1/g) exactly when g is a power of two)
+    const float t = F.g_pow2 ? (float)g_index * F.inv_g : (float)g_index / F.g;
+    float w = ((float)tile_xy + t) * inv_tc;        // compute_local_position: (xy + uv) / tile_count(lod)
+    if (!SPHERICAL) {
+        const float p = w - 0.5f;                   // local x (axis 0) or z (axis 1); local y = 0
+        const float* a = U.mesh.world_from_local;
+        if (axis == 0)   // position_local_to_world: (a[k] * p.x + a[3 + k] * p.y) — the first sum of every row, with p.y = 0
+            return make_float4(t, a[0] * p + a[3] * 0.0f, a[1] * p + a[4] * 0.0f, a[2] * p + a[5] * 0.0f);
+        return make_float4(t, a[6] * p, a[7] * p, a[8] * p);   // ... + a[6 + k] * p.z
+    }
+    w = (w - 0.5f) * 2.0f;                          // (uv - 0.5) / 0.5, exact
+    const float q = div_rn(w, sqrt_rn(BT_ONE_PLUS_C_SQR_F - (BT_C_SQR_F * w) * w));   // the cube-to-sphere warp of one axis
+    return make_float4(t, q, 0.0f, 0.0f);
+}
+
+// One item's tables, computed by the 32 lanes of the setup warp.
+template <bool SPHERICAL>
+__device__ __forceinline__ void build_item_tables(const ViewUniforms& U, const FrameConsts& F, const bt_tile_tree_entry* __restrict__ tile_tree,
+                                                  ItemTables& T, float4* rows, const bt_tile& tile, uint32_t c0, uint32_t n_cols, uint32_t n_rows, int lane) {
+    const float inv_tc = exp2i(-(int)(tile.lod & 31u));
+    for (uint32_t lx = (uint32_t)lane; lx < n_cols; lx += 32u) T.col[lx] = axis_terms<SPHERICAL>(U, F, tile.x, inv_tc, c0 + lx, 0);
+    for (uint32_t gy = (uint32_t)lane; gy < n_rows; gy += 32u) rows[gy] = axis_terms<SPHERICAL>(U, F, tile.y, inv_tc, gy, 1);
+    if (lane == 0) T.tile = make_uint4(tile.side, tile.lod, tile.x, tile.y);
+    const uint32_t L = (uint32_t)lane;
+    LodRecord r{0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f, LODREC_SLOW};
+    if (L < F.lod_count && L <= tile.lod) {
+        // first coordinate_change_lod: tile.lod -> L (down or equal)
+        uint32_t x = tile.x, y = tile.y;
+        const int d1 = (int)L - (int)tile.lod;
+        if (d1 != 0) {
+            const uint32_t shift = (uint32_t)(-d1) & 31u, mask = (1u << shift) - 1u;
+            r.f1x = (float)(x & mask);
+            r.f1y = (float)(y & mask);
+            r.s1 = exp2i(d1);
+            x >>= shift;
+            y >>= shift;
+        }
+        const uint32_t ts = F.tree_size;
+        const uint32_t tx = F.tree_mask ? (x & F.tree_mask) : x % ts, ty = F.tree_mask ? (y & F.tree_mask) : y % ts;
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(tile_tree) + (((tile.side * F.lod_count + L) * ts + tx) * ts + ty));
+        // second coordinate_change_lod: L -> entry.atlas_lod (down or equal for a valid table; INVALID = 0xFFFFFFFF is "down" too)
+        const int d2 = (int)e.y - (int)L;
+        if (d2 <= 0) {
+            if (d2 != 0) {
+                const uint32_t shift = (uint32_t)(-d2) & 31u, mask = (1u << shift) - 1u;
+                r.f2x = (float)(x & mask);
+                r.f2y = (float)(y & mask);
+                r.s2 = exp2i(d2);
+            }
+            r.dbs = div_rn(F.side_length, F.size0 * tile_count(e.y));
+            r.layer = min(e.x, F.last_layer);
+        }
+    }
+    T.lod[lane] = r;
+}
+
+struct Lookup {
+    const uint16_t* layer;
+    float u, v;        // attachment_uv of the resolved atlas coordinate
+    float dbs;
+};
+
+// lookup_tile + attachment_uv through the item's LOD record; generic per-vertex evaluation when the record says so
+template <bool SPHERICAL>
+__device__ __forceinline__ Lookup lookup_sample_point(const FrameConsts& F, const ItemTables& T, const bt_tile_tree_entry* __restrict__ tile_tree,
+                                                      const uint16_t* __restrict__ atlas, const bt_tile& tile, float cu, float cv, uint32_t lod) {
+    Lookup out;
+    const uint32_t tile_texels = (uint32_t)(F.T * F.T);
+    const LodRecord* rec = &T.lod[lod & 31u];
+    const float4 ra = *reinterpret_cast<const float4*>(rec);
+    const float4 rb = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(rec) + 16);
+    const uint32_t layer_bits = __float_as_uint(rb.w);
+    float u, v;
+    if (lod < 32u && !(layer_bits & LODREC_SLOW)) {
+        const float2 t1 = __fmul2_rn(__fadd2_rn(make_float2(ra.x, ra.y), make_float2(cu, cv)), make_float2(rb.x, rb.x));
+        const float2 t2 = __fmul2_rn(make_float2(ra.z + t1.x, ra.w + t1.y), make_float2(rb.y, rb.y));
+        u = t2.x;
+        v = t2.y;
+        out.layer = atlas + (size_t)layer_bits * tile_texels;
+        out.dbs = rb.z;
+    } else {
+        const AtlasTile t = lookup_tile(F, tile_tree, Coord{tile.side, tile.lod, tile.x, tile.y, cu, cv}, lod);
+        u = t.c.u;
+        v = t.c.v;
+        out.layer = atlas + (size_t)min(t.index, F.last_layer) * tile_texels;
+        out.dbs = div_rn(F.side_length, F.size0 * tile_count(t.c.lod));
+    }
+    // attachment_uv — attachments.wgsl:7-10
+    const float2 s = __fmul2_rn(make_float2(u, v), make_float2(F.a_scale, F.a_scale));
+    out.u = s.x + F.a_offset;
+    out.v = s.y + F.a_offset;
+    return out;
+}
+
+// floor(log2_det(x)) clamped like compute_blend does, WITHOUT evaluating log2_det when the result is certain:
+// for a positive normal x = m * 2^k with m <= 2 - 2^-10, log2_det(x) lies in [k, k + 1 - 7e-4] (its error is < 1e-5), so
+// u32(min(log2_det(x), cap)) == clamp(k, 0, u32(cap)) exactly.  Everything else (m within 2^-10 of 2, denormals, inf, nan,
+// non-positive) evaluates the full function.
+__device__ __forceinline__ uint32_t blend_lod_of(float x, float lod_cap) {
+    int k;
+    uint32_t mant;
+    if (split_normal(x, k, mant) && mant < 0x007fe000u) return (uint32_t)min(max(k, 0), (int)f2u(lod_cap));
+    return f2u(fminf(log2_det(x), lod_cap));
+}
+
 // vertex_info + vertex + vertex_output — vertex.wgsl:30-98
 template <bool SPHERICAL>
-__device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const FrameConsts& F, const bt_tile_tree_entry* __restrict__ tile_tree,
-                                                 const uint16_t* __restrict__ atlas, uint32_t flags, const bt_tile& tile,
-                                                 uint32_t tile_index, uint32_t gx, uint32_t gy) {
+__device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const FrameConsts& F, const ItemTables& T, const float4* __restrict__ rows,
+                                                 const bt_tile_tree_entry* __restrict__ tile_tree, const uint16_t* __restrict__ atlas,
+                                                 uint32_t flags, const bt_tile& tile, uint32_t tile_index, uint32_t lx, uint32_t gy) {
     const bt_view_config_uniform& vc = U.view_config;
     const bt_model_approximation& ap = U.approximation;
     const float g = F.g;
-    // compute_tile_uv — functions.wgsl:64-71 (x / g == x * (1/g) exactly when g is a power of two)
-    const float u0 = F.g_pow2 ? (float)gx * F.inv_g : (float)gx / g;
-    const float v0 = F.g_pow2 ? (float)gy * F.inv_g : (float)gy / g;
-    const Coord c0{tile.side, tile.lod, tile.x, tile.y, u0, v0};
-    Vec3 lp = local_position<SPHERICAL>(c0);
-    Vec3 wp = position_local_to_world(U.mesh, lp);
-    Vec3 wn = SPHERICAL ? normal_local_to_world<SPHERICAL>(U.mesh, lp) : F.planar_normal;
+    const float4 cr = T.col[lx], rr = rows[gy];
+    const float u0 = cr.x, v0 = rr.x;          // compute_tile_uv
+    Vec3 lp, wp, wn;
+    if (!SPHERICAL) {
+        const float* a = U.mesh.world_from_local;
+        wp = Vec3{(cr.y + rr.y) + a[9], (cr.z + rr.z) + a[10], (cr.w + rr.w) + a[11]};   // position_local_to_world, column + row + translation
+        wn = F.planar_normal;
+        lp = Vec3{0.0f, 0.0f, 0.0f};
+    } else {
+        const float qu = cr.y, qv = rr.y;
+        Vec3 p;
+        switch (tile.side) {
+            case 0: p = Vec3{-1.0f, -qv, qu}; break;
+            case 1: p = Vec3{qu, -qv, 1.0f}; break;
+            case 2: p = Vec3{qu, 1.0f, qv}; break;
+            case 3: p = Vec3{1.0f, -qu, qv}; break;
+            case 4: p = Vec3{qv, -qu, -1.0f}; break;
+            case 5: p = Vec3{qv, -1.0f, qu}; break;
+            default: p = Vec3{0.0f, 0.0f, 0.0f}; break;
+        }
+        lp = normalize3(p);
+        wp = position_local_to_world(U.mesh, lp);
+        wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
+    }
     const float h0 = ap.approximate_height;
     const float* e = U.view_world_position;
     float d = length3(Vec3{(wp.x + h0 * wn.x) - e[0], (wp.y + h0 * wn.y) - e[1], (wp.z + h0 * wn.z) - e[2]});
+    const Coord c0{tile.side, tile.lod, tile.x, tile.y, u0, v0};
     const bool high_precision = (flags & BT_FLAG_HIGH_PRECISION) && d < vc.precision_threshold_distance;
     if (high_precision) {
         const Vec3 rel = relative_position(ap, c0);
         d = length3(Vec3{rel.x + h0 * wn.x, rel.y + h0 * wn.y, rel.z + h0 * wn.z});
     }
     // compute_morph — functions.wgsl:35-49
-    Coord c = c0;
+    float cu = u0, cv = v0;
+    bool morphed = false;    // false: the morph ratio is exactly 0, so mix(uv, even_uv, 0) == uv bit for bit and nothing moves
     if (flags & BT_FLAG_MORPH) {
-        const float target_lod = log2_det(div_rn(2.0f * vc.morph_distance, d));
-        const float ratio = (c0.lod == 0u) ? 0.0f : inverse_mix_rn((float)c0.lod + vc.morph_range, (float)c0.lod, target_lod);
-        const float even_u = F.g_pow2 ? (float)(f2u(c0.u * g) & ~1u) * F.inv_g : (float)(f2u(c0.u * g) & ~1u) / g;
-        const float even_v = F.g_pow2 ? (float)(f2u(c0.v * g) & ~1u) * F.inv_g : (float)(f2u(c0.v * g) & ~1u) / g;
-        c.u = mix(c0.u, even_u, ratio);
-        c.v = mix(c0.v, even_v, ratio);
+        const float xm = div_rn(2.0f * vc.morph_distance, d);
+        int k;
+        uint32_t mant;
+        const bool zero = tile.lod == 0u || (split_normal(xm, k, mant) && (k > (int)tile.lod || (k == (int)tile.lod && mant >= F.morph_mant)) &&
+                                             F.morph_mant != 0xFFFFFFFFu);
+        if (!zero) {
+            const float target_lod = log2_det(xm);
+            const float ratio = inverse_mix_rn((float)tile.lod + vc.morph_range, (float)tile.lod, target_lod);
+            const float even_u = F.g_pow2 ? (float)(f2u(u0 * g) & ~1u) * F.inv_g : (float)(f2u(u0 * g) & ~1u) / g;
+            const float even_v = F.g_pow2 ? (float)(f2u(v0 * g) & ~1u) * F.inv_g : (float)(f2u(v0 * g) & ~1u) / g;
+            cu = mix(u0, even_u, ratio);
+            cv = mix(v0, even_v, ratio);
+            morphed = true;
+        }
     }
     if (high_precision) {
-        const Vec3 rel = relative_position(ap, c);
+        const Vec3 rel = relative_position(ap, Coord{tile.side, tile.lod, tile.x, tile.y, cu, cv});
         wp = Vec3{e[0] + rel.x, e[1] + rel.y, e[2] + rel.z};
-    } else if (flags & BT_FLAG_MORPH) {
+    } else if (morphed) {
         // without MORPH the coordinate is unchanged and the recomputation would reproduce lp/wp/wn bit for bit
-        lp = local_position<SPHERICAL>(c);
+        lp = local_position<SPHERICAL>(Coord{tile.side, tile.lod, tile.x, tile.y, cu, cv});
         wp = position_local_to_world(U.mesh, lp);
         if (SPHERICAL) wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
     }
     // compute_blend — functions.wgsl:51-62
-    const float target_lod = fminf(log2_det(div_rn(vc.blend_distance, d)), F.lod_cap);
-    const uint32_t blend_lod = f2u(target_lod);
+    uint32_t blend_lod;
     float blend_ratio = 0.0f;
-    if ((flags & BT_FLAG_BLEND) && blend_lod != 0u)
-        blend_ratio = inverse_mix_rn((float)blend_lod + vc.blend_range, (float)blend_lod, target_lod);
+    const float blend_x = div_rn(vc.blend_distance, d);
+    if (flags & BT_FLAG_BLEND) {
+        int k;
+        uint32_t mant;
+        const bool normal = split_normal(blend_x, k, mant);
+        const int lod_max = (int)f2u(F.lod_cap);
+        if (normal && k < 0) {
+            blend_lod = 0u;                        // log2 < 0: u32() clamps to 0, and LOD 0 never blends
+        } else if (normal && k <= lod_max && mant >= F.blend_mant && mant < 0x007fe000u) {
+            blend_lod = (uint32_t)k;               // floor is certain and the ratio is certainly 0 (see range_mantissa_threshold)
+        } else {
+            const float target_lod = fminf(log2_det(blend_x), F.lod_cap);
+            blend_lod = f2u(target_lod);
+            if (blend_lod != 0u) blend_ratio = inverse_mix_rn((float)blend_lod + vc.blend_range, (float)blend_lod, target_lod);
+        }
+    } else {
+        blend_lod = blend_lod_of(blend_x, F.lod_cap);   // only the integer part is consumed
+    }
 
-    const int tile_texels = F.T * F.T;
     const bool normals = (flags & BT_FLAG_NORMALS) != 0u;
-    const AtlasTile ta = lookup_tile(F, tile_tree, c, blend_lod);
-    // An INVALID entry (0xFFFFFFFF: no tile loaded yet for this slot) samples like the reference does: WGSL clamps the
-    // texture-array index to the last layer (textureSampleLevel array_index), so the frame keeps rendering.
-    const uint16_t* layer_a = atlas + (size_t)min(ta.index, F.last_layer) * tile_texels;
-    const float ua = ta.c.u * F.a_scale + F.a_offset, va = ta.c.v * F.a_scale + F.a_offset;  // attachment_uv
+    const Lookup la = lookup_sample_point<SPHERICAL>(F, T, tile_tree, atlas, tile, cu, cv, blend_lod);
     float height;
     Vec3 nrm = wn;
     if (normals) {
-        const FiveTaps taps = sample_five(F, layer_a, ua, va);
+        const FiveTaps taps = sample_five(F, la.layer, la.u, la.v);
         height = mix(F.min_h, F.max_h, taps.centre);
-        nrm = sample_normal<SPHERICAL>(F, layer_a, ta, ua, va, wn, &taps);
+        nrm = sample_normal<SPHERICAL>(F, la.layer, tile.side, la.dbs, la.u, la.v, wn, taps);
     } else {
-        height = sample_height_uv(F, layer_a, ua, va);
+        height = sample_height_uv(F, la.layer, la.u, la.v);
     }
     if (blend_ratio > 0.0f) {
-        const AtlasTile tb = lookup_tile(F, tile_tree, c, blend_lod - 1u);
-        const uint16_t* layer_b = atlas + (size_t)min(tb.index, F.last_layer) * tile_texels;
-        const float ub = tb.c.u * F.a_scale + F.a_offset, vb = tb.c.v * F.a_scale + F.a_offset;
+        const Lookup lb = lookup_sample_point<SPHERICAL>(F, T, tile_tree, atlas, tile, cu, cv, blend_lod - 1u);
         if (normals) {  // fragment.wgsl:103-107
-            const FiveTaps taps = sample_five(F, layer_b, ub, vb);
+            const FiveTaps taps = sample_five(F, lb.layer, lb.u, lb.v);
             height = mix(height, mix(F.min_h, F.max_h, taps.centre), blend_ratio);
-            const Vec3 n2 = sample_normal<SPHERICAL>(F, layer_b, tb, ub, vb, wn, &taps);
+            const Vec3 n2 = sample_normal<SPHERICAL>(F, lb.layer, tile.side, lb.dbs, lb.u, lb.v, wn, taps);
             nrm = Vec3{mix(nrm.x, n2.x, blend_ratio), mix(nrm.y, n2.y, blend_ratio), mix(nrm.z, n2.z, blend_ratio)};
         } else {
-            height = mix(height, sample_height_uv(F, layer_b, ub, vb), blend_ratio);
+            height = mix(height, sample_height_uv(F, lb.layer, lb.u, lb.v), blend_ratio);
         }
     }
     Record r;  // vertex_output — vertex.wgsl:73-83
@@ -374,16 +586,15 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     r.w[0] = make_float2(wp.x + hn.x, wp.y + hn.y);
     r.w[1] = make_float2(wp.z + height * wn.z, 1.0f);
     r.w[2] = make_float2(nrm.x, nrm.y);
-    r.w[3] = make_float2(nrm.z, c.u);
-    r.w[4] = make_float2(c.v, __uint_as_float(tile_index));
+    r.w[3] = make_float2(nrm.z, cu);
+    r.w[4] = make_float2(cv, __uint_as_float(tile_index));
     return r;
 }
 
-// Record k of a strip starts at 40*k bytes: 16-byte aligned for even k, 8 (mod 16) for odd k — the parity is static at every
-// call site, so each copy is two 128-bit stores and one 64-bit store.
+// One 40-byte record at dst (8-byte aligned): 16-byte aligned records take two 128-bit stores + one 64-bit store, the others
+// 64 + 128 + 128.  ODD is static at every call site.
 template <int ODD>
-__device__ __forceinline__ void store_record(unsigned char* image, uint32_t strip_stride, uint32_t strip, uint32_t k, const Record& r) {
-    unsigned char* dst = image + strip * strip_stride + k * (uint32_t)sizeof(bt_vertex);
+__device__ __forceinline__ void store_record_at(unsigned char* dst, const Record& r) {
     if (ODD) {
         *reinterpret_cast<float2*>(dst) = r.w[0];
         *reinterpret_cast<float4*>(dst + 8) = make_float4(r.w[1].x, r.w[1].y, r.w[2].x, r.w[2].y);
@@ -400,6 +611,7 @@ struct GenSmemHeader {
     uint64_t bar;                   // uniform-block TMA load
     uint64_t full[GEN_BUFFERS];     // image b completely written by the compute warps (count = compute warps)
     uint64_t empty[GEN_BUFFERS];    // image b completely read by the TMA stores (count = 1, the store warp)
+    uint64_t tab_ready[GEN_TABLE_SLOTS];   // tables of slot s written by the auxiliary warp (count = 1)
 };
 
 // Warp-specialised pipeline, one CTA per SM:
@@ -407,20 +619,23 @@ struct GenSmemHeader {
 //     on the steady-state path: a warp that has finished its chunks of item i arrives on full[b] and starts on its
 //     chunks of item i+1 in the other image, so the ragged last round of an item (1105 vertices = 34.5 warp-chunks) is
 //     filled with the next item's work
-//   * one store warp waits on full[b], issues the item's TMA bulk stores, waits until they have READ the image
-//     (cp.async.bulk.wait_group.read) and arrives on empty[b], which the compute warps wait on before reusing image b
-// FLAGS_CT >= 0: the flag word is a compile-time constant (the two common sets get their own instantiation, so the flag
+//   * one auxiliary warp builds the per-item tables (above) GEN_TABLE_LEAD items ahead and, per item, waits on full[b], issues the
+//     item's TMA bulk stores, waits until they have READ the image (cp.async.bulk.wait_group.read) and arrives on empty[b],
+//     which the compute warps wait on before reusing image b
+// FLAGS_CT >= 0: the flag word is a compile-time constant (the common sets get their own instantiation, so the flag
 // branches and the code of the disabled features disappear); FLAGS_CT < 0: generic kernel, flags read from the parameters.
 template <bool SPHERICAL, int FLAGS_CT>
 __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     GenSmemHeader& H = *reinterpret_cast<GenSmemHeader*>(smem_raw);
-    unsigned char* images = smem_raw + ((sizeof(GenSmemHeader) + 127) & ~size_t(127));
+    unsigned char* tables = smem_raw + ((sizeof(GenSmemHeader) + 127) & ~size_t(127));
+    unsigned char* images = tables + (size_t)GEN_TABLE_SLOTS * P.table_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&H.bar, 1);
         for (int b = 0; b < GEN_BUFFERS; ++b) { mbar_init(&H.full[b], GEN_COMPUTE_WARPS); mbar_init(&H.empty[b], 1); }
+        for (int s = 0; s < GEN_TABLE_SLOTS; ++s) mbar_init(&H.tab_ready[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -450,17 +665,37 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
     }
     const uint32_t n_items = n_tiles * P.items_per_tile;
 
+    const FrameConsts F = make_frame_consts<SPHERICAL>(U);
+
     if (warp == GEN_COMPUTE_WARPS) {
-        // ---------------- store warp ----------------
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        // ---------------- auxiliary warp: per-item tables (all lanes) + TMA stores (lane 0) ----------------
+        // Tables are built GEN_TABLE_LEAD items ahead.  Slot (it + LEAD) % SLOTS last held item it + LEAD - SLOTS <= it - 2, and this
+        // warp has already seen full[] of that item (every compute warp was done with it), so no extra hand-back barrier is needed.
+        auto build = [&](uint32_t w, uint32_t it) {
+            const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
+            const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
+            const uint32_t n_strips = min(P.strips_per_item, g - c0);
+            const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
+            const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
+            ItemTables& T = *reinterpret_cast<ItemTables*>(tables + (size_t)(it % GEN_TABLE_SLOTS) * P.table_bytes);
+            float4* rows = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&T) + sizeof(ItemTables));
+            build_item_tables<SPHERICAL>(U, F, P.tile_tree, T, rows, tile, c0, n_strips + 1u, g + 1u, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&H.tab_ready[it % GEN_TABLE_SLOTS]);
+        };
+        for (uint32_t k = 0; k < (uint32_t)GEN_TABLE_LEAD; ++k)
+            if (blockIdx.x + k * gridDim.x < n_items) build(blockIdx.x + k * gridDim.x, k);
+        uint32_t it = 0;
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+            const uint32_t w_ahead = w + (uint32_t)GEN_TABLE_LEAD * gridDim.x;
+            if (w_ahead < n_items) build(w_ahead, it + GEN_TABLE_LEAD);
+            if (lane == 0) {
                 const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
                 const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
                 const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
                 const uint32_t n_strips = min(P.strips_per_item, g - c0);
                 unsigned char* image = images + (size_t)b * P.image_bytes;
-                mbar_wait_parked(&H.full[b], use & 1u, 256u);   // every compute warp has written (and proxy-fenced) its records
+                mbar_wait_parked(&H.full[b], use & 1u, BT_GEN_FULL_SLEEP_NS);   // every compute warp has written (and proxy-fenced) its records
                 fence_proxy_async();
                 unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
                                      ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
@@ -470,50 +705,60 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
                 bulk_wait_read<0>();                      // the TMA has read the image: hand it back
                 mbar_arrive(&H.empty[b]);
             }
-            bulk_wait<0>();                               // all global writes complete before the CTA exits
+            __syncwarp();
         }
+        if (lane == 0) bulk_wait<0>();                    // all global writes complete before the CTA exits
         return;
     }
 
     // ---------------- compute warps ----------------
-    const FrameConsts F = make_frame_consts<SPHERICAL>(U);
     uint32_t it = 0, rot = 0;
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
+        const uint32_t ts = it % GEN_TABLE_SLOTS, tuse = it / GEN_TABLE_SLOTS;
         const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
         const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
         const uint32_t n_strips = min(P.strips_per_item, g - c0);
         const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
         unsigned char* image = images + (size_t)b * P.image_bytes;
-        if (use > 0u) mbar_wait_parked(&H.empty[b], (use - 1u) & 1u, 64u);   // the stores of the previous user of image b have read it
+        const ItemTables& T = *reinterpret_cast<const ItemTables*>(tables + (size_t)ts * P.table_bytes);
+        const float4* rows = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(&T) + sizeof(ItemTables));
+        mbar_wait_parked(&H.tab_ready[ts], tuse & 1u, 32u);                       // this item's tables are written
+        if (use > 0u) mbar_wait_parked(&H.empty[b], (use - 1u) & 1u, BT_GEN_EMPTY_SLEEP_NS);        // the stores of the previous user of image b have read it
 
-        const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
+        const uint4 tq = T.tile;
         const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
         const uint32_t n_verts = n_cols * n_rows;
         const uint32_t n_chunks = (n_verts + 31u) >> 5;
         // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32; the full-width magic comes from the host
         const uint32_t magic = n_strips == P.strips_per_item ? P.magic_cols : P.magic_cols_ragged;
-        // chunk c of this item goes to warp (c + rotation) mod GEN_COMPUTE_WARPS; the rotation spreads the ragged tail
         uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;   // chunk c of this item goes to warp (rot + c) mod GEN_COMPUTE_WARPS
         if (first >= GEN_COMPUTE_WARPS) first -= GEN_COMPUTE_WARPS;
         rot += GEN_ROTATION % GEN_COMPUTE_WARPS;                     // spreads the ragged tail (measured: DESIGN.md section 6)
         if (rot >= GEN_COMPUTE_WARPS) rot -= GEN_COMPUTE_WARPS;
         for (uint32_t c = first; c < n_chunks; c += GEN_COMPUTE_WARPS) {
-            const uint32_t i = (c << 5) + (uint32_t)lane;
-            if (i < n_verts) {
-                const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
-                const Record r = compute_vertex<SPHERICAL>(U, F, P.tile_tree, P.height_atlas, FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags, tile, tile_index, c0 + lx, gy);
-                // strip `lx`: this vertex is (column, row 2*gy) -> position 2*gy+1 (+ duplicated first index)
-                if (lx < n_strips) {
-                    store_record<1>(image, strip_stride, lx, 2u * gy + 1u, r);
-                    if (gy == 0u) store_record<0>(image, strip_stride, lx, 0u, r);
-                }
-                // strip `lx-1`: this vertex is (column+1, row 2*gy+1) -> position 2*gy+2 (+ duplicated last index)
-                if (lx >= 1u) {
-                    store_record<0>(image, strip_stride, lx - 1u, 2u * gy + 2u, r);
-                    if (gy == g) store_record<1>(image, strip_stride, lx - 1u, vpr - 1u, r);   // vpr = 2 * (g + 2) is even
-                }
-            }
+            // every lane computes a vertex (the lanes past the end of a ragged last chunk recompute the last one and store nothing),
+            // so the row tests below are full-warp votes
+            const uint32_t i_raw = (c << 5) + (uint32_t)lane;
+            const bool live = i_raw < n_verts;
+            const uint32_t i = live ? i_raw : n_verts - 1u;
+            const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
+#ifdef BT_GEN_SKIP_COMPUTE   // store-pipeline floor measurement only (tools/gen_probe.py): NOT the product path
+            Record r;
+            r.w[0] = make_float2((float)lx, (float)gy); r.w[1] = make_float2(0.0f, 1.0f); r.w[2] = r.w[0]; r.w[3] = r.w[1];
+            r.w[4] = make_float2(0.0f, __uint_as_float(tile_index));
+#else
+            const Record r = compute_vertex<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags, tile, tile_index, lx, gy);
+#endif
+            // strip `lx`: this vertex is (column, row 2*gy) -> record 2*gy+1; strip `lx-1`: it is (column+1, row 2*gy+1) -> record 2*gy+2
+            unsigned char* d1 = image + lx * strip_stride + (2u * gy + 1u) * (uint32_t)sizeof(bt_vertex);
+            unsigned char* d2 = d1 - strip_stride + (uint32_t)sizeof(bt_vertex);
+            const bool in1 = live && lx < n_strips, in2 = live && lx >= 1u;
+            if (in1) store_record_at<1>(d1, r);
+            if (in2) store_record_at<0>(d2, r);
+            // the duplicated first / last index of a strip (degenerate triangles): only warps that touch row 0 or row g
+            if (__any_sync(0xffffffffu, gy == 0u) && in1 && gy == 0u) store_record_at<0>(d1 - sizeof(bt_vertex), r);
+            if (__any_sync(0xffffffffu, gy == g) && in2 && gy == g) store_record_at<1>(d2 + sizeof(bt_vertex), r);   // record vpr - 1 (vpr is even)
         }
         fence_proxy_async();   // this lane's generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -532,9 +777,12 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     if (grid_size == 0) return cudaErrorInvalidValue;
     const uint32_t strip_stride = strip_stride_for(2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex));
     const size_t header = (sizeof(GenSmemHeader) + 127) & ~size_t(127);
-    const size_t budget = (200 * 1024) / GEN_CTAS_PER_SM - header - 1024;  // per CTA; leaves L1 some room out of the 227 KiB
+    const size_t table_bytes = (sizeof(ItemTables) + (size_t)(grid_size + 1u) * sizeof(float4) + 127) & ~size_t(127);
+    if (header + GEN_TABLE_SLOTS * table_bytes + 2048 > (size_t)208 * 1024) return cudaErrorInvalidValue;   // grid_size too large for the row tables
+    const size_t budget = (208 * 1024) / GEN_CTAS_PER_SM - header - GEN_TABLE_SLOTS * table_bytes - 1024;  // per CTA; leaves L1 some room out of the 227 KiB
     uint32_t cb = (uint32_t)(budget / ((size_t)GEN_BUFFERS * strip_stride));
-    if (cb > 16u) cb = 16u;
+    if (cb > (uint32_t)BT_GEN_MAX_CB) cb = BT_GEN_MAX_CB;
+    if (cb + 1u > (uint32_t)GEN_MAX_COLS) cb = GEN_MAX_COLS - 1u;
     if (cb > grid_size) cb = grid_size;
     if (cb == 0) return cudaErrorInvalidValue;  // grid_size too large for one strip per CTA
     GenParams P;
@@ -558,7 +806,8 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
         const uint32_t last_strips = grid_size - (P.items_per_tile - 1u) * cb;   // 1..cb
         P.magic_cols_ragged = 0xFFFFFFFFu / (last_strips + 1u) + 1u;
     }
-    const size_t smem = header + (size_t)GEN_BUFFERS * P.image_bytes;
+    P.table_bytes = (uint32_t)table_bytes;
+    const size_t smem = header + GEN_TABLE_SLOTS * table_bytes + (size_t)GEN_BUFFERS * P.image_bytes;
     // kernels specialised for the common flag sets (measured: 6 % faster than the generic kernel for NORMALS, 3 % for the
     // reference default + NORMALS); everything else (HIGH_PRECISION, partial sets) takes the generic one
     constexpr int kNone = 0, kNormals = BT_FLAG_NORMALS, kMorphBlend = BT_FLAG_MORPH | BT_FLAG_BLEND, kDefault = kMorphBlend | BT_FLAG_NORMALS;

@@ -40,11 +40,21 @@ def build() -> None:
     subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
 
 
+def _stale() -> bool:
+    """the built checker is older than its sources (an edit without `make -C oracle`): rebuild instead of testing stale code"""
+    try:
+        d = os.path.dirname(ORACLE_LIB)
+        built = os.path.getmtime(ORACLE_LIB)
+        return any(os.path.getmtime(os.path.join(d, f)) > built for f in os.listdir(d) if f.endswith((".c", ".h")))
+    except OSError:
+        return False
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(ORACLE_LIB):
+    if not os.path.exists(ORACLE_LIB) or _stale():
         build()
     L = C.CDLL(ORACLE_LIB)
     P, vp = C.POINTER, C.c_void_p
