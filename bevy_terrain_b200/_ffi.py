@@ -189,6 +189,9 @@ def _declare(lib: C.CDLL) -> None:
         "bt_view_update": (i32, [vp, P(ViewFrame), vp]),
         "bt_select_tiles": (i32, [vp, u32, vp]),
         "bt_gen_vertices": (i32, [vp, u32, vp, P(VertexBuffer)]),
+        "bt_view_batch_create": (i32, [P(vp), u32, P(vp)]),
+        "bt_view_batch_destroy": (None, [vp]),
+        "bt_select_tiles_batch": (i32, [vp, u32, vp]),
         "bt_view_run_frame": (i32, [vp, P(ViewFrame), u32, u32, vp, P(Tile), u32, P(u32), P(Indirect), P(VertexBuffer)]),
         "bt_view_readback": (i32, [vp, P(Tile), u32, P(u32), P(Indirect), vp]),
         "bt_view_select_status": (i32, [vp, P(u32), vp]),

@@ -445,6 +445,25 @@ class TileTree:
             self._tree = C.c_void_p()
 
 
+class ViewBatch:
+    """bt_view_batch: the views of one frame refined by ONE select_tiles launch (one CTA per view)."""
+
+    def __init__(self, trees):
+        self.trees = list(trees)
+        self.ctx = self.trees[0].ctx
+        arr = (C.c_void_p * len(self.trees))(*[t._view for t in self.trees])
+        self._h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.bt_view_batch_create(arr, len(self.trees), C.byref(self._h)))
+
+    def select_tiles(self, flags: int = 0, stream: int = 0) -> None:
+        self.ctx.check(self.ctx.lib.bt_select_tiles_batch(self._h, flags, C.c_void_p(stream)))
+
+    def close(self) -> None:
+        if self._h:
+            self.ctx.lib.bt_view_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def load_image(path: str) -> np.ndarray:
     """Decode a PNG / TIFF source image through the library (bt_image_load): (H, W) uint16 for 16-bit gray, (H, W, 4) uint8 for colour."""
     lib = F.load_library()

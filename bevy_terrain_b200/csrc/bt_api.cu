@@ -271,6 +271,10 @@ bt_status bt_atlas_device_ptr(bt_terrain* t, uint32_t attachment, void** out) {
 // ------------------------------------------------------------------------------------------------
 // view
 // ------------------------------------------------------------------------------------------------
+static btd::SelectViewParams select_params_of(const bt_view* v) {
+    return btd::SelectViewParams{v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->d_indirect, v->d_select_status, v->desc.geometry_tile_count, 0u};
+}
+
 bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out) {
     if (!t || !desc || !out) return BT_ERR_INVALID_ARG;
     bt_context* ctx = t->ctx;
@@ -293,11 +297,16 @@ bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out)
     alloc((void**)&v->d_indirect, sizeof(bt_indirect));
     alloc((void**)&v->d_select_status, sizeof(btd::SelectStatus));
     alloc((void**)&v->d_gen_status, sizeof(btd::GenStatus));
+    alloc((void**)&v->d_select_params, sizeof(btd::SelectViewParams));
     alloc((void**)&v->d_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
     if (e == cudaSuccess) e = cudaMemset(v->d_indirect, 0, sizeof(bt_indirect));
     if (e == cudaSuccess) e = cudaMemset(v->d_select_status, 0, sizeof(btd::SelectStatus));
     if (e == cudaSuccess) e = cudaMemset(v->d_gen_status, 0, sizeof(btd::GenStatus));
     if (e == cudaSuccess) e = cudaMemset(v->d_tile_tree, 0xFF, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+    if (e == cudaSuccess) {
+        const btd::SelectViewParams sp = select_params_of(v);
+        e = cudaMemcpy(v->d_select_params, &sp, sizeof(sp), cudaMemcpyHostToDevice);
+    }
     // pinned staging so bt_view_update is a pair of truly asynchronous copies
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_uniforms, sizeof(ViewUniforms), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaHostAllocDefault);
@@ -330,7 +339,7 @@ void bt_view_destroy(bt_view* v) {
     cudaSetDevice(v->terrain->ctx->device);
     cudaDeviceSynchronize();
     cudaFree(v->d_uniforms); cudaFree(v->d_final_tiles); cudaFree(v->d_temporary_tiles); cudaFree(v->d_indirect);
-    cudaFree(v->d_select_status); cudaFree(v->d_gen_status); cudaFree(v->d_tile_tree); cudaFree(v->d_vertices);
+    cudaFree(v->d_select_status); cudaFree(v->d_gen_status); cudaFree(v->d_tile_tree); cudaFree(v->d_vertices); cudaFree(v->d_select_params);
     if (v->h_uniforms) cudaFreeHost(v->h_uniforms);
     if (v->h_tile_tree) cudaFreeHost(v->h_tile_tree);
     if (v->h_readback) cudaFreeHost(v->h_readback);
@@ -400,8 +409,49 @@ bt_status bt_select_tiles(bt_view* v, uint32_t flags, void* stream) {
     bt_context* ctx = v->terrain->ctx;
     if (!v->updated) { ctx->set_error("bt_select_tiles: bt_view_update has not been called"); return BT_ERR_INVALID_ARG; }
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
-    BT_CUDA(ctx, bt_launch_select_tiles(v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->desc.geometry_tile_count, v->d_indirect,
-                                        v->d_select_status, v->terrain->desc.kind == BT_KIND_SPHERICAL, flags, (cudaStream_t)stream));
+    BT_CUDA(ctx, bt_launch_select_tiles(v->d_select_params, 1u, v->terrain->desc.kind == BT_KIND_SPHERICAL, flags, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+// ---- the views of one frame in ONE select launch (TilingPrepassNode::run iterates (terrain, view) pairs, tiling_prepass.rs:224-263) ----
+bt_status bt_view_batch_create(bt_view* const* views, uint32_t count, bt_view_batch** out) {
+    if (!views || !out || count == 0 || !views[0]) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = views[0]->terrain->ctx;
+    const int spherical = views[0]->terrain->desc.kind == BT_KIND_SPHERICAL;
+    std::vector<btd::SelectViewParams> params;
+    for (uint32_t i = 0; i < count; ++i) {
+        if (!views[i] || views[i]->terrain->ctx != ctx || (views[i]->terrain->desc.kind == BT_KIND_SPHERICAL) != spherical) {
+            ctx->set_error("bt_view_batch_create: the views of a batch must share one context and one terrain kind");
+            return BT_ERR_INVALID_ARG;
+        }
+        params.push_back(select_params_of(views[i]));
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    bt_view_batch* b = new bt_view_batch();
+    b->ctx = ctx;
+    b->spherical = spherical;
+    b->views.assign(views, views + count);
+    cudaError_t e = cudaMalloc((void**)&b->d_params, params.size() * sizeof(btd::SelectViewParams));
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_params, params.data(), params.size() * sizeof(btd::SelectViewParams), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(b->d_params); delete b; ctx->set_error("bt_view_batch_create: %s", cudaGetErrorString(e)); return BT_ERR_CUDA; }
+    *out = b;
+    return BT_OK;
+}
+
+void bt_view_batch_destroy(bt_view_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaFree(b->d_params);
+    delete b;
+}
+
+bt_status bt_select_tiles_batch(bt_view_batch* b, uint32_t flags, void* stream) {
+    if (!b) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = b->ctx;
+    for (bt_view* v : b->views)
+        if (!v->updated) { ctx->set_error("bt_select_tiles_batch: bt_view_update has not been called on every view"); return BT_ERR_INVALID_ARG; }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, bt_launch_select_tiles(b->d_params, (uint32_t)b->views.size(), b->spherical, flags, (cudaStream_t)stream));
     return BT_OK;
 }
 

@@ -16,6 +16,17 @@ struct SelectStatus {
     uint32_t overflow;         // 1 = a tile list exceeded its capacity (unchecked in the reference)
 };
 
+// device-resident launch record of one view for select_tiles_kernel (one CTA per entry)
+struct SelectViewParams {
+    const void* uniforms;      // ViewUniforms
+    bt_tile* final_tiles;
+    bt_tile* temporary_tiles;
+    bt_indirect* indirect;
+    SelectStatus* status;
+    uint32_t capacity;
+    uint32_t _pad;
+};
+
 struct GenStatus {
     uint32_t vertex_count_lo, vertex_count_hi;
     uint32_t overflow;         // vertex buffer too small for indirect.vertex_count
@@ -55,9 +66,8 @@ struct DatasetDevice {
 }  // namespace btd
 
 extern "C" {
-cudaError_t bt_launch_select_tiles(const void* uniforms, bt_tile* final_tiles, bt_tile* temporary_tiles,
-                                   uint32_t capacity, bt_indirect* indirect, btd::SelectStatus* status,
-                                   int spherical, uint32_t flags, cudaStream_t stream);
+cudaError_t bt_launch_select_tiles(const btd::SelectViewParams* device_views, uint32_t n_views, int spherical, uint32_t flags,
+                                   cudaStream_t stream);
 cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_tile* final_tiles, const bt_indirect* indirect,
                                    const bt_tile_tree_entry* tile_tree, const uint16_t* height_atlas,
                                    bt_vertex* vertices, uint64_t vertex_capacity, btd::GenStatus* status,

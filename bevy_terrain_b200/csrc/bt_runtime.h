@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/bevy_terrain_b200.h"
 #include "bt_kernels.h"
@@ -48,6 +49,7 @@ struct bt_view {
     bt_indirect* d_indirect = nullptr;
     btd::SelectStatus* d_select_status = nullptr;
     btd::GenStatus* d_gen_status = nullptr;
+    btd::SelectViewParams* d_select_params = nullptr;   // this view's launch record (a batch of one)
     bt_tile_tree_entry* d_tile_tree = nullptr;
     bt_vertex* d_vertices = nullptr;
     uint64_t vertex_capacity = 0;
@@ -62,6 +64,14 @@ struct bt_view {
     uint32_t h_tiles_cap = 0;
     size_t h2d_bytes_last_update = 0;
     bool updated = false;
+};
+
+// several views of one frame refined by ONE select_tiles launch (gridDim.x = views)
+struct bt_view_batch {
+    bt_context* ctx = nullptr;
+    std::vector<bt_view*> views;
+    btd::SelectViewParams* d_params = nullptr;
+    int spherical = 0;
 };
 
 extern "C" {

@@ -95,7 +95,8 @@ struct FrameConsts {
     float lod_cap;             // f32(lod_count) - 0.00001 (functions.wgsl:52)
     uint32_t tree_size, tree_mask, lod_count;  // tree_mask = tree_size - 1 when tree_size is a power of two, else 0
     uint32_t last_layer;       // atlas_size - 1: texture-array indices clamp to it
-    uint32_t morph_mant, blend_mant;   // mantissa thresholds of the certain-zero tests of the morph / blend ratio (ratio_is_certainly_zero)
+    uint32_t morph_mant, blend_mant;   // mantissa thresholds of the certain-zero tests of the morph / blend ratio (range_mantissa_threshold)
+    uint32_t blend_window, lod_max;    // 0x7fe000 - blend_mant (0 = shortcut disabled); u32(lod_cap)
 };
 
 // The morph and blend ratios are  inverse_mix(lod + range, lod, t) = saturate((t - (lod + range)) / (lod - (lod + range)))  with
@@ -144,6 +145,8 @@ __device__ __forceinline__ FrameConsts make_frame_consts(const ViewUniforms& U) 
     F.last_layer = U.atlas_size ? U.atlas_size - 1u : 0u;
     F.morph_mant = range_mantissa_threshold(U.view_config.morph_range);
     F.blend_mant = range_mantissa_threshold(U.view_config.blend_range);
+    F.blend_window = F.blend_mant == 0xFFFFFFFFu ? 0u : 0x007fe000u - F.blend_mant;
+    F.lod_max = f2u(F.lod_cap);
     return F;
 }
 
@@ -342,8 +345,7 @@ __device__ __forceinline__ Vec3 sample_normal(const FrameConsts& F, const uint16
 // Blend LODs above the tile's own LOD (a geometry tile coarser than the data it samples: lookups then differ
 // per vertex) and table entries with atlas_lod > lod take the generic per-vertex path.
 // ------------------------------------------------------------------------------------------------
-constexpr int GEN_TABLE_SLOTS = 4;      // tables of up to 4 items in flight
-constexpr int GEN_TABLE_LEAD = 2;       // the auxiliary warp builds them this many items ahead of the item whose image it stores
+constexpr int GEN_TABLE_SLOTS = 2 * GEN_BUFFERS;   // tables of up to 2 * GEN_BUFFERS items in flight
 constexpr int GEN_MAX_COLS = 32;        // strips per item + 1 <= 17
 constexpr uint32_t LODREC_SLOW = 0x80000000u;
 
@@ -358,6 +360,7 @@ struct alignas(16) ItemTables {
     float4 col[GEN_MAX_COLS];
     LodRecord lod[32];
     uint4 tile;                         // side, lod, x, y
+    uint4 meta;                         // tile_index, n_strips, magic (floor(i / n_cols) == umulhi(i, magic)), bits of morph_zero_from
     // float4 row[grid_size + 1] follows
 };
 
@@ -378,14 +381,23 @@ __device__ __forceinline__ float4 axis_terms(const ViewUniforms& U, const FrameC
     return make_float4(t, q, 0.0f, 0.0f);
 }
 
-// One item's tables, computed by the 32 lanes of the setup warp.
+// One item's tables, computed by GEN_BUILDER_LANES lanes (index `lane` = 0..30) of the auxiliary warp.
+constexpr uint32_t GEN_BUILDER_LANES = 31u;
 template <bool SPHERICAL>
 __device__ __forceinline__ void build_item_tables(const ViewUniforms& U, const FrameConsts& F, const bt_tile_tree_entry* __restrict__ tile_tree,
-                                                  ItemTables& T, float4* rows, const bt_tile& tile, uint32_t c0, uint32_t n_cols, uint32_t n_rows, int lane) {
+                                                  ItemTables& T, float4* rows, const bt_tile& tile, uint32_t tile_index, uint32_t magic,
+                                                  uint32_t c0, uint32_t n_cols, uint32_t n_rows, int lane) {
     const float inv_tc = exp2i(-(int)(tile.lod & 31u));
-    for (uint32_t lx = (uint32_t)lane; lx < n_cols; lx += 32u) T.col[lx] = axis_terms<SPHERICAL>(U, F, tile.x, inv_tc, c0 + lx, 0);
-    for (uint32_t gy = (uint32_t)lane; gy < n_rows; gy += 32u) rows[gy] = axis_terms<SPHERICAL>(U, F, tile.y, inv_tc, gy, 1);
-    if (lane == 0) T.tile = make_uint4(tile.side, tile.lod, tile.x, tile.y);
+    for (uint32_t lx = (uint32_t)lane; lx < n_cols; lx += GEN_BUILDER_LANES) T.col[lx] = axis_terms<SPHERICAL>(U, F, tile.x, inv_tc, c0 + lx, 0);
+    for (uint32_t gy = (uint32_t)lane; gy < n_rows; gy += GEN_BUILDER_LANES) rows[gy] = axis_terms<SPHERICAL>(U, F, tile.y, inv_tc, gy, 1);
+    if (lane == 0) {
+        T.tile = make_uint4(tile.side, tile.lod, tile.x, tile.y);
+        // compute_morph's ratio is exactly 0 for every x = 2 * morph_distance / d >= morph_zero_from (range_mantissa_threshold):
+        // the float with exponent tile.lod and mantissa bits morph_mant; LOD 0 never morphs (-inf); +inf disables the shortcut
+        const uint32_t zero_from = tile.lod == 0u ? 0xff800000u : (F.morph_mant == 0xFFFFFFFFu ? 0x7f800000u : (((127u + (tile.lod & 31u)) << 23) | F.morph_mant));
+        T.meta = make_uint4(tile_index, n_cols - 1u, magic, zero_from);
+        T.lod[31] = LodRecord{0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f, LODREC_SLOW};   // LOD 31 does not exist (lod_count <= 31): generic path
+    }
     const uint32_t L = (uint32_t)lane;
     LodRecord r{0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f, LODREC_SLOW};
     if (L < F.lod_count && L <= tile.lod) {
@@ -472,7 +484,7 @@ __device__ __forceinline__ uint32_t blend_lod_of(float x, float lod_cap) {
 template <bool SPHERICAL>
 __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const FrameConsts& F, const ItemTables& T, const float4* __restrict__ rows,
                                                  const bt_tile_tree_entry* __restrict__ tile_tree, const uint16_t* __restrict__ atlas,
-                                                 uint32_t flags, const bt_tile& tile, uint32_t tile_index, uint32_t lx, uint32_t gy) {
+                                                 uint32_t flags, const bt_tile& tile, uint32_t tile_index, float morph_zero_from, uint32_t lx, uint32_t gy) {
     const bt_view_config_uniform& vc = U.view_config;
     const bt_model_approximation& ap = U.approximation;
     const float g = F.g;
@@ -514,13 +526,9 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     bool morphed = false;    // false: the morph ratio is exactly 0, so mix(uv, even_uv, 0) == uv bit for bit and nothing moves
     if (flags & BT_FLAG_MORPH) {
         const float xm = div_rn(2.0f * vc.morph_distance, d);
-        int k;
-        uint32_t mant;
-        const bool zero = tile.lod == 0u || (split_normal(xm, k, mant) && (k > (int)tile.lod || (k == (int)tile.lod && mant >= F.morph_mant)) &&
-                                             F.morph_mant != 0xFFFFFFFFu);
-        if (!zero) {
+        if (!(xm >= morph_zero_from)) {      // (positive floats order like their (exponent, mantissa) pairs; +inf gives ratio 0 as well)
             const float target_lod = log2_det(xm);
-            const float ratio = inverse_mix_rn((float)tile.lod + vc.morph_range, (float)tile.lod, target_lod);
+            const float ratio = (tile.lod == 0u) ? 0.0f : inverse_mix_rn((float)tile.lod + vc.morph_range, (float)tile.lod, target_lod);
             const float even_u = F.g_pow2 ? (float)(f2u(u0 * g) & ~1u) * F.inv_g : (float)(f2u(u0 * g) & ~1u) / g;
             const float even_v = F.g_pow2 ? (float)(f2u(v0 * g) & ~1u) * F.inv_g : (float)(f2u(v0 * g) & ~1u) / g;
             cu = mix(u0, even_u, ratio);
@@ -542,14 +550,11 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
     float blend_ratio = 0.0f;
     const float blend_x = div_rn(vc.blend_distance, d);
     if (flags & BT_FLAG_BLEND) {
-        int k;
-        uint32_t mant;
-        const bool normal = split_normal(blend_x, k, mant);
-        const int lod_max = (int)f2u(F.lod_cap);
-        if (normal && k < 0) {
-            blend_lod = 0u;                        // log2 < 0: u32() clamps to 0, and LOD 0 never blends
-        } else if (normal && k <= lod_max && mant >= F.blend_mant && mant < 0x007fe000u) {
-            blend_lod = (uint32_t)k;               // floor is certain and the ratio is certainly 0 (see range_mantissa_threshold)
+        const uint32_t bits = __float_as_uint(blend_x), expo = bits >> 23;   // sign + exponent
+        if ((expo - 1u) < 126u) {
+            blend_lod = 0u;                        // positive normal below 1: log2 < 0, u32() clamps to 0, and LOD 0 never blends
+        } else if ((expo - 127u) <= F.lod_max && ((bits & 0x007fffffu) - F.blend_mant) < F.blend_window) {
+            blend_lod = expo - 127u;               // floor is certain and the ratio is certainly 0 (see range_mantissa_threshold)
         } else {
             const float target_lod = fminf(log2_det(blend_x), F.lod_cap);
             blend_lod = f2u(target_lod);
@@ -596,9 +601,10 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
 template <int ODD>
 __device__ __forceinline__ void store_record_at(unsigned char* dst, const Record& r) {
     if (ODD) {
-        *reinterpret_cast<float2*>(dst) = r.w[0];
-        *reinterpret_cast<float4*>(dst + 8) = make_float4(r.w[1].x, r.w[1].y, r.w[2].x, r.w[2].y);
-        *reinterpret_cast<float4*>(dst + 24) = make_float4(r.w[3].x, r.w[3].y, r.w[4].x, r.w[4].y);
+        // five 64-bit stores: the 128-bit form would need (w1,w2) and (w3,w4) in 4-aligned register quads while the even copy of the
+        // same record needs (w0,w1) and (w2,w3) there, i.e. eight register moves per vertex
+#pragma unroll
+        for (int k = 0; k < 5; ++k) *reinterpret_cast<float2*>(dst + 8 * k) = r.w[k];
     } else {
         *reinterpret_cast<float4*>(dst) = make_float4(r.w[0].x, r.w[0].y, r.w[1].x, r.w[1].y);
         *reinterpret_cast<float4*>(dst + 16) = make_float4(r.w[2].x, r.w[2].y, r.w[3].x, r.w[3].y);
@@ -668,29 +674,44 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
     const FrameConsts F = make_frame_consts<SPHERICAL>(U);
 
     if (warp == GEN_COMPUTE_WARPS) {
-        // ---------------- auxiliary warp: per-item tables (all lanes) + TMA stores (lane 0) ----------------
-        // Tables are built GEN_TABLE_LEAD items ahead.  Slot (it + LEAD) % SLOTS last held item it + LEAD - SLOTS <= it - 2, and this
-        // warp has already seen full[] of that item (every compute warp was done with it), so no extra hand-back barrier is needed.
-        auto build = [&](uint32_t w, uint32_t it) {
-            const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
-            const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
-            const uint32_t n_strips = min(P.strips_per_item, g - c0);
-            const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
-            const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
-            ItemTables& T = *reinterpret_cast<ItemTables*>(tables + (size_t)(it % GEN_TABLE_SLOTS) * P.table_bytes);
-            float4* rows = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&T) + sizeof(ItemTables));
-            build_item_tables<SPHERICAL>(U, F, P.tile_tree, T, rows, tile, c0, n_strips + 1u, g + 1u, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&H.tab_ready[it % GEN_TABLE_SLOTS]);
-        };
-        for (uint32_t k = 0; k < (uint32_t)GEN_TABLE_LEAD; ++k)
-            if (blockIdx.x + k * gridDim.x < n_items) build(blockIdx.x + k * gridDim.x, k);
-        uint32_t it = 0;
-        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-            const uint32_t w_ahead = w + (uint32_t)GEN_TABLE_LEAD * gridDim.x;
-            if (w_ahead < n_items) build(w_ahead, it + GEN_TABLE_LEAD);
-            if (lane == 0) {
-                const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
+        // ---------------- auxiliary warp: TMA stores (lane 0) and per-item tables (lanes 1-31), two independent loops ----------------
+        const uint32_t n_local = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+        if (lane != 0) {
+            // Builder lanes.  The tables of item `it` go to slot it % GEN_TABLE_SLOTS, which last held item it - 2 * GEN_BUFFERS; they are
+            // built as soon as full[] of item it - GEN_BUFFERS has completed (every compute warp is then past that item), i.e. before
+            // the image of item `it` can even be free.  (full[] of item it cannot complete before its tables exist: no parity aliasing.)
+            const int bl = lane - 1;
+            for (uint32_t it = 0; it < n_local; ++it) {
+                if (it >= (uint32_t)GEN_BUFFERS) mbar_wait_parked(&H.full[it % GEN_BUFFERS], ((it - GEN_BUFFERS) / GEN_BUFFERS) & 1u, 128u);
+                const uint32_t w = blockIdx.x + it * gridDim.x;
+                const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
+                const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
+                const uint32_t n_strips = min(P.strips_per_item, g - c0);
+                const uint4 tq = __ldg(reinterpret_cast<const uint4*>(P.tiles) + tile_index);
+                const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
+                ItemTables& T = *reinterpret_cast<ItemTables*>(tables + (size_t)(it % GEN_TABLE_SLOTS) * P.table_bytes);
+                float4* rows = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(&T) + sizeof(ItemTables));
+                build_item_tables<SPHERICAL>(U, F, P.tile_tree, T, rows, tile, tile_index, n_strips == P.strips_per_item ? P.magic_cols : P.magic_cols_ragged,
+                                             c0, n_strips + 1u, g + 1u, bl);
+                __syncwarp(0xFFFFFFFEu);
+                if (bl == 0) mbar_arrive(&H.tab_ready[it % GEN_TABLE_SLOTS]);
+            }
+            return;
+        }
+        // Store scheduling (lane 0), adaptive so that BOTH regimes run without bubbles:
+        //   * an image is handed back as soon as the TMA has read it (the compute warps may then start the item after next), and
+        //   * if the NEXT item's image is already full at that point in time, its stores are issued FIRST, so that two bulk groups are
+        //     in flight and the DRAM write stream never waits for the ~1 us TMA start-up of the following item.
+        // issued / released count this CTA's items; item k lives in image k % GEN_BUFFERS; at most GEN_BUFFERS groups are in flight.
+        uint32_t issued = 0, released = 0;
+        while (released < n_local) {
+            const uint32_t in_flight = issued - released;
+            bool can_issue = issued < n_local && in_flight < (uint32_t)GEN_BUFFERS;
+            if (can_issue && in_flight != 0u)       // something is draining: only issue the next item if its image is full NOW
+                can_issue = mbar_try_wait(&H.full[issued % GEN_BUFFERS], (issued / GEN_BUFFERS) & 1u);
+            if (can_issue) {
+                const uint32_t it = issued, b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
+                const uint32_t w = blockIdx.x + it * gridDim.x;
                 const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
                 const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
                 const uint32_t n_strips = min(P.strips_per_item, g - c0);
@@ -699,15 +720,21 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
                 fence_proxy_async();
                 unsigned char* out = reinterpret_cast<unsigned char*>(P.vertices) +
                                      ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(bt_vertex);
+#ifndef BT_GEN_SKIP_STORE   // (compute-only measurement variant of tools/gen_probe.py: NOT the product path)
                 for (uint32_t s = 0; s < n_strips; ++s)
                     bulk_store(out + (size_t)s * strip_bytes, image + (size_t)s * strip_stride, strip_bytes);
+#endif
                 bulk_commit();
-                bulk_wait_read<0>();                      // the TMA has read the image: hand it back
-                mbar_arrive(&H.empty[b]);
+                ++issued;
+            } else {
+                // the oldest group in flight: wait until the TMA has READ its image, then hand the image back
+                if (in_flight >= 3u) bulk_wait_read<2>(); else if (in_flight == 2u) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                static_assert(GEN_BUFFERS <= 3, "the wait_group.read immediates above cover three groups in flight");
+                mbar_arrive(&H.empty[released % GEN_BUFFERS]);
+                ++released;
             }
-            __syncwarp();
         }
-        if (lane == 0) bulk_wait<0>();                    // all global writes complete before the CTA exits
+        bulk_wait<0>();                                   // all global writes complete before the CTA exits
         return;
     }
 
@@ -716,22 +743,20 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const uint32_t b = it % GEN_BUFFERS, use = it / GEN_BUFFERS;
         const uint32_t ts = it % GEN_TABLE_SLOTS, tuse = it / GEN_TABLE_SLOTS;
-        const uint32_t tile_index = P.items_per_tile == 1u ? w : __umulhi(w, P.magic_items);
-        const uint32_t c0 = (w - tile_index * P.items_per_tile) * P.strips_per_item;
-        const uint32_t n_strips = min(P.strips_per_item, g - c0);
-        const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
         unsigned char* image = images + (size_t)b * P.image_bytes;
         const ItemTables& T = *reinterpret_cast<const ItemTables*>(tables + (size_t)ts * P.table_bytes);
         const float4* rows = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(&T) + sizeof(ItemTables));
         mbar_wait_parked(&H.tab_ready[ts], tuse & 1u, 32u);                       // this item's tables are written
         if (use > 0u) mbar_wait_parked(&H.empty[b], (use - 1u) & 1u, BT_GEN_EMPTY_SLEEP_NS);        // the stores of the previous user of image b have read it
 
-        const uint4 tq = T.tile;
+        // the item's scalars come from its tables (computed once by the builder lanes instead of by every compute warp)
+        const uint4 tq = T.tile, mq = T.meta;
         const bt_tile tile{tq.x, tq.y, tq.z, tq.w};
+        const uint32_t tile_index = mq.x, n_strips = mq.y, magic = mq.z;
+        const float morph_zero_from = __uint_as_float(mq.w);
+        const uint32_t n_cols = n_strips + 1u, n_rows = g + 1u;
         const uint32_t n_verts = n_cols * n_rows;
         const uint32_t n_chunks = (n_verts + 31u) >> 5;
-        // floor(i / n_cols) == umulhi(i, magic) for i * n_cols < 2^32; the full-width magic comes from the host
-        const uint32_t magic = n_strips == P.strips_per_item ? P.magic_cols : P.magic_cols_ragged;
         uint32_t first = (uint32_t)warp + GEN_COMPUTE_WARPS - rot;   // chunk c of this item goes to warp (rot + c) mod GEN_COMPUTE_WARPS
         if (first >= GEN_COMPUTE_WARPS) first -= GEN_COMPUTE_WARPS;
         rot += GEN_ROTATION % GEN_COMPUTE_WARPS;                     // spreads the ragged tail (measured: DESIGN.md section 6)
@@ -748,7 +773,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
             r.w[0] = make_float2((float)lx, (float)gy); r.w[1] = make_float2(0.0f, 1.0f); r.w[2] = r.w[0]; r.w[3] = r.w[1];
             r.w[4] = make_float2(0.0f, __uint_as_float(tile_index));
 #else
-            const Record r = compute_vertex<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags, tile, tile_index, lx, gy);
+            const Record r = compute_vertex<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags, tile, tile_index, morph_zero_from, lx, gy);
 #endif
             // strip `lx`: this vertex is (column, row 2*gy) -> record 2*gy+1; strip `lx-1`: it is (column+1, row 2*gy+1) -> record 2*gy+2
             unsigned char* d1 = image + lx * strip_stride + (2u * gy + 1u) * (uint32_t)sizeof(bt_vertex);
@@ -778,8 +803,11 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
     const uint32_t strip_stride = strip_stride_for(2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex));
     const size_t header = (sizeof(GenSmemHeader) + 127) & ~size_t(127);
     const size_t table_bytes = (sizeof(ItemTables) + (size_t)(grid_size + 1u) * sizeof(float4) + 127) & ~size_t(127);
-    if (header + GEN_TABLE_SLOTS * table_bytes + 2048 > (size_t)208 * 1024) return cudaErrorInvalidValue;   // grid_size too large for the row tables
-    const size_t budget = (208 * 1024) / GEN_CTAS_PER_SM - header - GEN_TABLE_SLOTS * table_bytes - 1024;  // per CTA; leaves L1 some room out of the 227 KiB
+#ifndef BT_GEN_SMEM_KB
+#define BT_GEN_SMEM_KB 208
+#endif
+    if (header + GEN_TABLE_SLOTS * table_bytes + 2048 > (size_t)BT_GEN_SMEM_KB * 1024) return cudaErrorInvalidValue;   // grid_size too large for the row tables
+    const size_t budget = ((size_t)BT_GEN_SMEM_KB * 1024) / GEN_CTAS_PER_SM - header - GEN_TABLE_SLOTS * table_bytes - 1024;  // per CTA; leaves L1 some room out of the 227 KiB
     uint32_t cb = (uint32_t)(budget / ((size_t)GEN_BUFFERS * strip_stride));
     if (cb > (uint32_t)BT_GEN_MAX_CB) cb = BT_GEN_MAX_CB;
     if (cb + 1u > (uint32_t)GEN_MAX_COLS) cb = GEN_MAX_COLS - 1u;

@@ -87,11 +87,18 @@ struct SelectSmem {
     bt_tile frontier[2][SELECT_SMEM_TILES];
 };
 
+// gridDim.x = number of views: CTA v refines view v (the views of a frame are independent; the reference loops over
+// (terrain, view) pairs on the host, tiling_prepass.rs:224-263, with 63 dispatches each)
 template <bool SPHERICAL>
 __global__ void __launch_bounds__(SELECT_THREADS, 1)
-select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restrict__ final_tiles,
-                    bt_tile* temporary_tiles, uint32_t capacity, bt_indirect* __restrict__ indirect,
-                    SelectStatus* __restrict__ status, uint32_t flags) {
+select_tiles_kernel(const SelectViewParams* __restrict__ views, uint32_t flags) {
+    const SelectViewParams V = views[blockIdx.x];
+    const ViewUniforms* __restrict__ uniforms = static_cast<const ViewUniforms*>(V.uniforms);
+    bt_tile* __restrict__ final_tiles = V.final_tiles;
+    bt_tile* temporary_tiles = V.temporary_tiles;
+    const uint32_t capacity = V.capacity;
+    bt_indirect* __restrict__ indirect = V.indirect;
+    SelectStatus* __restrict__ status = V.status;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SelectSmem& S = *reinterpret_cast<SelectSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -203,18 +210,15 @@ select_tiles_kernel(const ViewUniforms* __restrict__ uniforms, bt_tile* __restri
 
 }  // namespace btd
 
-extern "C" cudaError_t bt_launch_select_tiles(const void* uniforms, bt_tile* final_tiles, bt_tile* temporary_tiles,
-                                              uint32_t capacity, bt_indirect* indirect, btd::SelectStatus* status,
-                                              int spherical, uint32_t flags, cudaStream_t stream) {
+extern "C" cudaError_t bt_launch_select_tiles(const btd::SelectViewParams* device_views, uint32_t n_views, int spherical, uint32_t flags,
+                                              cudaStream_t stream) {
     using namespace btd;
+    if (n_views == 0) return cudaSuccess;
     const size_t smem = sizeof(SelectSmem);
     cudaError_t e = cudaFuncSetAttribute(spherical ? select_tiles_kernel<true> : select_tiles_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const ViewUniforms* u = static_cast<const ViewUniforms*>(uniforms);
-    if (spherical)
-        select_tiles_kernel<true><<<1, SELECT_THREADS, smem, stream>>>(u, final_tiles, temporary_tiles, capacity, indirect, status, flags);
-    else
-        select_tiles_kernel<false><<<1, SELECT_THREADS, smem, stream>>>(u, final_tiles, temporary_tiles, capacity, indirect, status, flags);
+    if (spherical) select_tiles_kernel<true><<<n_views, SELECT_THREADS, smem, stream>>>(device_views, flags);
+    else select_tiles_kernel<false><<<n_views, SELECT_THREADS, smem, stream>>>(device_views, flags);
     return cudaGetLastError();
 }

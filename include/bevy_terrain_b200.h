@@ -273,6 +273,14 @@ bt_status bt_view_update(bt_view* view, const bt_view_frame* frame, void* stream
  * Output order is the order a sequential execution of the reference shaders would produce.    */
 bt_status bt_select_tiles(bt_view* view, uint32_t flags, void* stream);
 
+/* The views of one frame in ONE launch (gridDim.x = views): TilingPrepassNode::run loops over (terrain, view) pairs on the
+ * host (tiling_prepass.rs:224-263, 63 dispatches each); here every view gets its own CTA of the same kernel, so N views cost
+ * the latency of one.  The views must share a context and a terrain kind; results are exactly those of N bt_select_tiles calls. */
+typedef struct bt_view_batch bt_view_batch;
+bt_status bt_view_batch_create(bt_view* const* views, uint32_t count, bt_view_batch** out);
+void      bt_view_batch_destroy(bt_view_batch* batch);      /* before the views it references */
+bt_status bt_select_tiles_batch(bt_view_batch* batch, uint32_t flags, void* stream);
+
 /* Replaces the vertex stage of the indirect draw (DrawTerrainCommand,
  * terrain_view_bind_group.rs:274-298; vertex.wgsl:85-98) by writing the strip-ordered vertex
  * stream (indirect.vertex_count records) to a device buffer.                                  */

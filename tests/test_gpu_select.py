@@ -99,3 +99,35 @@ def test_select_spills_to_global_frontier(ctx):
     assert res.max_frontier > 4096
     assert status == F.BT_OK
     assert np.array_equal(tiles, exp_tiles)
+
+
+@pytest.mark.parametrize("kind", ["planar", "spherical"])
+def test_select_batch_equals_per_view_and_oracle(ctx, kind):
+    """bt_select_tiles_batch: the views of a frame in ONE launch (one CTA per view) give exactly the per-view results, in order"""
+    from bevy_terrain_b200 import api
+    scene = Scene(kind, lod_count=3 if kind == "spherical" else 4, T=16, B=2, src=32, grid_size=16)
+    positions = (spherical_view_positions() if kind == "spherical" else planar_view_positions(6))[:6]
+    atlas = api.TileAtlas(ctx, scene.terrain_config())
+    trees = [api.TileTree(atlas, scene.cfg) for _ in positions]
+    batch = None
+    try:
+        for tree, pos in zip(trees, positions):
+            scene.move_view(pos)
+            tree.prepare(frame=scene.view_frame())
+        batch = api.ViewBatch(trees)
+        batch.select_tiles()
+        for tree, pos in zip(trees, positions):
+            scene.move_view(pos)
+            exp_tiles, exp_ind, res = scene.oracle_select()
+            tiles, ind = tree.readback()
+            assert np.array_equal(tiles, exp_tiles), f"batched tile list differs at view {pos}"
+            assert ind.vertex_count == exp_ind.vertex_count and tree.select_status() == res.dropped_parents
+            tree.select_tiles()                         # the single-view launch of the same kernel
+            again, _ = tree.readback()
+            assert np.array_equal(again, tiles)
+    finally:
+        if batch:
+            batch.close()
+        for tree in trees:
+            tree.close()
+        atlas.close()
