@@ -207,7 +207,23 @@ __device__ __forceinline__ float lerp2(float v00, float v01, float v10, float v1
     return a + (b - a) * rx;
 }
 
-__device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
+// The five taps in three steps, so that the caller can put the loads of TWO vertices in flight before consuming either
+// (the kernel is latency-bound at 5 warps per scheduler: two independent vertices per lane double the work each warp can issue
+// while its texel loads are outstanding):
+//   prepare_taps : tap coordinates, weights, which-texel selectors, and whether the whole plus lies inside the texture
+//   load_taps    : the 12 raw texels (interior: one base address, +-T row pointers, immediate column offsets; else clamped)
+//   finish_taps  : decode + the five bilinear results
+struct TapSetup {
+    const uint16_t* layer;
+    float rxc, ryc, rxl, rxr, ryu, ryd;
+    int ix, iy;
+    bool jl, jr, ju, jd;      // left / right / up / down tap starts one texel further (offsets of ~0.5 texel: 0 or 1)
+    bool ok;                  // the selectors are all 0 / 1 (always, for offsets < 1 texel; guarded anyway)
+    bool interior;
+};
+struct TapTexels { uint32_t r10, r11, r12, r13, r20, r21, r22, r23, r01, r02, r31, r32; };   // raw texel r<row><col>
+
+__device__ __forceinline__ TapSetup prepare_taps(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
     const float o = F.normal_offset;
     // tap coordinates: (centre x, centre y), (left x, right x), (up y, down y) as packed pairs; each product is followed by a
     // scalar "- 0.5" (same two roundings per value as sample_r16)
@@ -216,44 +232,65 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
     const float2 plr = __fmul2_rn(__fadd2_rn(make_float2(u, u), make_float2(-o, o)), Tf2);
     const float2 pud = __fmul2_rn(__fadd2_rn(make_float2(v, v), make_float2(-o, o)), Tf2);
     const float pxc = pc.x - 0.5f, pyc = pc.y - 0.5f, pxl = plr.x - 0.5f, pxr = plr.y - 0.5f, pyu = pud.x - 0.5f, pyd = pud.y - 0.5f;
-    const float fxc = floorf(pxc), fyc = floorf(pyc), fxl = floorf(pxl), fxr = floorf(pxr), fyu = floorf(pyu), fyd = floorf(pyd);
+    // texel coordinates are far inside floor_small's range (|p| < 2^22): floors and the two integer indices without FRND / F2I
+    const FloorInt fcx = floor_small(pxc), fcy = floor_small(pyc);
+    const float fxc = fcx.f, fyc = fcy.f, fxl = floor_small_f(pxl), fxr = floor_small_f(pxr), fyu = floor_small_f(pyu), fyd = floor_small_f(pyd);
     const float2 rc = __fadd2_rn(make_float2(pxc, pyc), make_float2(-fxc, -fyc));
     const float2 rlr = __fadd2_rn(make_float2(pxl, pxr), make_float2(-fxl, -fxr));
     const float2 rud = __fadd2_rn(make_float2(pyu, pyd), make_float2(-fyu, -fyd));
-    const float rxc = rc.x, ryc = rc.y, rxl = rlr.x, rxr = rlr.y, ryu = rud.x, ryd = rud.y;
-    const int ix = (int)fxc, iy = (int)fyc;
-    const uint32_t jl = (uint32_t)((int)fxl - ix + 1), jr = (uint32_t)((int)fxr - ix);  // expected jl in {0,1}, jr in {0,1}
-    const uint32_t ju = (uint32_t)((int)fyu - iy + 1), jd = (uint32_t)((int)fyd - iy);
+    TapSetup s;
+    s.layer = layer;
+    s.rxc = rc.x; s.ryc = rc.y; s.rxl = rlr.x; s.rxr = rlr.y; s.ryu = rud.x; s.ryd = rud.y;
+    s.ix = fcx.i;
+    s.iy = fcy.i;
+    // the floors are integers in float form: the selectors come from float compares (no float->int conversions on the XU pipe)
+    s.jl = fxl == fxc;             // (int)fxl - ix + 1 == 1
+    s.jr = fxr != fxc;             // (int)fxr - ix == 1
+    s.ju = fyu == fyc;
+    s.jd = fyd != fyc;
+    s.ok = (s.jl || fxl == fxc - 1.0f) && (!s.jr || fxr == fxc + 1.0f) && (s.ju || fyu == fyc - 1.0f) && (!s.jd || fyd == fyc + 1.0f);
+    s.interior = (uint32_t)(s.ix - 1) < F.interior && (uint32_t)(s.iy - 1) < F.interior;
+    return s;
+}
+
+__device__ __forceinline__ TapTexels load_taps_interior(const FrameConsts& F, const TapSetup& s) {
+    // the whole plus lies inside the texture (always the case for uv inside a tile with border_size >= 2)
+    const uint16_t* p1 = s.layer + (s.iy * F.T + s.ix);
+    const uint16_t* p0 = p1 - F.T;
+    const uint16_t* p2 = p1 + F.T;
+    const uint16_t* p3 = p2 + F.T;
+    TapTexels t;
+    t.r10 = __ldg(p1 - 1); t.r11 = __ldg(p1); t.r12 = __ldg(p1 + 1); t.r13 = __ldg(p1 + 2);
+    t.r20 = __ldg(p2 - 1); t.r21 = __ldg(p2); t.r22 = __ldg(p2 + 1); t.r23 = __ldg(p2 + 2);
+    t.r01 = __ldg(p0); t.r02 = __ldg(p0 + 1);
+    t.r31 = __ldg(p3); t.r32 = __ldg(p3 + 1);
+    return t;
+}
+
+__device__ __forceinline__ TapTexels load_taps_clamped(const FrameConsts& F, const TapSetup& s) {
+    const int ix = s.ix, iy = s.iy;
+    const int c0 = min(max(ix - 1, 0), F.Tm1), c1 = min(max(ix, 0), F.Tm1), c2 = min(max(ix + 1, 0), F.Tm1), c3 = min(max(ix + 2, 0), F.Tm1);
+    const uint16_t* q0 = s.layer + min(max(iy - 1, 0), F.Tm1) * F.T;
+    const uint16_t* q1 = s.layer + min(max(iy, 0), F.Tm1) * F.T;
+    const uint16_t* q2 = s.layer + min(max(iy + 1, 0), F.Tm1) * F.T;
+    const uint16_t* q3 = s.layer + min(max(iy + 2, 0), F.Tm1) * F.T;
+    TapTexels t;
+    t.r10 = __ldg(q1 + c0); t.r11 = __ldg(q1 + c1); t.r12 = __ldg(q1 + c2); t.r13 = __ldg(q1 + c3);
+    t.r20 = __ldg(q2 + c0); t.r21 = __ldg(q2 + c1); t.r22 = __ldg(q2 + c2); t.r23 = __ldg(q2 + c3);
+    t.r01 = __ldg(q0 + c1); t.r02 = __ldg(q0 + c2);
+    t.r31 = __ldg(q3 + c1); t.r32 = __ldg(q3 + c2);
+    return t;
+}
+
+__device__ __forceinline__ FiveTaps finish_taps(const TapSetup& s, const TapTexels& t) {
     FiveTaps out;
-    out.ok = (jl | jr | ju | jd) <= 1u;   // offsets of 0.5/size texture units = ~0.5 texel: always true; guarded anyway
-    // raw texel r<row><col>
-    uint32_t r10, r11, r12, r13, r20, r21, r22, r23, r01, r02, r31, r32;
-    if ((uint32_t)(ix - 1) < F.interior && (uint32_t)(iy - 1) < F.interior) {
-        // the whole plus lies inside the texture (always the case for uv inside a tile with border_size >= 2):
-        // one base address, row pointers by +-T, column offsets as immediates; no clamping
-        const uint16_t* p1 = layer + (iy * F.T + ix);
-        const uint16_t* p0 = p1 - F.T;
-        const uint16_t* p2 = p1 + F.T;
-        const uint16_t* p3 = p2 + F.T;
-        r10 = __ldg(p1 - 1); r11 = __ldg(p1); r12 = __ldg(p1 + 1); r13 = __ldg(p1 + 2);
-        r20 = __ldg(p2 - 1); r21 = __ldg(p2); r22 = __ldg(p2 + 1); r23 = __ldg(p2 + 2);
-        r01 = __ldg(p0); r02 = __ldg(p0 + 1);
-        r31 = __ldg(p3); r32 = __ldg(p3 + 1);
-    } else {
-        const int c0 = min(max(ix - 1, 0), F.Tm1), c1 = min(max(ix, 0), F.Tm1), c2 = min(max(ix + 1, 0), F.Tm1), c3 = min(max(ix + 2, 0), F.Tm1);
-        const uint16_t* q0 = layer + min(max(iy - 1, 0), F.Tm1) * F.T;
-        const uint16_t* q1 = layer + min(max(iy, 0), F.Tm1) * F.T;
-        const uint16_t* q2 = layer + min(max(iy + 1, 0), F.Tm1) * F.T;
-        const uint16_t* q3 = layer + min(max(iy + 2, 0), F.Tm1) * F.T;
-        r10 = __ldg(q1 + c0); r11 = __ldg(q1 + c1); r12 = __ldg(q1 + c2); r13 = __ldg(q1 + c3);
-        r20 = __ldg(q2 + c0); r21 = __ldg(q2 + c1); r22 = __ldg(q2 + c2); r23 = __ldg(q2 + c3);
-        r01 = __ldg(q0 + c1); r02 = __ldg(q0 + c2);
-        r31 = __ldg(q3 + c1); r32 = __ldg(q3 + c2);
-    }
+    out.ok = s.ok;
+    const float rxc = s.rxc, ryc = s.ryc, rxl = s.rxl, rxr = s.rxr, ryu = s.ryu, ryd = s.ryd;
+    const bool jl = s.jl, jr = s.jr, ju = s.ju, jd = s.jd;
     // decode in pairs of adjacent columns of one row — the layout the packed y-lerps consume without re-pairing
-    const float2 A01 = unorm16x2_to_float(r10, r11), A23 = unorm16x2_to_float(r12, r13);   // row 1: (t10, t11), (t12, t13)
-    const float2 B01 = unorm16x2_to_float(r20, r21), B23 = unorm16x2_to_float(r22, r23);   // row 2
-    const float2 E0 = unorm16x2_to_float(r01, r02), E3 = unorm16x2_to_float(r31, r32);     // rows 0 and 3: columns 1, 2
+    const float2 A01 = unorm16x2_to_float(t.r10, t.r11), A23 = unorm16x2_to_float(t.r12, t.r13);   // row 1: (t10, t11), (t12, t13)
+    const float2 B01 = unorm16x2_to_float(t.r20, t.r21), B23 = unorm16x2_to_float(t.r22, t.r23);   // row 2
+    const float2 E0 = unorm16x2_to_float(t.r01, t.r02), E3 = unorm16x2_to_float(t.r31, t.r32);     // rows 0 and 3: columns 1, 2
     // y-lerps of rows (1, 2) with the centre's ry:  L<col> = t1c + (t2c - t1c) * ryc  — lerp2's `a` / `b` for centre, left, right.
     // Packed: difference and product for two columns per instruction; the final additions stay scalar (a packed mul feeding a
     // packed add would be contracted into FFMA2 by ptxas, which the numerics contract forbids).
@@ -284,6 +321,12 @@ __device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint
         out.down = da + m.y;
     }
     return out;
+}
+
+__device__ __forceinline__ FiveTaps sample_five(const FrameConsts& F, const uint16_t* __restrict__ layer, float u, float v) {
+    const TapSetup s = prepare_taps(F, layer, u, v);
+    const TapTexels t = s.interior ? load_taps_interior(F, s) : load_taps_clamped(F, s);
+    return finish_taps(s, t);
 }
 
 // sample_normal — attachments.wgsl:51-107 (textureSampleLevel branch); `pre` carries the shared taps, `distance_between_samples`
@@ -480,11 +523,23 @@ __device__ __forceinline__ uint32_t blend_lod_of(float x, float lod_cap) {
     return f2u(fminf(log2_det(x), lod_cap));
 }
 
-// vertex_info + vertex + vertex_output — vertex.wgsl:30-98
+// vertex_info + vertex + vertex_output — vertex.wgsl:30-98, in two halves around the texel loads of the first sample:
+//   vertex_front : vertex_info (position, distance, morph, blend) + lookup_tile + the tap coordinates of the first sample
+//   vertex_back  : the samples' arithmetic, the blend with the LOD below, vertex_output
+// so that the compute loop can run the fronts of two vertices, issue both sets of texel loads, and only then consume them.
+struct Front {
+    Vec3 wp, wn;
+    float cu, cv;
+    uint32_t blend_lod;
+    float blend_ratio;
+    Lookup la;
+    TapSetup taps;     // NORMALS only
+};
+
 template <bool SPHERICAL>
-__device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const FrameConsts& F, const ItemTables& T, const float4* __restrict__ rows,
-                                                 const bt_tile_tree_entry* __restrict__ tile_tree, const uint16_t* __restrict__ atlas,
-                                                 uint32_t flags, const bt_tile& tile, uint32_t tile_index, float morph_zero_from, uint32_t lx, uint32_t gy) {
+__device__ __forceinline__ Front vertex_front(const ViewUniforms& U, const FrameConsts& F, const ItemTables& T, const float4* __restrict__ rows,
+                                              const bt_tile_tree_entry* __restrict__ tile_tree, const uint16_t* __restrict__ atlas,
+                                              uint32_t flags, const bt_tile& tile, float morph_zero_from, uint32_t lx, uint32_t gy) {
     const bt_view_config_uniform& vc = U.view_config;
     const bt_model_approximation& ap = U.approximation;
     const float g = F.g;
@@ -564,19 +619,32 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
         blend_lod = blend_lod_of(blend_x, F.lod_cap);   // only the integer part is consumed
     }
 
+    Front f;
+    f.wp = wp; f.wn = wn; f.cu = cu; f.cv = cv; f.blend_lod = blend_lod; f.blend_ratio = blend_ratio;
+    f.la = lookup_sample_point<SPHERICAL>(F, T, tile_tree, atlas, tile, cu, cv, blend_lod);
+    if (flags & BT_FLAG_NORMALS) f.taps = prepare_taps(F, f.la.layer, f.la.u, f.la.v);
+    return f;
+}
+
+template <bool SPHERICAL>
+__device__ __forceinline__ Record vertex_back(const FrameConsts& F, const ItemTables& T, const bt_tile_tree_entry* __restrict__ tile_tree,
+                                              const uint16_t* __restrict__ atlas, uint32_t flags, const bt_tile& tile, uint32_t tile_index,
+                                              const Front& f, const TapTexels* texels) {
     const bool normals = (flags & BT_FLAG_NORMALS) != 0u;
-    const Lookup la = lookup_sample_point<SPHERICAL>(F, T, tile_tree, atlas, tile, cu, cv, blend_lod);
+    const Vec3 wp = f.wp, wn = f.wn;
+    const float cu = f.cu, cv = f.cv, blend_ratio = f.blend_ratio;
+    const Lookup& la = f.la;
     float height;
     Vec3 nrm = wn;
     if (normals) {
-        const FiveTaps taps = sample_five(F, la.layer, la.u, la.v);
+        const FiveTaps taps = finish_taps(f.taps, *texels);
         height = mix(F.min_h, F.max_h, taps.centre);
         nrm = sample_normal<SPHERICAL>(F, la.layer, tile.side, la.dbs, la.u, la.v, wn, taps);
     } else {
         height = sample_height_uv(F, la.layer, la.u, la.v);
     }
     if (blend_ratio > 0.0f) {
-        const Lookup lb = lookup_sample_point<SPHERICAL>(F, T, tile_tree, atlas, tile, cu, cv, blend_lod - 1u);
+        const Lookup lb = lookup_sample_point<SPHERICAL>(F, T, tile_tree, atlas, tile, cu, cv, f.blend_lod - 1u);
         if (normals) {  // fragment.wgsl:103-107
             const FiveTaps taps = sample_five(F, lb.layer, lb.u, lb.v);
             height = mix(height, mix(F.min_h, F.max_h, taps.centre), blend_ratio);
@@ -601,10 +669,11 @@ __device__ __forceinline__ Record compute_vertex(const ViewUniforms& U, const Fr
 template <int ODD>
 __device__ __forceinline__ void store_record_at(unsigned char* dst, const Record& r) {
     if (ODD) {
-        // five 64-bit stores: the 128-bit form would need (w1,w2) and (w3,w4) in 4-aligned register quads while the even copy of the
-        // same record needs (w0,w1) and (w2,w3) there, i.e. eight register moves per vertex
-#pragma unroll
-        for (int k = 0; k < 5; ++k) *reinterpret_cast<float2*>(dst + 8 * k) = r.w[k];
+        // (five 64-bit stores would save the register moves that the two quad layouts of one record cost, but 64-bit stores are 2-way
+        //  bank-conflicted at the image's strip stride: measured slower)
+        *reinterpret_cast<float2*>(dst) = r.w[0];
+        *reinterpret_cast<float4*>(dst + 8) = make_float4(r.w[1].x, r.w[1].y, r.w[2].x, r.w[2].y);
+        *reinterpret_cast<float4*>(dst + 24) = make_float4(r.w[3].x, r.w[3].y, r.w[4].x, r.w[4].y);
     } else {
         *reinterpret_cast<float4*>(dst) = make_float4(r.w[0].x, r.w[0].y, r.w[1].x, r.w[1].y);
         *reinterpret_cast<float4*>(dst + 16) = make_float4(r.w[2].x, r.w[2].y, r.w[3].x, r.w[3].y);
@@ -761,30 +830,73 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
         if (first >= GEN_COMPUTE_WARPS) first -= GEN_COMPUTE_WARPS;
         rot += GEN_ROTATION % GEN_COMPUTE_WARPS;                     // spreads the ragged tail (measured: DESIGN.md section 6)
         if (rot >= GEN_COMPUTE_WARPS) rot -= GEN_COMPUTE_WARPS;
-        for (uint32_t c = first; c < n_chunks; c += GEN_COMPUTE_WARPS) {
-            // every lane computes a vertex (the lanes past the end of a ragged last chunk recompute the last one and store nothing),
-            // so the row tests below are full-warp votes
-            const uint32_t i_raw = (c << 5) + (uint32_t)lane;
-            const bool live = i_raw < n_verts;
-            const uint32_t i = live ? i_raw : n_verts - 1u;
-            const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
-#ifdef BT_GEN_SKIP_COMPUTE   // store-pipeline floor measurement only (tools/gen_probe.py): NOT the product path
-            Record r;
-            r.w[0] = make_float2((float)lx, (float)gy); r.w[1] = make_float2(0.0f, 1.0f); r.w[2] = r.w[0]; r.w[3] = r.w[1];
-            r.w[4] = make_float2(0.0f, __uint_as_float(tile_index));
-#else
-            const Record r = compute_vertex<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags, tile, tile_index, morph_zero_from, lx, gy);
-#endif
-            // strip `lx`: this vertex is (column, row 2*gy) -> record 2*gy+1; strip `lx-1`: it is (column+1, row 2*gy+1) -> record 2*gy+2
+        const uint32_t flags = FLAGS_CT >= 0 ? (uint32_t)FLAGS_CT : P.flags;
+        // scatter of one computed vertex: strip `lx` holds it as (column, row 2*gy) -> record 2*gy+1, strip `lx-1` as (column+1,
+        // row 2*gy+1) -> record 2*gy+2; the duplicated first / last index of a strip (degenerate triangles) only concerns warps that
+        // touch row 0 or row g (full-warp votes: every lane computes, lanes past the end of a ragged chunk store nothing)
+        auto scatter = [&](const Record& r, uint32_t lx, uint32_t gy, bool live) {
             unsigned char* d1 = image + lx * strip_stride + (2u * gy + 1u) * (uint32_t)sizeof(bt_vertex);
             unsigned char* d2 = d1 - strip_stride + (uint32_t)sizeof(bt_vertex);
             const bool in1 = live && lx < n_strips, in2 = live && lx >= 1u;
             if (in1) store_record_at<1>(d1, r);
             if (in2) store_record_at<0>(d2, r);
-            // the duplicated first / last index of a strip (degenerate triangles): only warps that touch row 0 or row g
             if (__any_sync(0xffffffffu, gy == 0u) && in1 && gy == 0u) store_record_at<0>(d1 - sizeof(bt_vertex), r);
             if (__any_sync(0xffffffffu, gy == g) && in2 && gy == g) store_record_at<1>(d2 + sizeof(bt_vertex), r);   // record vpr - 1 (vpr is even)
+        };
+#if defined(BT_GEN_SKIP_COMPUTE)   // store-pipeline floor measurement only (tools/gen_probe.py): NOT the product path
+        for (uint32_t c = first; c < n_chunks; c += GEN_COMPUTE_WARPS) {
+            const uint32_t i_raw = (c << 5) + (uint32_t)lane;
+            const bool live = i_raw < n_verts;
+            const uint32_t i = live ? i_raw : n_verts - 1u;
+            const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;
+            Record r;
+            r.w[0] = make_float2((float)lx, (float)gy); r.w[1] = make_float2(0.0f, 1.0f); r.w[2] = r.w[0]; r.w[3] = r.w[1];
+            r.w[4] = make_float2(0.0f, __uint_as_float(tile_index));
+            scatter(r, lx, gy, live);
         }
+#else
+        uint32_t c = first;
+#if defined(BT_GEN_PAIRS)   // (experiment, off: measured no faster for NORMALS and slower, through spills, with MORPH + BLEND)
+        // TWO chunks per iteration (a warp owns chunks first, first + NW, ...: usually exactly two per item): both fronts, then both
+        // sets of texel loads, then the backs — two independent vertices per lane in flight (the kernel is latency-bound)
+        if ((flags & BT_FLAG_NORMALS) != 0u) {
+            for (; c + GEN_COMPUTE_WARPS < n_chunks; c += 2u * GEN_COMPUTE_WARPS) {
+                const uint32_t ia = (c << 5) + (uint32_t)lane;                       // chunk c is never the ragged last one here
+                const uint32_t ib_raw = ((c + GEN_COMPUTE_WARPS) << 5) + (uint32_t)lane;
+                const bool live_b = ib_raw < n_verts;
+                const uint32_t ib = live_b ? ib_raw : n_verts - 1u;
+                const uint32_t gya = __umulhi(ia, magic), lxa = ia - gya * n_cols;
+                const uint32_t gyb = __umulhi(ib, magic), lxb = ib - gyb * n_cols;
+                const Front fa = vertex_front<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, flags, tile, morph_zero_from, lxa, gya);
+                const Front fb = vertex_front<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, flags, tile, morph_zero_from, lxb, gyb);
+                TapTexels ta, tb;
+                if (__all_sync(0xffffffffu, fa.taps.interior && fb.taps.interior)) {
+                    ta = load_taps_interior(F, fa.taps);
+                    tb = load_taps_interior(F, fb.taps);
+                } else {
+                    ta = fa.taps.interior ? load_taps_interior(F, fa.taps) : load_taps_clamped(F, fa.taps);
+                    tb = fb.taps.interior ? load_taps_interior(F, fb.taps) : load_taps_clamped(F, fb.taps);
+                }
+                const Record ra = vertex_back<SPHERICAL>(F, T, P.tile_tree, P.height_atlas, flags, tile, tile_index, fa, &ta);
+                scatter(ra, lxa, gya, true);
+                const Record rb = vertex_back<SPHERICAL>(F, T, P.tile_tree, P.height_atlas, flags, tile, tile_index, fb, &tb);
+                scatter(rb, lxb, gyb, live_b);
+            }
+        }
+#endif
+        for (; c < n_chunks; c += GEN_COMPUTE_WARPS) {
+            // every lane computes a vertex (the lanes past the end of a ragged last chunk recompute the last one and store nothing)
+            const uint32_t i_raw = (c << 5) + (uint32_t)lane;
+            const bool live = i_raw < n_verts;
+            const uint32_t i = live ? i_raw : n_verts - 1u;
+            const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
+            const Front f = vertex_front<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, flags, tile, morph_zero_from, lx, gy);
+            TapTexels t;
+            if (flags & BT_FLAG_NORMALS) t = f.taps.interior ? load_taps_interior(F, f.taps) : load_taps_clamped(F, f.taps);
+            const Record r = vertex_back<SPHERICAL>(F, T, P.tile_tree, P.height_atlas, flags, tile, tile_index, f, &t);
+            scatter(r, lx, gy, live);
+        }
+#endif
         fence_proxy_async();   // this lane's generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&H.full[b]);

@@ -459,6 +459,7 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
     if (i < 65536u) {
         volatile float m16 = 65535.0f, m8 = 255.0f;   // volatile: keep the reference form a true IEEE division
         if (unorm16_to_float(i) != (float)i / m16) atomicAdd(&mismatches[0], 1u);
+        if (u23_to_float(i) != (float)i || u23_to_float(i * 127u + 1u) != (float)(i * 127u + 1u)) atomicAdd(&mismatches[0], 1u);   // XU-free u32 -> f32 (i * 127 + 1 < 2^23)
         const float2 p16 = unorm16x2_to_float(i, 65535u - i);    // packed (FMUL2 / FFMA2) decode, both halves
         if (p16.x != (float)i / m16 || p16.y != (float)(65535u - i) / m16) atomicAdd(&mismatches[0], 1u);
         if (i < 256u) {
@@ -498,6 +499,18 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
                 const float l3 = length3(Vec3{fa, fb, fc});
                 volatile float ss = __fadd_rn(__fadd_rn(__fmul_rn(fa, fa), __fmul_rn(fb, fb)), __fmul_rn(fc, fc));
                 if (ss >= 1.17549435e-38f && l3 != sqrtf(ss)) atomicAdd(&mismatches[3], 1u);
+            }
+        }
+        // XU-free floor: floor_small against floorf / (int)floorf on values spread over (-2^22, 2^22), incl. exact integers and x[] itself
+        {
+            const float probes[4] = {(float)((int)(i % 4194301u) - 2097150) * 1.9999f, (float)((int)(i % 8191u) - 4096), fmodf(a, 4194000.0f), (float)(i % 1021u) * 0.5f - 255.25f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float q = probes[k];
+                if (fabsf(q) < 4194303.0f) {
+                    const FloorInt fi = floor_small(q);
+                    if (fi.f != floorf(q) || fi.i != (int)floorf(q) || floor_small_f(q) != floorf(q)) atomicAdd(&mismatches[3], 1u);
+                }
             }
         }
         // round-down pack (FADD.RM with 2^23) against floor(0.5 + M * clamp(v, 0, 1)), v spread over [-0.25, 1.25]
