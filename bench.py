@@ -79,13 +79,18 @@ def host_threads() -> int:
     return _HOST_THREADS
 
 
-def pin_openmp_env():
-    """must run before anything loads libgomp (torch, the oracle): thread count = the cores this process may run on,
-    threads bound to hardware threads (close) so that the CPU arm is reproducible from box to box"""
+def pin_openmp_env(bind: bool):
+    """must run before anything loads libgomp (torch, the oracle): thread count = the cores this process may run on; with `bind`
+    the threads are bound to hardware threads (close) so that the CPU arm is reproducible from box to box.  Ranks of a multi-GPU
+    run must NOT bind: every rank's initial thread would land on the same first place and the ranks would share one core."""
     n = host_threads()
     os.environ["OMP_NUM_THREADS"] = str(n)
-    os.environ["OMP_PROC_BIND"] = "close"
-    os.environ["OMP_PLACES"] = "threads"
+    if bind:
+        os.environ["OMP_PROC_BIND"] = "close"
+        os.environ["OMP_PLACES"] = "threads"
+    else:
+        os.environ["OMP_PROC_BIND"] = "false"
+        os.environ.pop("OMP_PLACES", None)
     return n
 
 
@@ -853,7 +858,8 @@ def emit(obj):
 def main():
     global _REAL_STDOUT
     args = parse_args()
-    pin_openmp_env()   # before torch / the oracle load libgomp
+    # before torch / the oracle load libgomp; only a process that is alone on the box (the CPU arm, or the 1-GPU arm with its cpu_baseline) binds
+    pin_openmp_env(bind=args.impl == "reference" or int(os.environ.get("WORLD_SIZE", "1")) == 1)
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)   # anything a library prints to fd 1 from here on lands on stderr

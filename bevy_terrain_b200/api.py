@@ -272,6 +272,15 @@ class TileAtlas:
         self.ctx.check(self.ctx.lib.bt_atlas_device_ptr(self._h, attachment, C.byref(p)))
         return p.value
 
+    def generate_mips(self, attachment: int, atlas_index: int, stream: int = 0) -> None:
+        """AttachmentData::generate_mipmaps at tile load (tile_atlas.rs:141), on the GPU"""
+        self.ctx.check(self.ctx.lib.bt_atlas_generate_mips(self._h, attachment, atlas_index, C.c_void_p(stream)))
+
+    def mips_device_ptr(self, attachment: int):
+        p, n = C.c_void_p(), C.c_size_t()
+        self.ctx.check(self.ctx.lib.bt_atlas_mips_device_ptr(self._h, attachment, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     def close(self) -> None:
         if self._state:
             self.ctx.lib.bt_atlas_state_destroy(self._state)
@@ -434,6 +443,12 @@ class TileTree:
     def download_vertices(self, first: int, count: int, stream: int = 0) -> np.ndarray:
         out = np.empty(count, dtype=VERTEX_DTYPE)
         self.ctx.check(self.ctx.lib.bt_view_download_vertices(self._view, out.ctypes.data, first, count, C.c_void_p(stream)))
+        return out
+
+    def download_albedo(self, first: int, count: int, stream: int = 0) -> np.ndarray:
+        """the per-vertex pack4x8unorm colours of the last gen_vertices(BT_FLAG_ALBEDO)"""
+        out = np.empty(count, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.bt_view_download_albedo(self._view, out.ctypes.data, first, count, C.c_void_p(stream)))
         return out
 
     def close(self) -> None:
@@ -662,6 +677,8 @@ def load_resident_tiles(tile_tree: TileTree, preprocessor: Preprocessor, view_wo
     for tile, atlas_index in loads:
         for a in attachments:
             tile_tree.atlas.copy_tile(a, atlas_index, preprocessor.tile_device_ptr(a, tile), stream)
+            if tile_tree.atlas.attachments[a].mip_level_count > 1:
+                tile_tree.atlas.generate_mips(a, atlas_index, stream)     # the CPU mip generation at tile load, on the GPU
         tile_tree.mark_loaded(tile)
     tile_tree.adjust_to_tile_atlas()
     return len(loads)

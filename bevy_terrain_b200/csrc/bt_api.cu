@@ -104,15 +104,57 @@ bt_status bt_terrain_create(bt_context* ctx, const bt_terrain_desc* desc, bt_ter
             bt_terrain_destroy(t);
             return e == cudaErrorMemoryAllocation ? BT_ERR_OUT_OF_MEMORY : BT_ERR_CUDA;
         }
+        // mip levels 1.. of every slot (AttachmentData::generate_mipmaps appends them after mip 0, terrain_data/mod.rs:143-219):
+        // filled by bt_atlas_generate_mips, consumed by BT_FLAG_FILTER_TRILINEAR_ANISO
+        uint32_t chain = 0;
+        for (uint32_t level = 1; level < a.mip_level_count; ++level) chain += (a.texture_size >> level) * (a.texture_size >> level);
+        t->mip_chain_texels[i] = chain;
+        t->mip_chain_bytes[i] = (size_t)chain * px;
+        if (chain) {
+            e = cudaMalloc(&t->atlas_mips[i], t->mip_chain_bytes[i] * desc->atlas_size);
+            if (e == cudaSuccess) e = cudaMemset(t->atlas_mips[i], 0, t->mip_chain_bytes[i] * desc->atlas_size);
+            if (e != cudaSuccess) { ctx->set_error("bt_terrain_create: mip allocation failed: %s", cudaGetErrorString(e)); bt_terrain_destroy(t); return BT_ERR_OUT_OF_MEMORY; }
+        }
+    }
+    {   // the sRGB EOTF table (IEC 61966-2-1), computed in double and rounded once: the same formula as the oracle's
+        float lut[256];
+        for (int i = 0; i < 256; ++i) {
+            const double c = (double)i / 255.0;
+            lut[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+        }
+        cudaError_t e = cudaMalloc((void**)&t->d_srgb_lut, sizeof(lut));
+        if (e == cudaSuccess) e = cudaMemcpy(t->d_srgb_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { ctx->set_error("bt_terrain_create: %s", cudaGetErrorString(e)); bt_terrain_destroy(t); return BT_ERR_CUDA; }
     }
     *out = t;
+    return BT_OK;
+}
+
+// GPU replacement of the CPU mip generation at tile load (tile_atlas.rs:141 -> AttachmentData::generate_mipmaps): levels 1.. of
+// one atlas slot from its mip 0, same integer rules (R16: mean of the non-zero texels; Rgba8: sum / 4)
+bt_status bt_atlas_generate_mips(bt_terrain* t, uint32_t attachment, uint32_t atlas_index, void* stream) {
+    if (!t || attachment >= t->desc.attachment_count || atlas_index >= t->desc.atlas_size) return BT_ERR_INVALID_ARG;
+    if (!t->atlas_mips[attachment]) return BT_OK;     // mip_level_count == 1
+    const bt_attachment_config& a = t->desc.attachments[attachment];
+    BT_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
+    BT_CUDA(t->ctx, bt_launch_mipmaps(a.format, a.texture_size, a.mip_level_count,
+                                      static_cast<const unsigned char*>(t->atlas[attachment]) + t->tile_bytes[attachment] * atlas_index,
+                                      static_cast<unsigned char*>(t->atlas_mips[attachment]) + t->mip_chain_bytes[attachment] * atlas_index, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_atlas_mips_device_ptr(bt_terrain* t, uint32_t attachment, void** out, size_t* chain_bytes_per_slot) {
+    if (!t || !out || attachment >= t->desc.attachment_count) return BT_ERR_INVALID_ARG;
+    *out = t->atlas_mips[attachment];
+    if (chain_bytes_per_slot) *chain_bytes_per_slot = t->mip_chain_bytes[attachment];
     return BT_OK;
 }
 
 void bt_terrain_destroy(bt_terrain* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
-    for (int i = 0; i < 8; ++i) if (t->atlas[i]) cudaFree(t->atlas[i]);
+    for (int i = 0; i < 8; ++i) { if (t->atlas[i]) cudaFree(t->atlas[i]); if (t->atlas_mips[i]) cudaFree(t->atlas_mips[i]); }
+    cudaFree(t->d_srgb_lut);
     if (t->h_stage) cudaFreeHost(t->h_stage);
     if (t->stage_free) cudaEventDestroy(t->stage_free);
     delete t;
@@ -340,6 +382,7 @@ void bt_view_destroy(bt_view* v) {
     cudaDeviceSynchronize();
     cudaFree(v->d_uniforms); cudaFree(v->d_final_tiles); cudaFree(v->d_temporary_tiles); cudaFree(v->d_indirect);
     cudaFree(v->d_select_status); cudaFree(v->d_gen_status); cudaFree(v->d_tile_tree); cudaFree(v->d_vertices); cudaFree(v->d_select_params);
+    cudaFree(v->d_albedo);
     if (v->h_uniforms) cudaFreeHost(v->h_uniforms);
     if (v->h_tile_tree) cudaFreeHost(v->h_tile_tree);
     if (v->h_readback) cudaFreeHost(v->h_readback);
@@ -476,10 +519,45 @@ bt_status bt_gen_vertices(bt_view* v, uint32_t flags, void* stream, bt_vertex_bu
             v->vertex_capacity = ind.vertex_count;
         }
     }
+    btd::GenFilterInputs filter{};
+    const btd::GenFilterInputs* filter_ptr = nullptr;
+    if (flags & (BT_FLAG_FILTER_TRILINEAR_ANISO | BT_FLAG_ALBEDO)) {
+        bt_terrain* t = v->terrain;
+        const uint32_t aa = 1u;   // the albedo attachment of the reference's examples (planar.rs:64-70): attachment 1, Rgba8
+        if (flags & BT_FLAG_ALBEDO) {
+            if (t->desc.attachment_count <= aa || t->desc.attachments[aa].format != BT_FORMAT_RGBA8 ||
+                t->desc.attachments[aa].texture_size != t->desc.attachments[0].texture_size) {
+                ctx->set_error("bt_gen_vertices: BT_FLAG_ALBEDO needs attachment 1 = Rgba8 with the height attachment's texture size");
+                return BT_ERR_INVALID_ARG;
+            }
+            if (v->albedo_capacity < v->vertex_capacity) {   // one-time growth on the first ALBEDO frame (like the grow-on-demand vertex buffer)
+                if (v->d_albedo) BT_CUDA(ctx, cudaFree(v->d_albedo));
+                v->d_albedo = nullptr;
+                v->albedo_capacity = 0;
+                cudaError_t e = cudaMalloc((void**)&v->d_albedo, (size_t)v->vertex_capacity * sizeof(uint32_t));
+                if (e != cudaSuccess) { ctx->set_error("bt_gen_vertices: albedo stream allocation failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return BT_ERR_OUT_OF_MEMORY; }
+                v->albedo_capacity = v->vertex_capacity;
+            }
+        }
+        if ((flags & BT_FLAG_FILTER_TRILINEAR_ANISO) && t->desc.attachments[0].mip_level_count > 1 && (flags & BT_FLAG_ALBEDO) &&
+            t->desc.attachments[aa].mip_level_count != t->desc.attachments[0].mip_level_count) {
+            ctx->set_error("bt_gen_vertices: the height and albedo attachments must have the same mip_level_count for the filtered sampler");
+            return BT_ERR_INVALID_ARG;
+        }
+        filter.height_mips = static_cast<const uint16_t*>(t->atlas_mips[0]);
+        filter.albedo_atlas = (flags & BT_FLAG_ALBEDO) ? t->atlas[aa] : nullptr;
+        filter.albedo_mips = (flags & BT_FLAG_ALBEDO) ? t->atlas_mips[aa] : nullptr;
+        filter.srgb_lut = t->d_srgb_lut;
+        filter.albedo_out = v->d_albedo;
+        filter.mip_level_count = t->desc.attachments[0].mip_level_count ? t->desc.attachments[0].mip_level_count : 1u;
+        filter.mip_chain_texels = t->mip_chain_texels[0];
+        filter.albedo_attachment = aa;
+        filter_ptr = &filter;
+    }
     BT_CUDA(ctx, bt_launch_gen_vertices(v->d_uniforms, v->d_final_tiles, v->d_indirect, v->d_tile_tree,
                                         static_cast<const uint16_t*>(v->terrain->atlas[0]), v->d_vertices, v->vertex_capacity,
                                         v->d_gen_status, v->terrain->desc.kind == BT_KIND_SPHERICAL, flags, v->desc.grid_size,
-                                        ctx->sm_count, s));
+                                        ctx->sm_count, filter_ptr, s));
     if (out) { out->vertices = v->d_vertices; out->capacity = v->vertex_capacity; }
     return BT_OK;
 }
@@ -569,6 +647,24 @@ bt_status bt_view_download_vertices(bt_view* v, bt_vertex* out, uint64_t first, 
     if (count) BT_CUDA(ctx, cudaMemcpyAsync(out, v->d_vertices + first, count * sizeof(bt_vertex), cudaMemcpyDeviceToHost, s));
     BT_CUDA(ctx, cudaStreamSynchronize(s));
     if (gs.overflow) { ctx->set_error("gen_vertices: vertex buffer (%llu vertices) too small", (unsigned long long)v->vertex_capacity); return BT_ERR_CAPACITY; }
+    return BT_OK;
+}
+
+// the per-vertex albedo stream of the last bt_gen_vertices with BT_FLAG_ALBEDO (device pointer, strip order, pack4x8unorm)
+bt_status bt_view_albedo_buffer(bt_view* v, uint32_t** device_albedo, uint64_t* capacity) {
+    if (!v || !device_albedo) return BT_ERR_INVALID_ARG;
+    *device_albedo = v->d_albedo;
+    if (capacity) *capacity = v->albedo_capacity;
+    return BT_OK;
+}
+
+bt_status bt_view_download_albedo(bt_view* v, uint32_t* out, uint64_t first, uint64_t count, void* stream) {
+    if (!v || !out) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = v->terrain->ctx;
+    if (!v->d_albedo || first + count > v->albedo_capacity) { ctx->set_error("bt_view_download_albedo: no albedo stream, or the range exceeds it"); return BT_ERR_INVALID_ARG; }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count) BT_CUDA(ctx, cudaMemcpyAsync(out, v->d_albedo + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    BT_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     return BT_OK;
 }
 

@@ -54,6 +54,16 @@ struct RowCopy {
     uint64_t bytes;   // multiple of 2
 };
 
+// extra inputs of gen_vertices for BT_FLAG_FILTER_TRILINEAR_ANISO / BT_FLAG_ALBEDO (all device pointers)
+struct GenFilterInputs {
+    const uint16_t* height_mips;
+    const void* albedo_atlas;
+    const void* albedo_mips;
+    const float* srgb_lut;
+    uint32_t* albedo_out;
+    uint32_t mip_level_count, mip_chain_texels, albedo_attachment, _pad;
+};
+
 struct TileHashTask { uint64_t key; uint32_t slot, _pad; };   // key = hash of (attachment-independent) tile coordinate
 
 struct DatasetDevice {
@@ -71,5 +81,6 @@ cudaError_t bt_launch_select_tiles(const btd::SelectViewParams* device_views, ui
 cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_tile* final_tiles, const bt_indirect* indirect,
                                    const bt_tile_tree_entry* tile_tree, const uint16_t* height_atlas,
                                    bt_vertex* vertices, uint64_t vertex_capacity, btd::GenStatus* status,
-                                   int spherical, uint32_t flags, uint32_t grid_size, int sm_count, cudaStream_t stream);
+                                   int spherical, uint32_t flags, uint32_t grid_size, int sm_count, const btd::GenFilterInputs* filter,
+                                   cudaStream_t stream);
 }

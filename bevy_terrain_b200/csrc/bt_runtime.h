@@ -34,6 +34,10 @@ struct bt_terrain {
     bt_terrain_desc desc{};
     void* atlas[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t tile_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* atlas_mips[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // levels 1.. of every slot (generate_mipmaps layout)
+    size_t mip_chain_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t mip_chain_texels[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float* d_srgb_lut = nullptr;    // 256 floats: the sRGB EOTF (Rgba8UnormSrgb decodes per texel before filtering)
     void* h_stage = nullptr;        // pinned staging for file loads
     size_t h_stage_bytes = 0;
     cudaEvent_t stage_free = nullptr;
@@ -53,6 +57,8 @@ struct bt_view {
     bt_tile_tree_entry* d_tile_tree = nullptr;
     bt_vertex* d_vertices = nullptr;
     uint64_t vertex_capacity = 0;
+    uint32_t* d_albedo = nullptr;   // per-vertex pack4x8unorm albedo stream (BT_FLAG_ALBEDO), same capacity as d_vertices
+    uint64_t albedo_capacity = 0;
     void* h_uniforms = nullptr;
     void* h_tile_tree = nullptr;
     void* h_readback = nullptr;

@@ -72,6 +72,15 @@ struct GenParams {
     uint32_t magic_cols;       // ceil(2^32 / (CB + 1)) for full-width items
     uint32_t magic_cols_ragged;  // the same for the narrower last item of a tile (g % CB strips), if any
     uint32_t table_bytes;      // one slot of per-item tables: sizeof(ItemTables) + (g + 1) row entries, 128-byte multiple
+    // configs[2] sampler + per-vertex albedo (BT_FLAG_FILTER_TRILINEAR_ANISO / BT_FLAG_ALBEDO; generic kernel only)
+    const uint16_t* height_mips;   // [atlas][chain]: levels 1.. of every atlas slot (generate_mipmaps layout), or nullptr
+    const uchar4* albedo_atlas;    // [atlas][T][T]
+    const uchar4* albedo_mips;
+    const float* srgb_lut;         // 256 entries: the sRGB EOTF, decoded per texel before filtering
+    uint32_t* albedo_out;          // strip-ordered pack4x8unorm colours, one per vertex
+    uint32_t mip_level_count, mip_chain_texels, albedo_attachment;
+    uint32_t albedo_image_bytes;   // per buffer: strips_per_item * albedo_stride (0 without BT_FLAG_ALBEDO)
+    uint32_t albedo_stride;        // vertices_per_row * 4
 };
 
 struct Record {  // one bt_vertex as five 8-byte words
@@ -681,6 +690,171 @@ __device__ __forceinline__ void store_record_at(unsigned char* dst, const Record
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// BASELINE configs[2]: the reference's sampler (linear / linear / linear, anisotropy clamp 16 — terrain_bind_group.rs:120-126;
+// textureSampleGrad in attachments.wgsl:16-20) evaluated per vertex with the footprint of one grid step, and the per-vertex
+// albedo.  Same operations in the same order as the oracle's sample_filtered / gen_vertex_filtered.
+// Generic kernel only (FLAGS_CT < 0): an opt-in variant, not the headline path.
+// ------------------------------------------------------------------------------------------------
+struct FilterCtx {
+    const void* mip0;
+    const void* mips;
+    const float* lut;      // non-null: Rgba8 texels (sRGB rgb through the table, alpha / 255)
+    uint32_t T, mip_level_count;
+    bool trilinear;
+};
+
+__device__ __forceinline__ uint32_t mip_offset_texels(uint32_t T, uint32_t level) {
+    uint32_t off = 0;
+    for (uint32_t j = 1; j < level; ++j) off += (T >> j) * (T >> j);
+    return off;
+}
+
+template <bool RGBA>
+__device__ __forceinline__ void bilinear_level(const void* __restrict__ texels, const float* __restrict__ lut, uint32_t size, float u, float v, float (&out)[4]) {
+    const float px = u * (float)size - 0.5f, py = v * (float)size - 0.5f;
+    const float fx = floorf(px), fy = floorf(py);
+    const float rx = px - fx, ry = py - fy;
+    const int ix = (int)fx, iy = (int)fy, m = (int)size - 1;
+    const int x0 = min(max(ix, 0), m), x1 = min(max(ix + 1, 0), m), y0 = min(max(iy, 0), m), y1 = min(max(iy + 1, 0), m);
+    if (!RGBA) {
+        const uint16_t* t = static_cast<const uint16_t*>(texels);
+        const float v00 = (float)__ldg(t + y0 * size + x0) / 65535.0f, v01 = (float)__ldg(t + y1 * size + x0) / 65535.0f;
+        const float v10 = (float)__ldg(t + y0 * size + x1) / 65535.0f, v11 = (float)__ldg(t + y1 * size + x1) / 65535.0f;
+        const float l0 = v00 + (v01 - v00) * ry, l1 = v10 + (v11 - v10) * ry;
+        out[0] = l0 + (l1 - l0) * rx;
+    } else {
+        const uchar4* t = static_cast<const uchar4*>(texels);
+        const uchar4 q00 = __ldg(t + y0 * size + x0), q01 = __ldg(t + y1 * size + x0), q10 = __ldg(t + y0 * size + x1), q11 = __ldg(t + y1 * size + x1);
+        const unsigned char c00[4] = {q00.x, q00.y, q00.z, q00.w}, c01[4] = {q01.x, q01.y, q01.z, q01.w};
+        const unsigned char c10[4] = {q10.x, q10.y, q10.z, q10.w}, c11[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v00 = c < 3 ? __ldg(lut + c00[c]) : (float)c00[c] / 255.0f, v01 = c < 3 ? __ldg(lut + c01[c]) : (float)c01[c] / 255.0f;
+            const float v10 = c < 3 ? __ldg(lut + c10[c]) : (float)c10[c] / 255.0f, v11 = c < 3 ? __ldg(lut + c11[c]) : (float)c11[c] / 255.0f;
+            const float l0 = v00 + (v01 - v00) * ry, l1 = v10 + (v11 - v10) * ry;
+            out[c] = l0 + (l1 - l0) * rx;
+        }
+    }
+}
+
+template <bool RGBA>
+__device__ __noinline__ void sample_filtered(const FilterCtx& fc, float u, float v, float step_u, float step_v, float (&out)[4]) {
+    constexpr int NCH = RGBA ? 4 : 1;
+    if (!fc.trilinear) { bilinear_level<RGBA>(fc.mip0, fc.lut, fc.T, u, v, out); return; }
+    const float Px = step_u * (float)fc.T, Py = step_v * (float)fc.T;
+    const float Pmax = fmaxf(Px, Py), Pmin = fminf(Px, Py);
+    const float ratio = ceilf(Pmax / Pmin);
+    const uint32_t N = (ratio >= 16.0f) ? 16u : (ratio >= 1.0f ? (uint32_t)ratio : 1u);   // NaN (0 / 0) -> 1
+    const float lambda = log2_det(Pmax / (float)N);
+    const float d = fminf(fmaxf(lambda, 0.0f), (float)(fc.mip_level_count - 1u));
+    const uint32_t lo = (uint32_t)floorf(d), hi = lo + 1u < fc.mip_level_count ? lo + 1u : lo;
+    const float w = d - (float)lo;
+    const bool x_major = Px >= Py;
+    constexpr uint32_t PX = RGBA ? 4u : 2u;
+    const unsigned char* base = static_cast<const unsigned char*>(fc.mips);
+    const void* lo_texels = lo == 0u ? fc.mip0 : static_cast<const void*>(base + (size_t)mip_offset_texels(fc.T, lo) * PX);
+    const void* hi_texels = base + (size_t)mip_offset_texels(fc.T, hi) * PX;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (uint32_t i = 0; i < N; ++i) {
+        const float t = ((float)i + 0.5f) / (float)N - 0.5f;
+        const float uu = x_major ? u + t * step_u : u, vv = x_major ? v : v + t * step_v;
+        float a[4], b[4];
+        bilinear_level<RGBA>(lo_texels, fc.lut, fc.T >> lo, uu, vv, a);
+        if (hi != lo) bilinear_level<RGBA>(hi_texels, fc.lut, fc.T >> hi, uu, vv, b);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[c] += (hi != lo) ? a[c] * (1.0f - w) + b[c] * w : a[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) out[c] = acc[c] / (float)N;
+}
+
+struct FilteredVertex { Record r; uint32_t albedo; };
+
+// the sampling half of the vertex with the configs[2] sampler (vertex_front supplies position, morphed uv, blend LOD / ratio)
+template <bool SPHERICAL>
+__device__ __noinline__ FilteredVertex vertex_back_filtered(const ViewUniforms& U, const FrameConsts& F, const GenParams& P, uint32_t flags,
+                                                            const bt_tile& tile, uint32_t tile_index, const Front& f) {
+    const Vec3 wp = f.wp, wn = f.wn;
+    const uint32_t tile_texels = (uint32_t)(F.T * F.T);
+    const uint32_t aa = P.albedo_attachment;
+    float height = 0.0f, color[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    Vec3 nrm = wn;
+    const uint32_t passes = f.blend_ratio > 0.0f ? 2u : 1u;
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+        const AtlasTile t = lookup_tile(F, P.tile_tree, Coord{tile.side, tile.lod, tile.x, tile.y, f.cu, f.cv}, f.blend_lod - pass);
+        const uint32_t layer = min(t.index, F.last_layer);
+        const float u = t.c.u * F.a_scale + F.a_offset, v = t.c.v * F.a_scale + F.a_offset;
+        const float inv_g = 1.0f / F.g;
+        const float rel = exp2i((int)t.c.lod - (int)tile.lod);
+        const float step = (inv_g * rel) * F.a_scale;
+        FilterCtx fh{P.height_atlas + (size_t)layer * tile_texels, P.height_mips ? P.height_mips + (size_t)layer * P.mip_chain_texels : nullptr, nullptr,
+                     (uint32_t)F.T, P.mip_level_count, (flags & BT_FLAG_FILTER_TRILINEAR_ANISO) != 0u};
+        float s[4];
+        sample_filtered<false>(fh, u, v, step, step, s);
+        const float h = mix(F.min_h, F.max_h, s[0]);
+        Vec3 n2 = wn;
+        if (flags & BT_FLAG_NORMALS) {
+            const float dbs = F.side_length / (F.size0 * tile_count(t.c.lod));
+            const float o = F.normal_offset;
+            float taps[4];
+            const float du[4] = {-o, 0.0f, o, 0.0f}, dv[4] = {0.0f, -o, 0.0f, o};   // left, up, right, down
+            for (int k = 0; k < 4; ++k) {
+                sample_filtered<false>(fh, u + du[k], v + dv[k], step, step, s);
+                taps[k] = mix(F.min_h, F.max_h, s[0]);
+            }
+            const Vec3 sn = normalize3(Vec3{taps[0] - taps[2], taps[3] - taps[1], dbs});
+            Vec3 r;
+            if (SPHERICAL) {
+                Vec3 face_up;
+                switch (t.c.side) {
+                    case 0: case 1: face_up = Vec3{0.0f, 1.0f, 0.0f}; break;
+                    case 2: case 3: face_up = Vec3{0.0f, 0.0f, -1.0f}; break;
+                    default: face_up = Vec3{-1.0f, 0.0f, 0.0f}; break;
+                }
+                const Vec3 n = normalize3(wn);
+                const Vec3 tg = cross3(face_up, n);
+                const Vec3 bt = cross3(n, tg);
+                r = Vec3{(tg.x * sn.x + bt.x * sn.y) + n.x * sn.z, (tg.y * sn.x + bt.y * sn.y) + n.y * sn.z, (tg.z * sn.x + bt.z * sn.y) + n.z * sn.z};
+            } else {
+                r = Vec3{sn.x, sn.z, sn.y};
+            }
+            n2 = normalize3(r);
+        }
+        float col[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (flags & BT_FLAG_ALBEDO) {
+            const float a_scale = U.attachments[aa].scale, a_offset = U.attachments[aa].offset;
+            const float ua = t.c.u * a_scale + a_offset, va = t.c.v * a_scale + a_offset;
+            const float step_a = (inv_g * rel) * a_scale;
+            FilterCtx fa{P.albedo_atlas + (size_t)layer * tile_texels, P.albedo_mips ? P.albedo_mips + (size_t)layer * P.mip_chain_texels : nullptr, P.srgb_lut,
+                         (uint32_t)F.T, P.mip_level_count, (flags & BT_FLAG_FILTER_TRILINEAR_ANISO) != 0u};
+            sample_filtered<true>(fa, ua, va, step_a, step_a, col);
+        }
+        if (pass == 0u) {
+            height = h;
+            nrm = n2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) color[k] = col[k];
+        } else {
+            height = mix(height, h, f.blend_ratio);
+            if (flags & BT_FLAG_NORMALS) nrm = Vec3{mix(nrm.x, n2.x, f.blend_ratio), mix(nrm.y, n2.y, f.blend_ratio), mix(nrm.z, n2.z, f.blend_ratio)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) color[k] = mix(color[k], col[k], f.blend_ratio);
+        }
+    }
+    FilteredVertex out;
+    out.r.w[0] = make_float2(wp.x + height * wn.x, wp.y + height * wn.y);
+    out.r.w[1] = make_float2(wp.z + height * wn.z, 1.0f);
+    out.r.w[2] = make_float2(nrm.x, nrm.y);
+    out.r.w[3] = make_float2(nrm.z, f.cu);
+    out.r.w[4] = make_float2(f.cv, __uint_as_float(tile_index));
+    uint32_t packed = 0;   // pack4x8unorm of the linear colour
+#pragma unroll
+    for (int k = 0; k < 4; ++k) packed |= (uint32_t)floorf(0.5f + 255.0f * saturate(color[k])) << (8 * k);
+    out.albedo = packed;
+    return out;
+}
+
 struct GenSmemHeader {
     ViewUniforms U;
     uint64_t bar;                   // uniform-block TMA load
@@ -697,6 +871,7 @@ struct GenSmemHeader {
 //   * one auxiliary warp builds the per-item tables (above) GEN_TABLE_LEAD items ahead and, per item, waits on full[b], issues the
 //     item's TMA bulk stores, waits until they have READ the image (cp.async.bulk.wait_group.read) and arrives on empty[b],
 //     which the compute warps wait on before reusing image b
+// FLAGS_CT == -2: generic flags + the configs[2] sampler / albedo stream (vertex_back_filtered).
 // FLAGS_CT >= 0: the flag word is a compile-time constant (the common sets get their own instantiation, so the flag
 // branches and the code of the disabled features disappear); FLAGS_CT < 0: generic kernel, flags read from the parameters.
 template <bool SPHERICAL, int FLAGS_CT>
@@ -705,6 +880,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
     GenSmemHeader& H = *reinterpret_cast<GenSmemHeader*>(smem_raw);
     unsigned char* tables = smem_raw + ((sizeof(GenSmemHeader) + 127) & ~size_t(127));
     unsigned char* images = tables + (size_t)GEN_TABLE_SLOTS * P.table_bytes;
+    unsigned char* aimages = images + (size_t)GEN_BUFFERS * P.image_bytes;      // albedo stream images (BT_FLAG_ALBEDO only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
@@ -792,6 +968,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
 #ifndef BT_GEN_SKIP_STORE   // (compute-only measurement variant of tools/gen_probe.py: NOT the product path)
                 for (uint32_t s = 0; s < n_strips; ++s)
                     bulk_store(out + (size_t)s * strip_bytes, image + (size_t)s * strip_stride, strip_bytes);
+                if (FLAGS_CT == -2 && P.albedo_image_bytes != 0u) {    // the 4-byte-per-vertex albedo stream of the same strips
+                    const unsigned char* aimage = aimages + (size_t)b * P.albedo_image_bytes;
+                    unsigned char* aout = reinterpret_cast<unsigned char*>(P.albedo_out) + ((size_t)tile_index * vpt + (size_t)c0 * vpr) * sizeof(uint32_t);
+                    for (uint32_t s = 0; s < n_strips; ++s)
+                        bulk_store(aout + (size_t)s * P.albedo_stride, aimage + (size_t)s * P.albedo_stride, P.albedo_stride);
+                }
 #endif
                 bulk_commit();
                 ++issued;
@@ -891,6 +1073,19 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_vertices_kernel(const GenP
             const uint32_t i = live ? i_raw : n_verts - 1u;
             const uint32_t gy = __umulhi(i, magic), lx = i - gy * n_cols;  // lanes walk along texel rows
             const Front f = vertex_front<SPHERICAL>(U, F, T, rows, P.tile_tree, P.height_atlas, flags, tile, morph_zero_from, lx, gy);
+            if (FLAGS_CT == -2) {
+                // configs[2] variant: trilinear + anisotropic sampler and / or the per-vertex albedo stream
+                const FilteredVertex fv = vertex_back_filtered<SPHERICAL>(U, F, P, flags, tile, tile_index, f);
+                scatter(fv.r, lx, gy, live);
+                if (P.albedo_image_bytes != 0u) {
+                    unsigned char* aimage = aimages + (size_t)b * P.albedo_image_bytes;
+                    uint32_t* a1 = reinterpret_cast<uint32_t*>(aimage + lx * P.albedo_stride) + (2u * gy + 1u);
+                    uint32_t* a2 = reinterpret_cast<uint32_t*>(aimage + (lx - 1u) * P.albedo_stride) + (2u * gy + 2u);
+                    if (live && lx < n_strips) { *a1 = fv.albedo; if (gy == 0u) a1[-1] = fv.albedo; }
+                    if (live && lx >= 1u) { *a2 = fv.albedo; if (gy == g) a2[1] = fv.albedo; }
+                }
+                continue;
+            }
             TapTexels t;
             if (flags & BT_FLAG_NORMALS) t = f.taps.interior ? load_taps_interior(F, f.taps) : load_taps_clamped(F, f.taps);
             const Record r = vertex_back<SPHERICAL>(F, T, P.tile_tree, P.height_atlas, flags, tile, tile_index, f, &t);
@@ -909,7 +1104,7 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
                                               const bt_tile_tree_entry* tile_tree, const uint16_t* height_atlas,
                                               bt_vertex* vertices, uint64_t vertex_capacity, btd::GenStatus* status,
                                               int spherical, uint32_t flags, uint32_t grid_size, int sm_count,
-                                              cudaStream_t stream) {
+                                              const btd::GenFilterInputs* filter, cudaStream_t stream) {
     using namespace btd;
     if (grid_size == 0) return cudaErrorInvalidValue;
     const uint32_t strip_stride = strip_stride_for(2u * (grid_size + 2u) * (uint32_t)sizeof(bt_vertex));
@@ -947,11 +1142,29 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
         P.magic_cols_ragged = 0xFFFFFFFFu / (last_strips + 1u) + 1u;
     }
     P.table_bytes = (uint32_t)table_bytes;
-    const size_t smem = header + GEN_TABLE_SLOTS * table_bytes + (size_t)GEN_BUFFERS * P.image_bytes;
+    P.height_mips = nullptr; P.albedo_atlas = nullptr; P.albedo_mips = nullptr; P.srgb_lut = nullptr; P.albedo_out = nullptr;
+    P.mip_level_count = 1u; P.mip_chain_texels = 0u; P.albedo_attachment = 1u; P.albedo_image_bytes = 0u; P.albedo_stride = 0u;
+    if (flags & (BT_FLAG_FILTER_TRILINEAR_ANISO | BT_FLAG_ALBEDO)) {
+        if (!filter) return cudaErrorInvalidValue;
+        P.height_mips = filter->height_mips;
+        P.albedo_atlas = static_cast<const uchar4*>(filter->albedo_atlas);
+        P.albedo_mips = static_cast<const uchar4*>(filter->albedo_mips);
+        P.srgb_lut = filter->srgb_lut;
+        P.albedo_out = filter->albedo_out;
+        P.mip_level_count = filter->mip_level_count;
+        P.mip_chain_texels = filter->mip_chain_texels;
+        P.albedo_attachment = filter->albedo_attachment;
+        if (flags & BT_FLAG_ALBEDO) {
+            P.albedo_stride = 2u * (grid_size + 2u) * (uint32_t)sizeof(uint32_t);
+            P.albedo_image_bytes = cb * P.albedo_stride;
+        }
+    }
+    const size_t smem = header + GEN_TABLE_SLOTS * table_bytes + (size_t)GEN_BUFFERS * (P.image_bytes + P.albedo_image_bytes);
+    if (smem > (size_t)227 * 1024) return cudaErrorInvalidValue;
     // kernels specialised for the common flag sets (measured: 6 % faster than the generic kernel for NORMALS, 3 % for the
     // reference default + NORMALS); everything else (HIGH_PRECISION, partial sets) takes the generic one
     constexpr int kNone = 0, kNormals = BT_FLAG_NORMALS, kMorphBlend = BT_FLAG_MORPH | BT_FLAG_BLEND, kDefault = kMorphBlend | BT_FLAG_NORMALS;
-    const uint32_t vertex_flags = flags & (BT_FLAG_MORPH | BT_FLAG_BLEND | BT_FLAG_HIGH_PRECISION | BT_FLAG_NORMALS);
+    const uint32_t vertex_flags = flags & (BT_FLAG_MORPH | BT_FLAG_BLEND | BT_FLAG_HIGH_PRECISION | BT_FLAG_NORMALS | BT_FLAG_FILTER_TRILINEAR_ANISO | BT_FLAG_ALBEDO);
     void (*kernel)(const GenParams);
     switch (vertex_flags) {
         case kNone: kernel = spherical ? gen_vertices_kernel<true, kNone> : gen_vertices_kernel<false, kNone>; break;
@@ -960,6 +1173,8 @@ extern "C" cudaError_t bt_launch_gen_vertices(const void* uniforms, const bt_til
         case kDefault: kernel = spherical ? gen_vertices_kernel<true, kDefault> : gen_vertices_kernel<false, kDefault>; break;
         default: kernel = spherical ? gen_vertices_kernel<true, -1> : gen_vertices_kernel<false, -1>; break;
     }
+    if (flags & (BT_FLAG_FILTER_TRILINEAR_ANISO | BT_FLAG_ALBEDO))    // the configs[2] sampler / albedo variant: its own generic instantiation
+        kernel = spherical ? gen_vertices_kernel<true, -2> : gen_vertices_kernel<false, -2>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (sm_count > 0 ? sm_count : 148) * GEN_CTAS_PER_SM;

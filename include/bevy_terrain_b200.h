@@ -160,9 +160,18 @@ enum {
     BT_FLAG_BLEND          = 1u << 2,
     BT_FLAG_HIGH_PRECISION = 1u << 3,
     BT_FLAG_NORMALS        = 1u << 4,  /* fuse sample_normal into the vertex record            */
-    BT_FLAG_FRUSTUM_CULL   = 1u << 6   /* bt_select_tiles extension; default off = reference behaviour: tiles whose
+    BT_FLAG_FRUSTUM_CULL   = 1u << 6,  /* bt_select_tiles extension; default off = reference behaviour: tiles whose
                                           ten bounding points (corners + centre at min/max height) lie outside
                                           one of culling.planes[5] are neither refined nor emitted            */
+    /* BASELINE configs[2] ("trilinear + aniso sampling"): the reference's SAMPLER (linear / linear / linear, anisotropy clamp 16,
+     * terrain_bind_group.rs:120-126; its fragment stage samples with textureSampleGrad, attachments.wgsl:16-20) evaluated per
+     * vertex with the footprint of one grid step: N = min(ceil(Pmax / Pmin), 16) taps along the major axis, lod =
+     * clamp(log2(Pmax / N), 0, mips - 1), every tap mix(bilinear(floor(lod)), bilinear(floor(lod) + 1), fract(lod)) over the
+     * generate_mipmaps chain (terrain_data/mod.rs:143-219).  Default off: the reference's vertex stage samples mip 0.          */
+    BT_FLAG_FILTER_TRILINEAR_ANISO = 1u << 7,
+    /* per-vertex albedo: the Rgba8 attachment (sRGB-decoded per texel before filtering) sampled at the vertex, blended across
+     * LODs like the height, written as pack4x8unorm to the view's albedo stream (bt_view_albedo_buffer), 4 bytes per vertex   */
+    BT_FLAG_ALBEDO         = 1u << 8
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -247,6 +256,12 @@ bt_status bt_tile_config_load(const char* path, bt_tile* tiles, uint32_t capacit
  * one atlas tile at lookup.atlas_uv with the twin's exact f32 arithmetic; fetches the four texels from the device (blocking).
  * An INVALID lookup yields zeros, as in the reference.                                                                   */
 bt_status bt_atlas_sample(bt_terrain* terrain, uint32_t attachment, const bt_tile_lookup* lookup, float out[4]);
+/* Mip levels 1.. of one atlas slot from its mip 0 on the GPU = AttachmentData::generate_mipmaps, which the reference runs on
+ * the CPU at tile load (tile_atlas.rs:141, terrain_data/mod.rs:143-219): R16 = mean of the non-zero texels (integer division),
+ * Rgba8 = sum / 4.  Call after uploading / copying a tile when the attachment has mip_level_count > 1 and the filtered
+ * sampler (BT_FLAG_FILTER_TRILINEAR_ANISO) is used.  The chain of every slot lives in a second array per attachment.           */
+bt_status bt_atlas_generate_mips(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index, void* stream);
+bt_status bt_atlas_mips_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out, size_t* chain_bytes_per_slot);
 /* device base pointer of an attachment's atlas array (for zero-copy interop / tests) */
 bt_status bt_atlas_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out);
 
@@ -304,6 +319,10 @@ bt_status bt_view_readback(bt_view* view, bt_tile* tiles, uint32_t capacity, uin
 bt_status bt_view_select_status(bt_view* view, uint32_t* dropped_parents, void* stream);
 bt_status bt_view_download_vertices(bt_view* view, bt_vertex* out, uint64_t first, uint64_t count,
                                     void* stream);
+/* BT_FLAG_ALBEDO: the per-vertex colour stream written beside the vertex stream by the last bt_gen_vertices (strip order, one
+ * pack4x8unorm word per vertex; allocated on the first ALBEDO frame, with the vertex buffer's capacity) */
+bt_status bt_view_albedo_buffer(bt_view* view, uint32_t** device_albedo, uint64_t* capacity);
+bt_status bt_view_download_albedo(bt_view* view, uint32_t* out, uint64_t first, uint64_t count, void* stream);
 /* device pointers (final_tiles, indirect) for zero-copy consumers */
 bt_status bt_view_device_ptrs(bt_view* view, bt_tile** final_tiles, bt_indirect** indirect);
 

@@ -396,6 +396,126 @@ static void sample_normal(const bto_vertex_inputs* in, const atlas_tile* t, cons
     o_normalize(r, out);
 }
 
+/* ============================================================================================ */
+/* configs[2]: "trilinear + anisotropic" sampling and per-vertex albedo (BT_FLAG_FILTER_TRILINEAR_ANISO,     */
+/* BT_FLAG_ALBEDO).  The reference's vertex stage samples mip 0 only; its SAMPLER is linear / linear / linear */
+/* with anisotropy_clamp 16 (src/render/terrain_bind_group.rs:120-126) and its fragment stage uses          */
+/* textureSampleGrad (src/shaders/attachments.wgsl:16-20).  This is that sampler evaluated per vertex with   */
+/* the footprint of one grid step, written down once here:      */
+/*   P = footprint of one grid step in texels of mip 0, per axis;  N = min(ceil(Pmax / Pmin), 16) taps along */
+/*   the major axis;  lod = clamp(log2(Pmax / N), 0, mips - 1);  every tap = mix(bilinear(floor(lod)),       */
+/*   bilinear(floor(lod) + 1), fract(lod));  result = mean of the taps.  Mips are generate_mipmaps' chain.   */
+/* ============================================================================================ */
+static float srgb_lut[256];
+static int srgb_lut_ready = 0;
+static void srgb_lut_init(void) {   /* Rgba8UnormSrgb decode per texel BEFORE filtering (sRGB EOTF, IEC 61966-2-1) */
+    if (srgb_lut_ready) return;
+    for (int i = 0; i < 256; ++i) {
+        double c = (double)i / 255.0;
+        srgb_lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+    }
+    srgb_lut_ready = 1;
+}
+
+static size_t mip_offset_texels(uint32_t T, uint32_t level) {   /* texels before `level` in the appended chain (levels 1..) */
+    size_t off = 0;
+    for (uint32_t j = 1; j < level; ++j) off += (size_t)(T >> j) * (T >> j);
+    return off;
+}
+
+/* one bilinear tap at one mip level; R16: out[0]; Rgba8: four channels (rgb through the sRGB table) */
+static void bilinear_level(const void* level_texels, int rgba, uint32_t size, float u, float v, float out[4]) {
+    float px = u * (float)size - 0.5f, py = v * (float)size - 0.5f;
+    float fx = floorf(px), fy = floorf(py);
+    float rx = px - fx, ry = py - fy;
+    int32_t ix = (int32_t)fx, iy = (int32_t)fy, m = (int32_t)size - 1;
+    int32_t x0 = ix < 0 ? 0 : (ix > m ? m : ix), x1 = ix + 1 < 0 ? 0 : (ix + 1 > m ? m : ix + 1);
+    int32_t y0 = iy < 0 ? 0 : (iy > m ? m : iy), y1 = iy + 1 < 0 ? 0 : (iy + 1 > m ? m : iy + 1);
+    const int32_t xs[2] = {x0, x1}, ys[2] = {y0, y1};
+    float t[2][2][4];   /* [x][y][channel] */
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+        size_t idx = (size_t)ys[b] * size + (size_t)xs[a];
+        if (!rgba) {
+            t[a][b][0] = (float)((const uint16_t*)level_texels)[idx] / 65535.0f;
+            t[a][b][1] = t[a][b][2] = t[a][b][3] = 0.0f;
+        } else {
+            const uint8_t* q = (const uint8_t*)level_texels + idx * 4;
+            t[a][b][0] = srgb_lut[q[0]]; t[a][b][1] = srgb_lut[q[1]]; t[a][b][2] = srgb_lut[q[2]];
+            t[a][b][3] = (float)q[3] / 255.0f;
+        }
+    }
+    for (int c = 0; c < (rgba ? 4 : 1); ++c) {
+        float l0 = t[0][0][c] + (t[0][1][c] - t[0][0][c]) * ry;
+        float l1 = t[1][0][c] + (t[1][1][c] - t[1][0][c]) * ry;
+        out[c] = l0 + (l1 - l0) * rx;
+    }
+}
+
+typedef struct filter_ctx {
+    const void* mip0;        /* the atlas tile (layer) */
+    const void* mips;        /* its appended levels 1.. (NULL when mip_level_count == 1) */
+    int rgba;
+    uint32_t T, mip_level_count;
+    int trilinear;           /* 0: plain bilinear at mip 0 (ALBEDO without FILTER) */
+} filter_ctx;
+
+static void sample_filtered(const filter_ctx* fc, float u, float v, float step_u, float step_v, float out[4]) {
+    const int nch = fc->rgba ? 4 : 1;
+    if (!fc->trilinear) { bilinear_level(fc->mip0, fc->rgba, fc->T, u, v, out); return; }
+    float Px = step_u * (float)fc->T, Py = step_v * (float)fc->T;
+    float Pmax = fmaxf(Px, Py), Pmin = fminf(Px, Py);
+    float ratio = ceilf(Pmax / Pmin);
+    uint32_t N = (ratio >= 16.0f) ? 16u : (ratio >= 1.0f ? (uint32_t)ratio : 1u);   /* NaN (0 / 0) -> 1 */
+    float lambda = bto_log2f(Pmax / (float)N);
+    float d = fminf(fmaxf(lambda, 0.0f), (float)(fc->mip_level_count - 1u));          /* fmaxf(NaN, 0) = 0 */
+    uint32_t lo = (uint32_t)floorf(d), hi = lo + 1u < fc->mip_level_count ? lo + 1u : lo;
+    float w = d - (float)lo;
+    const int x_major = Px >= Py;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (uint32_t i = 0; i < N; ++i) {
+        float t = ((float)i + 0.5f) / (float)N - 0.5f;
+        float uu = x_major ? u + t * step_u : u, vv = x_major ? v : v + t * step_v;
+        float a[4], b[4];
+        const uint8_t* base = (const uint8_t*)fc->mips;
+        const size_t px = fc->rgba ? 4 : 2;
+        bilinear_level(lo == 0 ? fc->mip0 : (const void*)(base + mip_offset_texels(fc->T, lo) * px), fc->rgba, fc->T >> lo, uu, vv, a);
+        if (hi != lo) bilinear_level((const void*)(base + mip_offset_texels(fc->T, hi) * px), fc->rgba, fc->T >> hi, uu, vv, b);
+        for (int c = 0; c < nch; ++c) acc[c] += (hi != lo) ? a[c] * (1.0f - w) + b[c] * w : a[c];
+    }
+    for (int c = 0; c < nch; ++c) out[c] = acc[c] / (float)N;
+}
+
+static size_t mip_chain_texels(uint32_t T, uint32_t levels) { return mip_offset_texels(T, levels); }
+
+/* filter context of one resolved atlas tile of attachment `a` (0 = height R16, 1 = albedo Rgba8) */
+static filter_ctx make_filter_ctx(const bto_vertex_inputs* in, const bto_filter_inputs* fi, int albedo, uint32_t atlas_index) {
+    filter_ctx fc;
+    uint32_t T = in->texture_size;
+    if (in->atlas_size && atlas_index > in->atlas_size - 1u) atlas_index = in->atlas_size - 1u;
+    const size_t chain = mip_chain_texels(T, fi->mip_level_count);
+    fc.rgba = albedo;
+    fc.T = T;
+    fc.mip_level_count = fi->mip_level_count;
+    fc.trilinear = (in->flags & BT_FLAG_FILTER_TRILINEAR_ANISO) != 0;
+    if (!albedo) {
+        fc.mip0 = in->height_atlas + (size_t)atlas_index * T * T;
+        fc.mips = fi->height_mips ? (const void*)(fi->height_mips + (size_t)atlas_index * chain) : NULL;
+    } else {
+        fc.mip0 = fi->albedo_atlas + (size_t)atlas_index * T * T * 4;
+        fc.mips = fi->albedo_mips ? (const void*)(fi->albedo_mips + (size_t)atlas_index * chain * 4) : NULL;
+    }
+    return fc;
+}
+
+/* the footprint of one grid step in the uv space of the resolved atlas tile (per axis; the grid is square) */
+static float grid_step_uv(const bto_vertex_inputs* in, uint32_t tile_lod, uint32_t atlas_lod, uint32_t attachment) {
+    float inv_g = 1.0f / in->view_config.grid_size;
+    float rel = ldexpf(1.0f, (int32_t)atlas_lod - (int32_t)tile_lod);
+    return (inv_g * rel) * in->attachments[attachment].scale;
+}
+
+static void gen_vertex_filtered(const bto_vertex_inputs* in, const bto_filter_inputs* fi, uint64_t vi, bt_vertex* out, uint32_t* albedo_out);
+
 static void gen_vertex(const bto_vertex_inputs* in, uint64_t vi, bt_vertex* out) {
     const bt_view_config_uniform* vc = &in->view_config;
     const bt_model_approximation* ap = &in->approximation;
@@ -473,6 +593,136 @@ static void gen_vertex(const bto_vertex_inputs* in, uint64_t vi, bt_vertex* out)
     out->normal[0] = nrm[0]; out->normal[1] = nrm[1]; out->normal[2] = nrm[2];
     out->uv[0] = c.uv[0]; out->uv[1] = c.uv[1];
     out->tile_index = tile_index;
+}
+
+/* gen_vertex with the configs[2] sampler: identical vertex_info / morph / blend / lookup; every height tap goes through
+ * sample_filtered (FILTER flag) and the albedo attachment is sampled at the same point (ALBEDO flag) */
+static void gen_vertex_filtered(const bto_vertex_inputs* in, const bto_filter_inputs* fi, uint64_t vi, bt_vertex* out, uint32_t* albedo_out) {
+    const bt_view_config_uniform* vc = &in->view_config;
+    const bt_model_approximation* ap = &in->approximation;
+    int sph = in->spherical;
+    uint32_t tile_index = (uint32_t)(vi / vc->vertices_per_tile);
+    bt_tile tile = in->tiles[tile_index];
+    uint32_t grid_index = (uint32_t)(vi % vc->vertices_per_tile);
+    uint32_t r = grid_index % vc->vertices_per_row;
+    uint32_t lo = 1u, hi = vc->vertices_per_row - 2u;
+    uint32_t row_index = (r < lo ? lo : (r > hi ? hi : r)) - 1u;
+    uint32_t column_index = grid_index / vc->vertices_per_row;
+    coord c0 = {tile.side, tile.lod, {tile.x, tile.y},
+                {(float)(column_index + (row_index & 1u)) / vc->grid_size, (float)(row_index >> 1) / vc->grid_size}};
+    float lp[3], wp[3], wn[3], q[3];
+    local_position(sph, &c0, lp);
+    position_local_to_world(&in->mesh, lp, wp);
+    normal_local_to_world(&in->mesh, sph, lp, wn);
+    for (int k = 0; k < 3; ++k) q[k] = (wp[k] + ap->approximate_height * wn[k]) - in->view_world_position[k];
+    float d = o_length(q);
+    int high_precision = (in->flags & BT_FLAG_HIGH_PRECISION) && d < vc->precision_threshold_distance;
+    if (high_precision) {
+        float rel[3];
+        relative_position(ap, c0, rel);
+        for (int k = 0; k < 3; ++k) q[k] = rel[k] + ap->approximate_height * wn[k];
+        d = o_length(q);
+    }
+    coord c = c0;
+    if (in->flags & BT_FLAG_MORPH) {
+        float target_lod = bto_log2f(2.0f * vc->morph_distance / d);
+        float ratio = (c0.lod == 0u) ? 0.0f : o_inverse_mix((float)c0.lod + vc->morph_range, (float)c0.lod, target_lod);
+        for (int k = 0; k < 2; ++k) {
+            float even = (float)(bto_f32_to_u32(c0.uv[k] * vc->grid_size) & ~1u) / vc->grid_size;
+            c.uv[k] = o_mix(c0.uv[k], even, ratio);
+        }
+    }
+    if (high_precision) {
+        float rel[3];
+        relative_position(ap, c, rel);
+        for (int k = 0; k < 3; ++k) wp[k] = in->view_world_position[k] + rel[k];
+    } else {
+        local_position(sph, &c, lp);
+        position_local_to_world(&in->mesh, lp, wp);
+        normal_local_to_world(&in->mesh, sph, lp, wn);
+    }
+    float target_lod = fminf(bto_log2f(vc->blend_distance / d), (float)in->terrain_config.lod_count - 0.00001f);
+    uint32_t blend_lod = bto_f32_to_u32(target_lod);
+    float blend_ratio = 0.0f;
+    if ((in->flags & BT_FLAG_BLEND) && blend_lod != 0u)
+        blend_ratio = o_inverse_mix((float)blend_lod + vc->blend_range, (float)blend_lod, target_lod);
+
+    float height = 0.0f, nrm[3] = {wn[0], wn[1], wn[2]}, color[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (uint32_t pass = 0; pass < (blend_ratio > 0.0f ? 2u : 1u); ++pass) {
+        atlas_tile t = lookup_tile(in, c, blend_lod, pass);
+        const uint32_t aa = fi->albedo_attachment;
+        float u = t.c.uv[0] * in->attachments[0].scale + in->attachments[0].offset;
+        float v = t.c.uv[1] * in->attachments[0].scale + in->attachments[0].offset;
+        float step = grid_step_uv(in, tile.lod, t.c.lod, 0);
+        filter_ctx fh = make_filter_ctx(in, fi, 0, t.index);
+        float s[4];
+        sample_filtered(&fh, u, v, step, step, s);
+        float h = o_mix(in->terrain_config.min_height, in->terrain_config.max_height, s[0]);
+        float n2[3] = {wn[0], wn[1], wn[2]};
+        if (in->flags & BT_FLAG_NORMALS) {   /* sample_normal with the filtered sampler for its four taps */
+            float side_length = in->spherical ? (float)(3.14159265359 / 4.0) * in->terrain_config.scale : in->terrain_config.scale;
+            float pixels_per_side = in->attachments[0].size * o_tile_count(t.c.lod);
+            float dbs = side_length / pixels_per_side;
+            float offset = 0.5f / in->attachments[0].size;
+            float taps[4];
+            const float du[4] = {-offset, 0.0f, offset, 0.0f}, dv[4] = {0.0f, -offset, 0.0f, offset};   /* left, up, right, down */
+            for (int k = 0; k < 4; ++k) {
+                sample_filtered(&fh, u + du[k], v + dv[k], step, step, s);
+                taps[k] = o_mix(in->terrain_config.min_height, in->terrain_config.max_height, s[0]);
+            }
+            float sv[3] = {taps[0] - taps[2], taps[3] - taps[1], dbs}, sn[3], rr[3];
+            o_normalize(sv, sn);
+            if (in->spherical) {
+                static const float FACE_UP[6][3] = {{0, 1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, -1}, {-1, 0, 0}, {-1, 0, 0}};
+                float n[3], tg[3], bt[3];
+                o_normalize(wn, n);
+                o_cross(FACE_UP[t.c.side], n, tg);
+                o_cross(n, tg, bt);
+                for (int k = 0; k < 3; ++k) rr[k] = (tg[k] * sn[0] + bt[k] * sn[1]) + n[k] * sn[2];
+            } else {
+                rr[0] = sn[0]; rr[1] = sn[2]; rr[2] = sn[1];
+            }
+            o_normalize(rr, n2);
+        }
+        float col[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (in->flags & BT_FLAG_ALBEDO) {
+            float ua = t.c.uv[0] * in->attachments[aa].scale + in->attachments[aa].offset;
+            float va = t.c.uv[1] * in->attachments[aa].scale + in->attachments[aa].offset;
+            float step_a = grid_step_uv(in, tile.lod, t.c.lod, aa);
+            filter_ctx fa = make_filter_ctx(in, fi, 1, t.index);
+            sample_filtered(&fa, ua, va, step_a, step_a, col);
+        }
+        if (pass == 0) {
+            height = h;
+            for (int k = 0; k < 3; ++k) nrm[k] = n2[k];
+            for (int k = 0; k < 4; ++k) color[k] = col[k];
+        } else {
+            height = o_mix(height, h, blend_ratio);
+            if (in->flags & BT_FLAG_NORMALS) for (int k = 0; k < 3; ++k) nrm[k] = o_mix(nrm[k], n2[k], blend_ratio);
+            for (int k = 0; k < 4; ++k) color[k] = o_mix(color[k], col[k], blend_ratio);
+        }
+    }
+    for (int k = 0; k < 3; ++k) out->position[k] = wp[k] + height * wn[k];
+    out->position[3] = 1.0f;
+    out->normal[0] = nrm[0]; out->normal[1] = nrm[1]; out->normal[2] = nrm[2];
+    out->uv[0] = c.uv[0]; out->uv[1] = c.uv[1];
+    out->tile_index = tile_index;
+    if (albedo_out) {   /* pack4x8unorm of the linear colour */
+        uint32_t packed = 0;
+        for (int k = 0; k < 4; ++k) packed |= (uint32_t)floorf(0.5f + 255.0f * o_saturate(color[k])) << (8 * k);
+        *albedo_out = packed;
+    }
+}
+
+void bto_gen_vertices_filtered(const bto_vertex_inputs* in, const bto_filter_inputs* fi, uint64_t first, uint64_t count, bt_vertex* out,
+                               uint32_t* albedo_out, int threads) {
+    srgb_lut_init();
+    (void)threads;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static, 4096) num_threads(threads)
+#endif
+    for (int64_t i = 0; i < (int64_t)count; ++i) gen_vertex_filtered(in, fi, first + (uint64_t)i, &out[i], albedo_out ? &albedo_out[i] : NULL);
 }
 
 void bto_gen_vertices(const bto_vertex_inputs* in, uint64_t first, uint64_t count, bt_vertex* out, int threads) {

@@ -66,6 +66,18 @@ typedef struct bto_vertex_inputs {
 void bto_gen_vertices(const bto_vertex_inputs* in, uint64_t first, uint64_t count, bt_vertex* out,
                       int threads);
 
+/* configs[2] sampler (BT_FLAG_FILTER_TRILINEAR_ANISO) and per-vertex albedo (BT_FLAG_ALBEDO): extra inputs beside bto_vertex_inputs.
+ * Mip chains use bto_generate_mipmaps' layout (levels 1.. appended), one chain per atlas slot.                        */
+typedef struct bto_filter_inputs {
+    const uint16_t* height_mips;     /* [atlas][chain] or NULL when mip_level_count == 1 */
+    const uint8_t*  albedo_atlas;    /* [atlas][T][T][4] mip 0 (Rgba8, sRGB-encoded rgb) */
+    const uint8_t*  albedo_mips;
+    uint32_t        mip_level_count;
+    uint32_t        albedo_attachment;   /* index into bto_vertex_inputs.attachments for the albedo's size / scale / offset */
+} bto_filter_inputs;
+void bto_gen_vertices_filtered(const bto_vertex_inputs* in, const bto_filter_inputs* fi, uint64_t first, uint64_t count,
+                               bt_vertex* out, uint32_t* albedo_out /* may be NULL */, int threads);
+
 /* ---- preprocess ---- */
 typedef struct bto_pyramid bto_pyramid;
 bto_pyramid* bto_pyramid_create(uint32_t kind, uint32_t format, uint32_t texture_size,

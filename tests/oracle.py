@@ -33,6 +33,11 @@ class VertexInputs(C.Structure):
                 ("height_atlas", C.c_void_p), ("tiles", C.POINTER(F.Tile)), ("tile_count", u32), ("flags", u32)]
 
 
+class FilterInputs(C.Structure):   # bto_filter_inputs: the configs[2] sampler / albedo extras
+    _fields_ = [("height_mips", C.c_void_p), ("albedo_atlas", C.c_void_p), ("albedo_mips", C.c_void_p),
+                ("mip_level_count", u32), ("albedo_attachment", u32)]
+
+
 _lib = None
 
 
@@ -81,6 +86,7 @@ def lib() -> C.CDLL:
         "bto_pyramid_tile": (vp, [vp, P(F.Tile)]),
         "bto_tile_neighbours": (None, [P(F.Tile), i32, P(F.Tile)]),
         "bto_generate_mipmaps": (None, [u32, u32, u32, vp, vp]),
+        "bto_gen_vertices_filtered": (None, [P(VertexInputs), P(FilterInputs), u64, u64, vp, vp, i32]),
         "bto_model_approximation": (None, [P(F.TerrainModel), P(f64), u32, f32, P(F.ModelApproximation)]),
         "bto_coordinate_from_world_position": (None, [P(F.TerrainModel), P(f64), P(u32), P(f64)]),
         "bto_project_point_ellipsoid": (None, [f64, f64, P(f64), P(f64)]),
@@ -194,6 +200,36 @@ def select_tiles(vc, approx, cull, mesh, spherical: bool, capacity: int | None =
 
 VERTEX_DTYPE = np.dtype([("position", "<f4", 4), ("normal", "<f4", 3), ("uv", "<f4", 2), ("tile_index", "<u4")])
 assert VERTEX_DTYPE.itemsize == 40
+
+
+def mip_chain_texels(T: int, levels: int) -> int:
+    return sum((T >> k) * (T >> k) for k in range(1, levels))
+
+
+def generate_mipmaps(tile: np.ndarray, levels: int) -> np.ndarray:
+    """levels 1.. of one tile appended (AttachmentData::generate_mipmaps); uint16 (T, T) or uint8 (T, T, 4)"""
+    T = tile.shape[0]
+    fmt = F.BT_FORMAT_R16 if tile.dtype == np.uint16 else F.BT_FORMAT_RGBA8
+    n = mip_chain_texels(T, levels)
+    out = np.zeros(n if fmt == F.BT_FORMAT_R16 else (n, 4), dtype=tile.dtype)
+    tile = np.ascontiguousarray(tile)
+    if n:
+        lib().bto_generate_mipmaps(fmt, T, levels, tile.ctypes.data, out.ctypes.data)
+    return out
+
+
+def gen_vertices_filtered(inputs: VertexInputs, height_mips, albedo_atlas, albedo_mips, mip_level_count: int, first: int, count: int,
+                          albedo_attachment: int = 1, threads: int = 0):
+    """vertices + per-vertex albedo with the configs[2] sampler (flags in inputs.flags); arrays may be None"""
+    fi = FilterInputs()
+    fi.height_mips = height_mips.ctypes.data if height_mips is not None else None
+    fi.albedo_atlas = albedo_atlas.ctypes.data if albedo_atlas is not None else None
+    fi.albedo_mips = albedo_mips.ctypes.data if albedo_mips is not None else None
+    fi.mip_level_count, fi.albedo_attachment = mip_level_count, albedo_attachment
+    out = np.empty(count, dtype=VERTEX_DTYPE)
+    albedo = np.zeros(count, dtype=np.uint32)
+    lib().bto_gen_vertices_filtered(C.byref(inputs), C.byref(fi), first, count, out.ctypes.data, albedo.ctypes.data, threads)
+    return out, albedo
 
 
 def gen_vertices(inputs: VertexInputs, first: int, count: int, threads: int = 0) -> np.ndarray:

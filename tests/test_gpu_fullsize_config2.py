@@ -74,7 +74,7 @@ def test_config2_frame_vertices(ctx, terrain):
     try:
         tree.add_existing_tiles(pre.tiles(0))
         pos = (-410.0, -100.0 + 250.0 + 5.0, 377.0)      # 5 above the surface: the 12-LOD tree refines to its deepest levels
-        assert 0 < api.load_resident_tiles(tree, pre, pos) <= cfg.atlas_size
+        assert 0 < api.load_resident_tiles(tree, pre, pos, attachments=(0, 1)) <= cfg.atlas_size
         tree.prepare()
         tree.select_tiles()
         tiles, ind = tree.readback()
@@ -90,5 +90,26 @@ def test_config2_frame_vertices(ctx, terrain):
         deep = np.flatnonzero(tiles[:, 1] >= 9)
         pick = np.concatenate([rng.choice(len(tiles), 24, replace=False), rng.choice(deep, min(8, len(deep)), replace=False)])
         assert_tiles_bit_exact(tree, vi, pick)
+        # ---- the configs[2] sampler ("trilinear + aniso") and the per-vertex albedo at full size: CUDA == oracle on whole tiles
+        fflags = flags | F.BT_FLAG_FILTER_TRILINEAR_ANISO | F.BT_FLAG_ALBEDO
+        tree.gen_vertices(fflags)
+        mips = cfg.attachments[0].mip_level_count
+        chain = O.mip_chain_texels(T, mips)
+        hm = np.empty((cfg.atlas_size, chain), dtype=np.uint16)
+        ctx.d2h(hm, atlas.mips_device_ptr(0)[0])
+        aa = np.empty((cfg.atlas_size, T, T, 4), dtype=np.uint8)
+        ctx.d2h(aa, atlas.device_ptr(1))
+        am = np.empty((cfg.atlas_size, chain, 4), dtype=np.uint8)
+        ctx.d2h(am, atlas.mips_device_ptr(1)[0])
+        for slot in rng.choice(cfg.atlas_size, 6, replace=False):       # the GPU mip chains are the oracle's
+            assert np.array_equal(hm[slot], O.generate_mipmaps(vi._keep[0][slot], mips))
+            assert np.array_equal(am[slot], O.generate_mipmaps(aa[slot], mips))
+        vi.flags = fflags
+        vi.attachments[1] = vi.attachments[0]
+        vpt = 8448
+        for t in pick[:12]:
+            exp, exp_col = O.gen_vertices_filtered(vi, hm, aa, am, mips, int(t) * vpt, vpt)
+            assert tree.download_vertices(int(t) * vpt, vpt).tobytes() == exp.tobytes(), f"filtered tile {t} differs"
+            assert np.array_equal(tree.download_albedo(int(t) * vpt, vpt), exp_col), f"albedo of tile {t} differs"
     finally:
         tree.close(); atlas.close()
