@@ -455,13 +455,13 @@ def run_b200(args):
 # ------------------------------------------------------------------------------------------------
 # extra workloads: configs[2] and configs[3] at full size (the shapes of tests/test_gpu_fullsize_config2.py / _spherical.py)
 # ------------------------------------------------------------------------------------------------
-def frame_views(api, ctx, cfg, vcfg, pre, positions, max_tiles):
+def frame_views(api, ctx, cfg, vcfg, pre, positions, max_tiles, attachments=(0,)):
     views = []
     for pos in positions:
         atlas = api.TileAtlas(ctx, cfg)
         tree = api.TileTree(atlas, vcfg, max_vertices=max_tiles * VPT)
         tree.add_existing_tiles(pre.tiles(0))
-        api.load_resident_tiles(tree, pre, pos)
+        api.load_resident_tiles(tree, pre, pos, attachments=attachments)
         tree.prepare()
         tree.select_tiles()
         tiles, ind = tree.readback()
@@ -487,13 +487,18 @@ def run_config2(torch, api, F, ctx):
     rng = np.random.default_rng(VIEW_SEED + 2)
     positions = [(float(rng.uniform(-700, 700)), -100.0 + 250.0 + 1.0, float(rng.uniform(-700, 700))) for _ in range(4)]
     vcfg = api.TerrainViewConfig(grid_size=64)
-    views = frame_views(api, ctx, cfg, vcfg, pre, positions, 12000)
+    views = frame_views(api, ctx, cfg, vcfg, pre, positions, 12000, attachments=(0, 1))
     flags = F.BT_FLAG_MORPH | F.BT_FLAG_BLEND | F.BT_FLAG_NORMALS
     r = time_views(torch, views, flags, 4)
+    # the "trilinear + aniso" sampler of the config's name + the per-vertex albedo stream (44 B / vertex written)
+    rf = time_views(torch, views, flags | F.BT_FLAG_FILTER_TRILINEAR_ANISO | F.BT_FLAG_ALBEDO, 2)
     out = {"workload": "configs[2]: planar 16384^2 height R16 + albedo Rgba8, 12 LODs (data LODs 0..5), grid 64, camera 1 above the surface, "
                        "MORPH + BLEND + NORMALS; 4 seeded views", "tiles_per_view": [v["tiles"] for v in views],
            "verts_per_view": [v["verts"] for v in views], "flags": "MORPH|BLEND|NORMALS", **r,
            "roofline": roofline_block(r["gen_vertices_ms"], r["verts_per_step"], None),
+           "trilinear_aniso_plus_albedo": {"flags": "MORPH|BLEND|NORMALS|FILTER_TRILINEAR_ANISO|ALBEDO", "Mverts_per_s": rf["Mverts_per_s"],
+                                           "gen_vertices_ms": rf["gen_vertices_ms"], "bytes_written_per_vertex": 44,
+                                           "frac_dram_compulsory": 44.0 * rf["verts_per_step"] / (rf["gen_vertices_ms"] * 1e-3) / 1e9 / hbm_peak()[0]},
            "preprocess_ms": p0.elapsed_time(p1), "preprocess_tiles": int(len(pre.tiles(0)) + len(pre.tiles(1)))}
     for v in views:
         v["tree"].close(); v["atlas"].close()

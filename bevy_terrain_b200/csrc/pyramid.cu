@@ -496,6 +496,9 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
                 const float2 q2 = div_by_rcp2(make_float2(fa, fb), len, r);
                 volatile float vl = len;
                 if (q2.x != fa / vl || q2.y != fb / vl) atomicAdd(&mismatches[2], 1u);
+                // normalize3 keeps the sign of a zero component (IEEE: -0 / len == -0)
+                const Vec3 nz = normalize3(Vec3{-0.0f, fb, 0.0f});
+                if (__float_as_uint(nz.x) != 0x80000000u || __float_as_uint(nz.z) != 0u || nz.y != fb / fabsf(fb)) atomicAdd(&mismatches[2], 1u);
                 const float l3 = length3(Vec3{fa, fb, fc});
                 volatile float ss = __fadd_rn(__fadd_rn(__fmul_rn(fa, fa), __fmul_rn(fb, fb)), __fmul_rn(fc, fc));
                 if (ss >= 1.17549435e-38f && l3 != sqrtf(ss)) atomicAdd(&mismatches[3], 1u);

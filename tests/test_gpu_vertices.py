@@ -79,7 +79,7 @@ def test_vertices_planar_grid64_bit_exact(ctx):
         _assert_vertices_equal(verts[t * vpt:(t + 1) * vpt], exp)
 
 
-@pytest.mark.parametrize("flags", [ALL, ALL | F.BT_FLAG_HIGH_PRECISION])
+@pytest.mark.parametrize("flags", [ALL, ALL | F.BT_FLAG_HIGH_PRECISION, 0, F.BT_FLAG_MORPH | F.BT_FLAG_BLEND])   # without NORMALS the record carries the MODEL normal (signed zeros of the cube-face coordinates included)
 def test_vertices_spherical_bit_exact(ctx, flags):
     scene = Scene("spherical", lod_count=3, T=32, B=2, src=64, grid_size=16)
     positions = spherical_view_positions()[:4]
