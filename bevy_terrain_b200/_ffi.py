@@ -20,7 +20,7 @@ BT_OK, BT_ERR_INVALID_ARG, BT_ERR_CAPACITY, BT_ERR_CUDA, BT_ERR_NCCL, BT_ERR_IO,
 BT_FORMAT_RGBA8, BT_FORMAT_R16 = 0, 1
 BT_KIND_PLANAR, BT_KIND_SPHERICAL, BT_KIND_ELLIPSOIDAL = 0, 1, 2
 BT_FLAG_MORPH, BT_FLAG_BLEND, BT_FLAG_HIGH_PRECISION, BT_FLAG_NORMALS, BT_FLAG_FRUSTUM_CULL = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 6
-BT_FLAG_FILTER_TRILINEAR_ANISO, BT_FLAG_ALBEDO = 1 << 7, 1 << 8
+BT_FLAG_FILTER_TRILINEAR_ANISO, BT_FLAG_ALBEDO, BT_FLAG_MINMAX_CULL = 1 << 7, 1 << 8, 1 << 9
 
 
 class Tile(C.Structure):  # bt_tile / TileCoordinate (coordinate.rs:156-166)
@@ -186,6 +186,8 @@ def _declare(lib: C.CDLL) -> None:
         "bt_image_free": (None, [P(Image)]),
         "bt_atlas_device_ptr": (i32, [vp, u32, P(vp)]),
         "bt_atlas_generate_mips": (i32, [vp, u32, u32, vp]),
+        "bt_atlas_update_minmax": (i32, [vp, u32, vp]),
+        "bt_atlas_minmax_device_ptr": (i32, [vp, P(vp)]),
         "bt_atlas_mips_device_ptr": (i32, [vp, u32, P(vp), P(C.c_size_t)]),
         "bt_view_albedo_buffer": (i32, [vp, P(vp), P(u64)]),
         "bt_view_download_albedo": (i32, [vp, vp, u64, u64, vp]),

@@ -276,6 +276,17 @@ class TileAtlas:
         """AttachmentData::generate_mipmaps at tile load (tile_atlas.rs:141), on the GPU"""
         self.ctx.check(self.ctx.lib.bt_atlas_generate_mips(self._h, attachment, atlas_index, C.c_void_p(stream)))
 
+    def update_minmax(self, atlas_index: int, stream: int = 0) -> None:
+        """(min, max) table of the height tile in a slot, for BT_FLAG_MINMAX_CULL"""
+        self.ctx.check(self.ctx.lib.bt_atlas_update_minmax(self._h, atlas_index, C.c_void_p(stream)))
+
+    def minmax_table(self) -> np.ndarray:
+        p = C.c_void_p()
+        self.ctx.check(self.ctx.lib.bt_atlas_minmax_device_ptr(self._h, C.byref(p)))
+        out = np.empty((self.atlas_size, 65, 2), dtype=np.uint16)
+        self.ctx.d2h(out, p.value)
+        return out
+
     def mips_device_ptr(self, attachment: int):
         p, n = C.c_void_p(), C.c_size_t()
         self.ctx.check(self.ctx.lib.bt_atlas_mips_device_ptr(self._h, attachment, C.byref(p), C.byref(n)))
@@ -679,6 +690,8 @@ def load_resident_tiles(tile_tree: TileTree, preprocessor: Preprocessor, view_wo
             tile_tree.atlas.copy_tile(a, atlas_index, preprocessor.tile_device_ptr(a, tile), stream)
             if tile_tree.atlas.attachments[a].mip_level_count > 1:
                 tile_tree.atlas.generate_mips(a, atlas_index, stream)     # the CPU mip generation at tile load, on the GPU
+            if a == 0:
+                tile_tree.atlas.update_minmax(atlas_index, stream)        # height bounds of the slot (min / max-height cull)
         tile_tree.mark_loaded(tile)
     tile_tree.adjust_to_tile_atlas()
     return len(loads)

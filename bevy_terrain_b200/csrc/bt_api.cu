@@ -116,6 +116,12 @@ bt_status bt_terrain_create(bt_context* ctx, const bt_terrain_desc* desc, bt_ter
             if (e != cudaSuccess) { ctx->set_error("bt_terrain_create: mip allocation failed: %s", cudaGetErrorString(e)); bt_terrain_destroy(t); return BT_ERR_OUT_OF_MEMORY; }
         }
     }
+    {   // per-slot (min, max) height table for BT_FLAG_MINMAX_CULL: zero = "nothing valid" = the terrain-wide range
+        const size_t bytes = (size_t)desc->atlas_size * 65 * 2 * sizeof(uint16_t);
+        cudaError_t e = cudaMalloc((void**)&t->d_minmax, bytes);
+        if (e == cudaSuccess) e = cudaMemset(t->d_minmax, 0, bytes);
+        if (e != cudaSuccess) { ctx->set_error("bt_terrain_create: %s", cudaGetErrorString(e)); bt_terrain_destroy(t); return BT_ERR_CUDA; }
+    }
     {   // the sRGB EOTF table (IEC 61966-2-1), computed in double and rounded once: the same formula as the oracle's
         float lut[256];
         for (int i = 0; i < 256; ++i) {
@@ -143,6 +149,22 @@ bt_status bt_atlas_generate_mips(bt_terrain* t, uint32_t attachment, uint32_t at
     return BT_OK;
 }
 
+// (min, max) of the height tile in one atlas slot: whole centre + 8 x 8 cells, each grown by a texel, zeros ignored (BT_FLAG_MINMAX_CULL)
+bt_status bt_atlas_update_minmax(bt_terrain* t, uint32_t atlas_index, void* stream) {
+    if (!t || atlas_index >= t->desc.atlas_size) return BT_ERR_INVALID_ARG;
+    const bt_attachment_config& a = t->desc.attachments[0];
+    BT_CUDA(t->ctx, cudaSetDevice(t->ctx->device));
+    BT_CUDA(t->ctx, bt_launch_tile_minmax(static_cast<const uint16_t*>(t->atlas[0]) + (size_t)a.texture_size * a.texture_size * atlas_index, a.texture_size,
+                                          a.border_size, t->d_minmax + (size_t)atlas_index * 65 * 2, (cudaStream_t)stream));
+    return BT_OK;
+}
+
+bt_status bt_atlas_minmax_device_ptr(bt_terrain* t, void** out) {
+    if (!t || !out) return BT_ERR_INVALID_ARG;
+    *out = t->d_minmax;
+    return BT_OK;
+}
+
 bt_status bt_atlas_mips_device_ptr(bt_terrain* t, uint32_t attachment, void** out, size_t* chain_bytes_per_slot) {
     if (!t || !out || attachment >= t->desc.attachment_count) return BT_ERR_INVALID_ARG;
     *out = t->atlas_mips[attachment];
@@ -155,6 +177,7 @@ void bt_terrain_destroy(bt_terrain* t) {
     cudaSetDevice(t->ctx->device);
     for (int i = 0; i < 8; ++i) { if (t->atlas[i]) cudaFree(t->atlas[i]); if (t->atlas_mips[i]) cudaFree(t->atlas_mips[i]); }
     cudaFree(t->d_srgb_lut);
+    cudaFree(t->d_minmax);
     if (t->h_stage) cudaFreeHost(t->h_stage);
     if (t->stage_free) cudaEventDestroy(t->stage_free);
     delete t;
@@ -314,7 +337,8 @@ bt_status bt_atlas_device_ptr(bt_terrain* t, uint32_t attachment, void** out) {
 // view
 // ------------------------------------------------------------------------------------------------
 static btd::SelectViewParams select_params_of(const bt_view* v) {
-    return btd::SelectViewParams{v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->d_indirect, v->d_select_status, v->desc.geometry_tile_count, 0u};
+    return btd::SelectViewParams{v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->d_indirect, v->d_select_status, v->desc.geometry_tile_count,
+                                 v->terrain->desc.atlas_size, v->d_tile_tree, v->terrain->d_minmax};
 }
 
 bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out) {

@@ -24,7 +24,9 @@ struct SelectViewParams {
     bt_indirect* indirect;
     SelectStatus* status;
     uint32_t capacity;
-    uint32_t _pad;
+    uint32_t atlas_size;
+    const bt_tile_tree_entry* tile_tree;   // the view's table (BT_FLAG_MINMAX_CULL)
+    const uint16_t* minmax;                // the terrain's [atlas_size][65][2] (min, max) table, or nullptr
 };
 
 struct GenStatus {

@@ -37,6 +37,7 @@ struct bt_terrain {
     void* atlas_mips[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // levels 1.. of every slot (generate_mipmaps layout)
     size_t mip_chain_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t mip_chain_texels[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint16_t* d_minmax = nullptr;   // [atlas_size][65][2]: (min, max) of every resident height tile: whole tile + 8 x 8 cells
     float* d_srgb_lut = nullptr;    // 256 floats: the sRGB EOTF (Rgba8UnormSrgb decodes per texel before filtering)
     void* h_stage = nullptr;        // pinned staging for file loads
     size_t h_stage_bytes = 0;
@@ -93,6 +94,7 @@ cudaError_t bt_launch_synth(uint32_t format, uint32_t width, uint32_t height, ui
                             uint32_t holes, void* out, cudaStream_t stream);
 cudaError_t bt_launch_selftest(const float* x, float* log2_out, uint32_t n, uint32_t* mismatches, cudaStream_t stream);
 cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream);
+cudaError_t bt_launch_tile_minmax(const uint16_t* tile, uint32_t T, uint32_t B, uint16_t* out130, cudaStream_t stream);
 cudaError_t bt_launch_tile_hash(const void* arena, uint64_t tile_bytes, const btd::TileHashTask* tasks, uint32_t n,
                                 unsigned long long* out, cudaStream_t stream);
 }

@@ -595,6 +595,47 @@ extern "C" cudaError_t bt_launch_tile_hash(const void* arena, uint64_t tile_byte
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// (min, max) table of one height tile for the min / max-height cull: block e = region e (0: centre, 1..64: 8 x 8 cells)
+// ------------------------------------------------------------------------------------------------
+namespace btd {
+__global__ void __launch_bounds__(128) tile_minmax_kernel(const uint16_t* __restrict__ tile, uint32_t T, uint32_t B, uint16_t* __restrict__ out) {
+    const uint32_t e = blockIdx.x, C_ = T - 2u * B;
+    uint32_t x0, x1, y0, y1;
+    if (e == 0u) { x0 = B; x1 = B + C_; y0 = B; y1 = B + C_; }
+    else {
+        const uint32_t cx = (e - 1u) % 8u, cy = (e - 1u) / 8u;
+        x0 = B + cx * C_ / 8u; x1 = B + (cx + 1u) * C_ / 8u;
+        y0 = B + cy * C_ / 8u; y1 = B + (cy + 1u) * C_ / 8u;
+    }
+    x0 = x0 > 0u ? x0 - 1u : 0u; y0 = y0 > 0u ? y0 - 1u : 0u;
+    x1 = min(x1 + 1u, T); y1 = min(y1 + 1u, T);
+    const uint32_t w = x1 - x0, n = w * (y1 - y0);
+    uint32_t mn = 0xFFFFu, mx = 0u;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t y = y0 + i / w, x = x0 + i % w;
+        const uint32_t v = tile[(size_t)y * T + x];
+        if (v != 0u) { mn = min(mn, v); mx = max(mx, v); }
+    }
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    __shared__ uint32_t smn[4], smx[4];
+    if ((threadIdx.x & 31u) == 0u) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        for (int k = 1; k < 4; ++k) { mn = min(mn, smn[k]); mx = max(mx, smx[k]); }
+        mn = min(mn, smn[0]); mx = max(mx, smx[0]);
+        if (mx == 0u) mn = 0u;
+        out[2u * e] = (uint16_t)mn;
+        out[2u * e + 1u] = (uint16_t)mx;
+    }
+}
+}  // namespace btd
+
+extern "C" cudaError_t bt_launch_tile_minmax(const uint16_t* tile, uint32_t T, uint32_t B, uint16_t* out130, cudaStream_t stream) {
+    btd::tile_minmax_kernel<<<65, 128, 0, stream>>>(tile, T, B, out130);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t bt_launch_row_copy(const btd::RowCopy* copies, uint32_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     btd::row_copy_kernel<<<(n + 7u) / 8u, 256, 0, stream>>>(copies, n);

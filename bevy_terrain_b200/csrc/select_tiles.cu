@@ -53,8 +53,35 @@ __device__ __forceinline__ bool should_be_divided(const ViewUniforms& U, const b
 // EXTENSION (BT_FLAG_FRUSTUM_CULL, default off — the reference does not cull at this commit): ten bounding
 // points (four corners + centre, at min_height and max_height) against the five planes of culling_bind_group.rs:25-38;
 // culled when all ten lie on the negative side of one plane.  Same arithmetic as the oracle's tile_outside_frustum.
+// EXTENSION (BT_FLAG_MINMAX_CULL, default off): the height range of the bounding points comes from the best resident atlas tile that
+// contains the geometry tile (docs/implementation.md:69: "a 2D min-max height data attachment to approximate the bounding volumes"):
+// the (min, max) table of bt_atlas_update_minmax — whole tile + 8 x 8 cells — looked up through the view's tile-tree table.
+// Same arithmetic as the oracle's tile_height_bounds.
+constexpr uint32_t MINMAX_CELLS = 8u, MINMAX_ENTRIES = 1u + MINMAX_CELLS * MINMAX_CELLS;
+__device__ __forceinline__ void tile_height_bounds(const ViewUniforms& U, const SelectViewParams& V, const bt_tile& tile, float& hmin, float& hmax) {
+    hmin = U.terrain_config.min_height;
+    hmax = U.terrain_config.max_height;
+    if (!V.minmax || !V.tile_tree) return;
+    const uint32_t lod_count = U.terrain_config.lod_count, ts = U.view_config.tree_size;
+    Coord c{tile.side, tile.lod, tile.x, tile.y, 0.5f, 0.5f};
+    const uint32_t L = min(tile.lod, lod_count - 1u);
+    change_lod(c, L);
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(V.tile_tree) + (((c.side * lod_count + c.lod) * ts + c.x % ts) * ts + c.y % ts));
+    if (e.x >= V.atlas_size || e.y > L) return;            // nothing resident (INVALID) or a malformed entry
+    change_lod(c, e.y);
+    uint32_t entry = 0u;
+    if (tile.lod - e.y >= 3u) {
+        const uint32_t cx = min(f2u(c.u * (float)MINMAX_CELLS), MINMAX_CELLS - 1u), cy = min(f2u(c.v * (float)MINMAX_CELLS), MINMAX_CELLS - 1u);
+        entry = 1u + cy * MINMAX_CELLS + cx;
+    }
+    const ushort2 mm = __ldg(reinterpret_cast<const ushort2*>(V.minmax) + ((size_t)e.x * MINMAX_ENTRIES + entry));
+    if (mm.y == 0) return;                                 // no valid texel in the region
+    hmin = mix(U.terrain_config.min_height, U.terrain_config.max_height, (float)mm.x / 65535.0f);
+    hmax = mix(U.terrain_config.min_height, U.terrain_config.max_height, (float)mm.y / 65535.0f);
+}
+
 template <bool SPHERICAL>
-__device__ __forceinline__ bool tile_outside_frustum(const ViewUniforms& U, const bt_tile& tile) {
+__device__ __forceinline__ bool tile_outside_frustum(const ViewUniforms& U, const bt_tile& tile, float hmin, float hmax) {
     uint32_t outside = 0x1Fu;  // bit p: all points so far are outside plane p
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -65,7 +92,7 @@ __device__ __forceinline__ bool tile_outside_frustum(const ViewUniforms& U, cons
         const Vec3 wn = normal_local_to_world<SPHERICAL>(U.mesh, lp);
 #pragma unroll
         for (int hsel = 0; hsel < 2; ++hsel) {
-            const float h = hsel ? U.terrain_config.max_height : U.terrain_config.min_height;
+            const float h = hsel ? hmax : hmin;
             const Vec3 q{wp.x + h * wn.x, wp.y + h * wn.y, wp.z + h * wn.z};
 #pragma unroll
             for (int p = 0; p < 5; ++p) {
@@ -144,7 +171,13 @@ select_tiles_kernel(const SelectViewParams* __restrict__ views, uint32_t flags) 
             bool valid = i < n_cur, divide = false;
             if (valid) {
                 tile = cur[i];
-                if ((flags & BT_FLAG_FRUSTUM_CULL) && tile_outside_frustum<SPHERICAL>(U, tile)) valid = false;  // culled: neither refined nor emitted
+                bool culled = false;
+                if (flags & (BT_FLAG_FRUSTUM_CULL | BT_FLAG_MINMAX_CULL)) {
+                    float hmin = U.terrain_config.min_height, hmax = U.terrain_config.max_height;
+                    if (flags & BT_FLAG_MINMAX_CULL) tile_height_bounds(U, V, tile, hmin, hmax);
+                    culled = tile_outside_frustum<SPHERICAL>(U, tile, hmin, hmax);
+                }
+                if (culled) valid = false;  // neither refined nor emitted
                 else divide = should_be_divided<SPHERICAL>(U, tile, planar_normal);
             }
             const uint32_t div_mask = __ballot_sync(0xffffffffu, valid && divide);

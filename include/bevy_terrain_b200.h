@@ -163,6 +163,11 @@ enum {
     BT_FLAG_FRUSTUM_CULL   = 1u << 6,  /* bt_select_tiles extension; default off = reference behaviour: tiles whose
                                           ten bounding points (corners + centre at min/max height) lie outside
                                           one of culling.planes[5] are neither refined nor emitted            */
+    /* bt_select_tiles extension, default off (docs/implementation.md:69 "The frustum culling uses a 2D min-max height data
+     * attachment to approximate the bounding volumes of each tile"): like BT_FLAG_FRUSTUM_CULL, but the height range of a tile's
+     * bounding points comes from the best RESIDENT atlas tile that contains it — the (min, max) table bt_atlas_update_minmax keeps
+     * per atlas slot (whole tile + 8 x 8 cells) — instead of the terrain-wide [min_height, max_height].                          */
+    BT_FLAG_MINMAX_CULL    = 1u << 9,
     /* BASELINE configs[2] ("trilinear + aniso sampling"): the reference's SAMPLER (linear / linear / linear, anisotropy clamp 16,
      * terrain_bind_group.rs:120-126; its fragment stage samples with textureSampleGrad, attachments.wgsl:16-20) evaluated per
      * vertex with the footprint of one grid step: N = min(ceil(Pmax / Pmin), 16) taps along the major axis, lod =
@@ -262,6 +267,10 @@ bt_status bt_atlas_sample(bt_terrain* terrain, uint32_t attachment, const bt_til
  * sampler (BT_FLAG_FILTER_TRILINEAR_ANISO) is used.  The chain of every slot lives in a second array per attachment.           */
 bt_status bt_atlas_generate_mips(bt_terrain* terrain, uint32_t attachment, uint32_t atlas_index, void* stream);
 bt_status bt_atlas_mips_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out, size_t* chain_bytes_per_slot);
+/* (min, max) table of the height tile in one atlas slot for BT_FLAG_MINMAX_CULL: 65 pairs of uint16 (the tile's centre region, then an
+ * 8 x 8 grid of cells over it; every region grown by one texel, zeros = no-data ignored).  Call after uploading / copying a height tile. */
+bt_status bt_atlas_update_minmax(bt_terrain* terrain, uint32_t atlas_index, void* stream);
+bt_status bt_atlas_minmax_device_ptr(bt_terrain* terrain, void** out);   /* uint16 [atlas_size][65][2] */
 /* device base pointer of an attachment's atlas array (for zero-copy interop / tests) */
 bt_status bt_atlas_device_ptr(bt_terrain* terrain, uint32_t attachment, void** out);
 

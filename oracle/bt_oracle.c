@@ -219,6 +219,69 @@ static int should_be_divided(const bt_view_config_uniform* vc, const bt_model_ap
  * planes of culling_bind_group.rs:25-38, with the bounding volume docs/implementation.md:69-70 describes approximated
  * by ten points: the four tile corners and the tile centre, each at min_height and max_height.  A tile is culled when
  * all ten points lie on the negative side of one plane. */
+/* ---- min / max-height culling (BT_FLAG_MINMAX_CULL; docs/implementation.md:69: "The frustum culling uses a 2D min-max height data
+ * attachment to approximate the bounding volumes of each tile") ----
+ * Per resident atlas tile a small table: entry 0 = (min, max) of the tile's centre region, entries 1..64 = an 8 x 8 grid of cells over
+ * it, every region grown by one texel (bilinear taps reach the neighbours) and zeros (no-data) ignored.  A geometry tile is bounded by
+ * the best resident atlas tile that CONTAINS it (the tile-tree entry of its centre at lod min(tile.lod, lod_count - 1)): the cell it
+ * falls into when it is at most 1/8 of the atlas tile wide, else the whole-tile entry; without a resident tile the terrain-wide
+ * [min_height, max_height] stays.  Conservative by construction: the bound only ever covers a superset of the tile. */
+#define BTO_MINMAX_CELLS 8
+void bto_tile_minmax(const uint16_t* tile, uint32_t T, uint32_t B, uint16_t out[(1 + BTO_MINMAX_CELLS * BTO_MINMAX_CELLS) * 2]) {
+    const uint32_t C_ = T - 2 * B;
+    for (uint32_t e = 0; e < 1 + BTO_MINMAX_CELLS * BTO_MINMAX_CELLS; ++e) {
+        uint32_t x0, x1, y0, y1;
+        if (e == 0) { x0 = B; x1 = B + C_; y0 = B; y1 = B + C_; }
+        else {
+            const uint32_t cx = (e - 1) % BTO_MINMAX_CELLS, cy = (e - 1) / BTO_MINMAX_CELLS;
+            x0 = B + cx * C_ / BTO_MINMAX_CELLS; x1 = B + (cx + 1) * C_ / BTO_MINMAX_CELLS;
+            y0 = B + cy * C_ / BTO_MINMAX_CELLS; y1 = B + (cy + 1) * C_ / BTO_MINMAX_CELLS;
+        }
+        x0 = x0 > 0 ? x0 - 1 : 0; y0 = y0 > 0 ? y0 - 1 : 0;
+        x1 = x1 + 1 < T ? x1 + 1 : T; y1 = y1 + 1 < T ? y1 + 1 : T;
+        uint32_t mn = 0xFFFFu, mx = 0u;
+        for (uint32_t y = y0; y < y1; ++y) for (uint32_t x = x0; x < x1; ++x) {
+            const uint32_t v = tile[(size_t)y * T + x];
+            if (v == 0) continue;
+            if (v < mn) mn = v;
+            if (v > mx) mx = v;
+        }
+        if (mx == 0u) mn = 0u;   /* no valid texel: (0, 0) */
+        out[2 * e] = (uint16_t)mn; out[2 * e + 1] = (uint16_t)mx;
+    }
+}
+
+typedef struct minmax_ctx {
+    const bt_tile_tree_entry* tile_tree;
+    const uint16_t* table;        /* [atlas_size][65][2] */
+    uint32_t lod_count, tree_size, atlas_size;
+    float terrain_min, terrain_max;
+} minmax_ctx;
+
+static void tile_height_bounds(const minmax_ctx* mc, const bt_tile* tile, float* hmin, float* hmax) {
+    *hmin = mc->terrain_min; *hmax = mc->terrain_max;
+    if (!mc->table || !mc->tile_tree) return;
+    coord c = {tile->side, tile->lod, {tile->x, tile->y}, {0.5f, 0.5f}};
+    const uint32_t L = tile->lod < mc->lod_count - 1u ? tile->lod : mc->lod_count - 1u;
+    change_lod(&c, L);
+    const uint32_t ts = mc->tree_size;
+    const bt_tile_tree_entry e = mc->tile_tree[((c.side * mc->lod_count + c.lod) * ts + c.xy[0] % ts) * ts + c.xy[1] % ts];
+    if (e.atlas_index >= mc->atlas_size || e.atlas_lod > L) return;       /* nothing resident (INVALID) or a malformed entry */
+    change_lod(&c, e.atlas_lod);
+    const uint32_t depth = tile->lod - e.atlas_lod;                       /* the tile is 2^-depth of the atlas tile wide */
+    uint32_t entry = 0;
+    if (depth >= 3u) {
+        uint32_t cx = bto_f32_to_u32(c.uv[0] * (float)BTO_MINMAX_CELLS), cy = bto_f32_to_u32(c.uv[1] * (float)BTO_MINMAX_CELLS);
+        if (cx > BTO_MINMAX_CELLS - 1u) cx = BTO_MINMAX_CELLS - 1u;
+        if (cy > BTO_MINMAX_CELLS - 1u) cy = BTO_MINMAX_CELLS - 1u;
+        entry = 1u + cy * BTO_MINMAX_CELLS + cx;
+    }
+    const uint16_t* mm = mc->table + ((size_t)e.atlas_index * (1 + BTO_MINMAX_CELLS * BTO_MINMAX_CELLS) + entry) * 2;
+    if (mm[1] == 0) return;                                               /* no valid texel in the region */
+    *hmin = o_mix(mc->terrain_min, mc->terrain_max, (float)mm[0] / 65535.0f);
+    *hmax = o_mix(mc->terrain_min, mc->terrain_max, (float)mm[1] / 65535.0f);
+}
+
 static int tile_outside_frustum(const bt_culling_uniform* cull, const bt_mesh_transform* mesh, int spherical,
                                 float min_height, float max_height, const bt_tile* tile) {
     static const float UV[5][2] = {{0.0f, 0.0f}, {1.0f, 0.0f}, {0.0f, 1.0f}, {1.0f, 1.0f}, {0.5f, 0.5f}};
@@ -254,6 +317,16 @@ void bto_select_tiles_ex(const bt_view_config_uniform* vc, const bt_model_approx
                          const bt_culling_uniform* culling, const bt_mesh_transform* mesh,
                          int spherical, int frustum_cull, float min_height, float max_height,
                          bt_tile* final_tiles, uint32_t capacity, bt_indirect* indirect, bto_select_result* result) {
+    bto_select_tiles_minmax(vc, approx, culling, mesh, spherical, frustum_cull, min_height, max_height, NULL, NULL, 0, 0,
+                            final_tiles, capacity, indirect, result);
+}
+
+void bto_select_tiles_minmax(const bt_view_config_uniform* vc, const bt_model_approximation* approx,
+                             const bt_culling_uniform* culling, const bt_mesh_transform* mesh,
+                             int spherical, int frustum_cull, float min_height, float max_height,
+                             const bt_tile_tree_entry* tile_tree, const uint16_t* minmax_table, uint32_t lod_count, uint32_t atlas_size,
+                             bt_tile* final_tiles, uint32_t capacity, bt_indirect* indirect, bto_select_result* result) {
+    minmax_ctx mc = {tile_tree, minmax_table, lod_count, vc->tree_size, atlas_size, min_height, max_height};
     /* The reference keeps parents and children in ONE buffer used as a double-ended stack
      * (refine_tiles.wgsl:9-11); executed with invocations in id order this is a FIFO queue:
      * children are read back in the order they were written.  We keep two growable arrays.   */
@@ -268,7 +341,11 @@ void bto_select_tiles_ex(const bt_view_config_uniform* vc, const bt_model_approx
         uint32_t n_nxt = 0;
         for (uint32_t i = 0; i < n_cur; ++i) {
             bt_tile tile = cur[i];
-            if (frustum_cull && tile_outside_frustum(culling, mesh, spherical, min_height, max_height, &tile)) continue;
+            if (frustum_cull) {
+                float hmin, hmax;
+                tile_height_bounds(&mc, &tile, &hmin, &hmax);      /* the terrain-wide range unless a min / max table is given */
+                if (tile_outside_frustum(culling, mesh, spherical, hmin, hmax, &tile)) continue;
+            }
             if (should_be_divided(vc, approx, culling, mesh, spherical, &tile)) {
                 if ((size_t)n_nxt + 4 > cap_b) { cap_b *= 2; nxt = (bt_tile*)realloc(nxt, cap_b * sizeof(bt_tile)); }
                 for (uint32_t c = 0; c < 4; ++c) { /* subdivide — refine_tiles.wgsl:24-31 */

@@ -44,6 +44,15 @@ void bto_select_tiles_ex(const bt_view_config_uniform* vc, const bt_model_approx
                          int spherical, int frustum_cull, float min_height, float max_height,
                          bt_tile* final_tiles, uint32_t capacity, bt_indirect* indirect, bto_select_result* result);
 
+/* min / max-height culling (BT_FLAG_MINMAX_CULL): per-atlas-tile bounds table (65 (min, max) pairs: whole tile + 8 x 8 cells) and the
+ * select variant that bounds every tile with it (tile_tree / minmax_table NULL = terrain-wide bounds = bto_select_tiles_ex) */
+void bto_tile_minmax(const uint16_t* tile, uint32_t T, uint32_t B, uint16_t out[130]);
+void bto_select_tiles_minmax(const bt_view_config_uniform* vc, const bt_model_approximation* approx,
+                             const bt_culling_uniform* culling, const bt_mesh_transform* mesh,
+                             int spherical, int frustum_cull, float min_height, float max_height,
+                             const bt_tile_tree_entry* tile_tree, const uint16_t* minmax_table, uint32_t lod_count, uint32_t atlas_size,
+                             bt_tile* final_tiles, uint32_t capacity, bt_indirect* indirect, bto_select_result* result);
+
 /* ---- per-frame: vertex generation ---- */
 typedef struct bto_vertex_inputs {
     bt_view_config_uniform    view_config;

@@ -73,6 +73,9 @@ def lib() -> C.CDLL:
         "bto_select_tiles_ex": (None, [P(F.ViewConfigUniform), P(F.ModelApproximation), P(F.CullingUniform), P(F.MeshTransform), i32, i32,
                                        f32, f32, P(F.Tile), u32, P(F.Indirect), P(SelectResult)]),
         "bto_gen_vertices": (None, [P(VertexInputs), u64, u64, vp, i32]),
+        "bto_tile_minmax": (None, [vp, u32, u32, vp]),
+        "bto_select_tiles_minmax": (None, [P(F.ViewConfigUniform), P(F.ModelApproximation), P(F.CullingUniform), P(F.MeshTransform), i32, i32,
+                                           f32, f32, vp, vp, u32, u32, P(F.Tile), u32, P(F.Indirect), P(SelectResult)]),
         "bto_pyramid_create": (vp, [u32, u32, u32, u32, u32]),
         "bto_pyramid_destroy": (None, [vp]),
         "bto_pyramid_add_dataset": (None, [vp, P(F.Dataset)]),
@@ -196,6 +199,25 @@ def select_tiles(vc, approx, cull, mesh, spherical: bool, capacity: int | None =
                               min_height, max_height, tiles, cap, C.byref(ind), C.byref(res))
     arr = np.frombuffer(tiles, dtype=np.uint32).reshape(-1, 4)[: res.final_count].copy()
     return arr, ind, res
+
+
+def tile_minmax(tile: np.ndarray, B: int) -> np.ndarray:
+    out = np.zeros((65, 2), dtype=np.uint16)
+    tile = np.ascontiguousarray(tile)
+    lib().bto_tile_minmax(tile.ctypes.data, tile.shape[0], B, out.ctypes.data)
+    return out
+
+
+def select_tiles_minmax(vc, approx, cull, mesh, spherical: bool, min_height: float, max_height: float, entries: np.ndarray, table: np.ndarray,
+                        lod_count: int, capacity: int | None = None):
+    """frustum cull with per-tile height bounds from the (min, max) table of the resident atlas tiles"""
+    cap = capacity if capacity is not None else vc.geometry_tile_count
+    tiles = (F.Tile * cap)()
+    ind, res = F.Indirect(), SelectResult()
+    entries, table = np.ascontiguousarray(entries, dtype=np.uint32), np.ascontiguousarray(table, dtype=np.uint16)
+    lib().bto_select_tiles_minmax(C.byref(vc), C.byref(approx), C.byref(cull), C.byref(mesh), int(spherical), 1, min_height, max_height,
+                                  entries.ctypes.data, table.ctypes.data, lod_count, len(table), tiles, cap, C.byref(ind), C.byref(res))
+    return np.frombuffer(tiles, dtype=np.uint32).reshape(-1, 4)[: res.final_count].copy(), ind, res
 
 
 VERTEX_DTYPE = np.dtype([("position", "<f4", 4), ("normal", "<f4", 3), ("uv", "<f4", 2), ("tile_index", "<u4")])
