@@ -25,9 +25,13 @@ pub const BT_FLAG_BLEND: u32 = 1 << 2;
 pub const BT_FLAG_HIGH_PRECISION: u32 = 1 << 3;
 pub const BT_FLAG_NORMALS: u32 = 1 << 4;
 pub const BT_FLAG_FRUSTUM_CULL: u32 = 1 << 6; // extension, default off (the reference does not cull at this commit)
+pub const BT_FLAG_FILTER_TRILINEAR_ANISO: u32 = 1 << 7; // configs[2] sampler: linear / linear / linear + anisotropy 16 per vertex
+pub const BT_FLAG_ALBEDO: u32 = 1 << 8;          // per-vertex albedo stream (bt_view_albedo_buffer)
+pub const BT_FLAG_MINMAX_CULL: u32 = 1 << 9;     // frustum cull with per-tile (min, max) height bounds
 
 macro_rules! opaque { ($($n:ident),*) => { $( #[repr(C)] pub struct $n { _p: [u8; 0] } )* } }
-opaque!(bt_context, bt_terrain, bt_view, bt_preprocessor, bt_tile_tree);
+opaque!(bt_context, bt_terrain, bt_view, bt_preprocessor, bt_tile_tree, bt_atlas_state, bt_comm, bt_view_batch);
+pub const BT_COMM_UNIQUE_ID_BYTES: usize = 128;
 
 /// `TileCoordinate` (src/math/coordinate.rs:156-166)
 #[repr(C)] #[derive(Clone, Copy, Debug, Default, PartialEq, Eq, Hash, Pod, Zeroable)]
@@ -84,7 +88,7 @@ pub struct bt_terrain_desc {
 }
 
 #[repr(C)] #[derive(Clone, Copy)]
-pub struct bt_view_desc { pub geometry_tile_count: u32, pub tree_size: u32, pub grid_size: u32, pub _pad: u32, pub max_vertices: u64 }
+pub struct bt_view_desc { pub geometry_tile_count: u32, pub tree_size: u32, pub grid_size: u32, pub readback_tile_capacity: u32, pub max_vertices: u64 }
 
 #[repr(C)]
 pub struct bt_view_frame {
@@ -136,78 +140,6 @@ pub struct bt_exchange_copy { pub tile: bt_tile, pub tile_row: u32, pub tile_col
 /// a decoded source image (`bt_image_load`): `pixels` is malloc'ed by the library, release it with `bt_image_free`
 #[repr(C)] pub struct bt_image { pub width: u32, pub height: u32, pub format: u32, pub _pad: u32, pub pixels: *mut c_void }
 
-// Every entry point of include/bevy_terrain_b200.h, generated by tools/gen_rust_ffi.py (argument names as in the header).
-#[link(name = "bevy_terrain_b200")]
-extern "C" {
-    pub fn bt_abi_version() -> u32;
-    pub fn bt_context_create(device: i32, out: *mut *mut bt_context) -> bt_status;
-    pub fn bt_context_destroy(ctx: *mut bt_context);
-    pub fn bt_last_error(ctx: *const bt_context) -> *const c_char;
-    pub fn bt_context_synchronize(ctx: *mut bt_context) -> bt_status;
-    pub fn bt_terrain_create(ctx: *mut bt_context, desc: *const bt_terrain_desc, out: *mut *mut bt_terrain) -> bt_status;
-    pub fn bt_terrain_destroy(terrain: *mut bt_terrain);
-    pub fn bt_atlas_upload_tile(terrain: *mut bt_terrain, attachment: u32, atlas_index: u32, texels: *const c_void, bytes: usize, stream: *mut c_void) -> bt_status;
-    pub fn bt_atlas_copy_tile(terrain: *mut bt_terrain, attachment: u32, atlas_index: u32, device_texels: *const c_void, bytes: usize, stream: *mut c_void) -> bt_status;
-    pub fn bt_atlas_download_tile(terrain: *mut bt_terrain, attachment: u32, atlas_index: u32, texels: *mut c_void, bytes: usize) -> bt_status;
-    pub fn bt_atlas_load_tile_file(terrain: *mut bt_terrain, attachment: u32, atlas_index: u32, directory: *const c_char, tile: *const bt_tile, stream: *mut c_void) -> bt_status;
-    pub fn bt_tile_config_load(path: *const c_char, tiles: *mut bt_tile, capacity: u32, count: *mut u32) -> bt_status;
-    pub fn bt_atlas_sample(terrain: *mut bt_terrain, attachment: u32, lookup: *const bt_tile_lookup, out: *mut f32) -> bt_status;
-    pub fn bt_atlas_device_ptr(terrain: *mut bt_terrain, attachment: u32, out: *mut *mut c_void) -> bt_status;
-    pub fn bt_view_create(terrain: *mut bt_terrain, desc: *const bt_view_desc, out: *mut *mut bt_view) -> bt_status;
-    pub fn bt_view_destroy(view: *mut bt_view);
-    pub fn bt_view_update(view: *mut bt_view, frame: *const bt_view_frame, stream: *mut c_void) -> bt_status;
-    pub fn bt_select_tiles(view: *mut bt_view, flags: u32, stream: *mut c_void) -> bt_status;
-    pub fn bt_gen_vertices(view: *mut bt_view, flags: u32, stream: *mut c_void, out: *mut bt_vertex_buffer) -> bt_status;
-    pub fn bt_view_run_frame(view: *mut bt_view, frame: *const bt_view_frame, select_flags: u32, gen_flags: u32, stream: *mut c_void, tiles: *mut bt_tile, capacity: u32, count: *mut u32, indirect: *mut bt_indirect, vertices: *mut bt_vertex_buffer) -> bt_status;
-    pub fn bt_view_readback(view: *mut bt_view, tiles: *mut bt_tile, capacity: u32, count: *mut u32, indirect: *mut bt_indirect, stream: *mut c_void) -> bt_status;
-    pub fn bt_view_select_status(view: *mut bt_view, dropped_parents: *mut u32, stream: *mut c_void) -> bt_status;
-    pub fn bt_view_download_vertices(view: *mut bt_view, out: *mut bt_vertex, first: u64, count: u64, stream: *mut c_void) -> bt_status;
-    pub fn bt_view_device_ptrs(view: *mut bt_view, final_tiles: *mut *mut bt_tile, indirect: *mut *mut bt_indirect) -> bt_status;
-    pub fn bt_terrain_model_planar(position: *const f64, side_length: f64, min_height: f32, max_height: f32, out: *mut bt_terrain_model);
-    pub fn bt_terrain_model_sphere(position: *const f64, radius: f64, min_height: f32, max_height: f32, out: *mut bt_terrain_model);
-    pub fn bt_terrain_model_ellipsoid(position: *const f64, major_axis: f64, minor_axis: f64, min_height: f32, max_height: f32, out: *mut bt_terrain_model);
-    pub fn bt_terrain_view_config_default(out: *mut bt_terrain_view_config);
-    pub fn bt_terrain_model_scale(model: *const bt_terrain_model) -> f64;
-    pub fn bt_terrain_model_mesh_transform(model: *const bt_terrain_model, out: *mut bt_mesh_transform);
-    pub fn bt_view_config_uniform_from(cfg: *const bt_terrain_view_config, model: *const bt_terrain_model, out: *mut bt_view_config_uniform);
-    pub fn bt_model_approximation_compute(model: *const bt_terrain_model, view_world_position: *const f64, origin_lod: u32, approximate_height: f32, out: *mut bt_model_approximation) -> bt_status;
-    pub fn bt_tile_tree_create(model: *const bt_terrain_model, cfg: *const bt_terrain_view_config, lod_count: u32, atlas_size: u32, out: *mut *mut bt_tile_tree) -> bt_status;
-    pub fn bt_tile_tree_destroy(tree: *mut bt_tile_tree);
-    pub fn bt_tile_tree_add_existing(tree: *mut bt_tile_tree, tiles: *const bt_tile, count: u32) -> bt_status;
-    pub fn bt_tile_tree_update(tree: *mut bt_tile_tree, view_world_position: *const f64, loads: *mut bt_tile_load, cap: u32, count: *mut u32) -> bt_status;
-    pub fn bt_tile_tree_mark_loaded(tree: *mut bt_tile_tree, tile: *const bt_tile) -> bt_status;
-    pub fn bt_tile_tree_entries(tree: *mut bt_tile_tree, entries: *mut bt_tile_tree_entry, entry_cap: u32, origins_xy: *mut u32, origin_cap: u32) -> bt_status;
-    pub fn bt_tile_tree_set_approximate_height(tree: *mut bt_tile_tree, h: f32);
-    pub fn bt_tile_tree_sample_lookup(tree: *mut bt_tile_tree, sample_world_position: *const f64, lookups: *mut bt_tile_lookup, lookup_count: *mut u32, blend_ratio: *mut f32) -> bt_status;
-    pub fn bt_preprocessor_create(ctx: *mut bt_context, kind: u32, attachments: *const bt_attachment_config, attachment_count: u32, lod_count: u32, shard: bt_shard, out: *mut *mut bt_preprocessor) -> bt_status;
-    pub fn bt_preprocessor_destroy(p: *mut bt_preprocessor);
-    pub fn bt_preprocessor_add_datasets(p: *mut bt_preprocessor, datasets: *const bt_dataset, count: u32) -> bt_status;
-    pub fn bt_preprocessor_reserve(p: *mut bt_preprocessor, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_run_split_downsample(p: *mut bt_preprocessor, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_run_stitch(p: *mut bt_preprocessor, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_run(p: *mut bt_preprocessor, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_plan(p: *mut bt_preprocessor) -> bt_status;
-    pub fn bt_preprocessor_plan_tiles(p: *mut bt_preprocessor, attachment: u32, tiles: *mut bt_tile, kinds: *mut u32, cap: u32, count: *mut u32) -> bt_status;
-    pub fn bt_preprocessor_plan_exchange(p: *mut bt_preprocessor, kind: u32, unpack: u32, out: *mut bt_exchange_copy, cap: u32, count: *mut u32) -> bt_status;
-    pub fn bt_preprocessor_halo_bytes(p: *mut bt_preprocessor, send_bytes_per_rank: *mut u64) -> bt_status;
-    pub fn bt_preprocessor_halo_pack(p: *mut bt_preprocessor, device_send: *mut c_void, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_halo_unpack(p: *mut bt_preprocessor, device_gathered: *const c_void, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_roots_bytes(p: *mut bt_preprocessor, send_bytes_per_rank: *mut u64) -> bt_status;
-    pub fn bt_preprocessor_roots_pack(p: *mut bt_preprocessor, device_send: *mut c_void, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_roots_unpack_and_finish(p: *mut bt_preprocessor, device_gathered: *const c_void, stream: *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_tile_count(p: *mut bt_preprocessor, attachment: u32, count: *mut u32) -> bt_status;
-    pub fn bt_preprocessor_list_tiles(p: *mut bt_preprocessor, attachment: u32, tiles: *mut bt_tile, cap: u32, count: *mut u32) -> bt_status;
-    pub fn bt_preprocessor_tile_device_ptr(p: *mut bt_preprocessor, attachment: u32, tile: *const bt_tile, out: *mut *mut c_void) -> bt_status;
-    pub fn bt_preprocessor_get_tile(p: *mut bt_preprocessor, attachment: u32, tile: *const bt_tile, host_out: *mut c_void, bytes: usize) -> bt_status;
-    pub fn bt_preprocessor_save(p: *mut bt_preprocessor, attachment: u32, directory: *const c_char) -> bt_status;
-    pub fn bt_culling_planes(clip_from_world: *const f32, planes: *mut f32);
-    pub fn bt_generate_mipmaps(ctx: *mut bt_context, format: u32, texture_size: u32, mip_level_count: u32, device_mip0: *const c_void, device_mips_out: *mut c_void, stream: *mut c_void) -> bt_status;
-    pub fn bt_synth_source(ctx: *mut bt_context, format: u32, width: u32, height: u32, x0: u32, y0: u32, seed: u32, holes: u32, device_out: *mut c_void, stream: *mut c_void) -> bt_status;
-    pub fn bt_image_load(path: *const c_char, out: *mut bt_image, error: *mut c_char, error_capacity: usize) -> bt_status;
-    pub fn bt_image_free(image: *mut bt_image);
-    pub fn bt_selftest_numerics(ctx: *mut bt_context, x: *const f32, log2_out: *mut f32, n: u32, mismatches: *mut u32) -> bt_status;
-    pub fn bt_device_alloc(ctx: *mut bt_context, bytes: usize, out: *mut *mut c_void) -> bt_status;
-    pub fn bt_device_free(ctx: *mut bt_context, ptr: *mut c_void) -> bt_status;
-    pub fn bt_memcpy_h2d(ctx: *mut bt_context, dst_device: *mut c_void, src_host: *const c_void, bytes: usize, stream: *mut c_void) -> bt_status;
-    pub fn bt_memcpy_d2h(ctx: *mut bt_context, dst_host: *mut c_void, src_device: *const c_void, bytes: usize, stream: *mut c_void) -> bt_status;
-}
+// Every entry point of include/bevy_terrain_b200.h: GENERATED by `python tools/gen_rust_ffi.py --write` into ffi_extern.rs
+// (tests/test_abi.py regenerates it and fails when the committed file is stale).
+include!("ffi_extern.rs");

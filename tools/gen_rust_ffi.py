@@ -13,7 +13,7 @@ SCALARS = {"uint32_t": "u32", "uint64_t": "u64", "int32_t": "i32", "int": "i32",
 
 
 def rust_type(ctype: str, array: bool) -> str:
-    ctype = ctype.strip()
+    ctype = re.sub(r"\*\s*const\b", "*", ctype.strip())     # `T* const*`: the inner const has no Rust counterpart in a raw pointer chain
     const = ctype.startswith("const ")
     base = ctype.replace("const ", "").strip()
     stars = base.count("*")
@@ -26,10 +26,31 @@ def rust_type(ctype: str, array: bool) -> str:
     return r
 
 
+def generate() -> str:
+    import io
+    buf = io.StringIO()
+    old = sys.stdout
+    sys.stdout = buf
+    try:
+        emit()
+    finally:
+        sys.stdout = old
+    return buf.getvalue()
+
+
 def main():
+    text = generate()
+    if "--write" in sys.argv:
+        open(os.path.join(ROOT, "rust", "bevy_terrain_b200", "src", "ffi_extern.rs"), "w").write(text)
+    else:
+        sys.stdout.write(text)
+
+
+def emit():
     src = open(os.path.join(ROOT, "include", "bevy_terrain_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = re.findall(r"^\s*((?:const\s+)?[A-Za-z_][\w]*\s*\**)\s*(bt_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.M)
+    print("// GENERATED from include/bevy_terrain_b200.h by tools/gen_rust_ffi.py — do not edit")
     print('#[link(name = "bevy_terrain_b200")]\nextern "C" {')
     for ret, name, params in protos:
         args = []
@@ -45,7 +66,7 @@ def main():
         rret = "" if ret == "void" else f" -> {rust_type(ret, False)}"
         print(f"    pub fn {name}({', '.join(args)}){rret};")
     print("}")
-    print(f"// {len(protos)} entry points", file=sys.stderr)
+    print(f"// {len(protos)} entry points")
 
 
 if __name__ == "__main__":
