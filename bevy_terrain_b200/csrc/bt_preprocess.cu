@@ -67,6 +67,7 @@ struct JobPlan {  // all task tables of one job, concatenated: [split | downsamp
     std::vector<PyramidTask> tasks;
     std::vector<DatasetDevice> datasets;
     Range split, stitch;
+    float split_src_per_px[2] = {0.0f, 0.0f};   // densest source of the split tasks, in source texels per tile pixel (x, y): sizes the kernel's stage buffers
     uint32_t stitch_local = 0;   // the first stitch_local tasks of `stitch` need nothing from another rank (run while the exchange is in flight)
     std::vector<Level> levels;
     PyramidTask* d_tasks = nullptr;
@@ -308,6 +309,11 @@ struct bt_preprocessor {
             x.row_begin = d.row_count ? d.row_begin : 0;
             x.row_count = d.row_count ? d.row_count : d.height;
             P.datasets.push_back(x);
+            const double px = (double)(s.cfg.texture_size - 2u * s.cfg.border_size) * (double)(1u << ((d.lod_end - 1u) & 31u));   // centre pixels across the unit square
+            const double rx = (double)d.bottom_right[0] - (double)d.top_left[0], ry = (double)d.bottom_right[1] - (double)d.top_left[1];
+            const float qx = rx > 0.0 ? (float)((double)d.width / (px * rx)) : 1e9f, qy = ry > 0.0 ? (float)((double)d.height / (px * ry)) : 1e9f;
+            P.split_src_per_px[0] = di == 0 ? qx : std::max(P.split_src_per_px[0], qx);
+            P.split_src_per_px[1] = di == 0 ? qy : std::max(P.split_src_per_px[1], qy);
             collect(ji, d, di, d.lod_end - 1, tasks);
         }
         P.split = Range{0u, (uint32_t)tasks.size()};
@@ -381,7 +387,8 @@ struct bt_preprocessor {
         Store& s = stores[j.attachment];
         const JobPlan& P = j.plan;
         if (with_split) {
-            BT_CUDA(ctx, bt_launch_split(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + P.split.begin, P.split.count, P.d_datasets, stream));
+            BT_CUDA(ctx, bt_launch_split(s.arena, s.tile_bytes, s.cfg.texture_size, s.cfg.border_size, s.cfg.format, P.d_tasks + P.split.begin, P.split.count, P.d_datasets,
+                                         P.split_src_per_px[0], P.split_src_per_px[1], stream));
             for (uint32_t i = P.split.begin; i < P.split.begin + P.split.count; ++i) s.written[P.tasks[i].slot] = 1;
         }
         for (const Level& lv : P.levels) {

@@ -83,7 +83,8 @@ struct bt_view_batch {
 
 extern "C" {
 cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
-                            const btd::PyramidTask* tasks, uint32_t n_tasks, const btd::DatasetDevice* datasets, cudaStream_t stream);
+                            const btd::PyramidTask* tasks, uint32_t n_tasks, const btd::DatasetDevice* datasets,
+                            float src_per_px_x, float src_per_px_y, cudaStream_t stream);
 cudaError_t bt_launch_downsample(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
                                  const btd::PyramidTask* tasks, uint32_t n_tasks, cudaStream_t stream);
 cudaError_t bt_launch_stitch(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,

@@ -90,6 +90,7 @@ __device__ __forceinline__ void store_packet(texel* row, uint32_t x, uint32_t T,
 // split — split.wgsl:18-43
 // ------------------------------------------------------------------------------------------------
 #include "split_kernel.cuh"
+#include "split_staged.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // downsample — downsample.wgsl:12-40
@@ -375,15 +376,60 @@ __global__ void synth_kernel(uint32_t format, uint32_t width, uint32_t height, u
 
 using namespace btd;
 
+// Stage geometry of split_staged_kernel for sources that hold at most `src_per_px_x` x `src_per_px_y` texels per tile pixel
+// (rows == 0: the window of a band would not fit, every CTA uses global loads).  BT_SPLIT_STAGES / BT_SPLIT_BANDS override
+// the defaults (tuning only).
+static SplitStageGeom split_stage_geometry(uint32_t T, uint32_t texel_bytes, float src_per_px_x, float src_per_px_y) {
+    static const int env_stages = [] { const char* e = getenv("BT_SPLIT_STAGES"); return e ? atoi(e) : 0; }();
+    static const int env_bands = [] { const char* e = getenv("BT_SPLIT_BANDS"); return e ? atoi(e) : 0; }();
+    SplitStageGeom G{0u, 16u, 2u, 8u};
+    if (env_stages == 1 || env_stages == 2) G.stages = (uint32_t)env_stages;
+    if (env_bands >= 1 && env_bands <= SPLIT_MAX_BANDS) G.bands = (uint32_t)env_bands;
+    const uint32_t bands_in_tile = (T + SPLIT_ROWS - 1) / SPLIT_ROWS;
+    if (G.bands > bands_in_tile) G.bands = bands_in_tile;
+    if (!(src_per_px_x > 0.0f) || !(src_per_px_y > 0.0f) || src_per_px_x > 4.0f || src_per_px_y > 4.0f) return G;
+    const uint32_t cols = T < (uint32_t)SPLIT_STAGE_COLS ? T : (uint32_t)SPLIT_STAGE_COLS;
+    // ix advances by at most src_per_px (+ rounding) per pixel: the window of `cols` pixels spans <= cols * ratio + 3 texels;
+    // + 16 bytes for the alignment of its first byte
+    const uint32_t win_cols = (uint32_t)ceilf((float)cols * src_per_px_x) + 3u;
+    const uint32_t win_rows = (uint32_t)ceilf((float)SPLIT_ROWS * src_per_px_y) + 3u;
+    G.pitch = ((win_cols * texel_bytes + 15u) & ~15u) + 16u;
+    G.rows = win_rows;
+    static const int env_budget = [] { const char* e = getenv("BT_SPLIT_SMEM_KB"); return e ? atoi(e) : 0; }();
+    uint32_t budget = texel_bytes == 2u ? 44u * 1024u : 75u * 1024u;   // R16: 5 CTAs of 128 threads per SM (two stages); Rgba8: 3 of 256 (one stage)
+    if (env_budget > 0) budget = (uint32_t)env_budget * 1024u;
+    if (split_staged_smem_bytes(G) > budget) G.stages = 1u;
+    if (split_staged_smem_bytes(G) > budget) G.rows = 0u;
+    return G;
+}
+
 extern "C" cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
                                        const PyramidTask* tasks, uint32_t n_tasks, const DatasetDevice* datasets,
-                                       cudaStream_t stream) {
+                                       float src_per_px_x, float src_per_px_y, cudaStream_t stream) {
     if (n_tasks == 0) return cudaSuccess;
     PyramidLayout L{static_cast<unsigned char*>(arena), tile_bytes, T, B, T - 2u * B, format};
+    static const bool legacy = [] { const char* e = getenv("BT_SPLIT_LEGACY"); return e && e[0] == '1'; }();
+    const SplitStageGeom G = split_stage_geometry(T, format == BT_FORMAT_R16 ? 2u : 4u, src_per_px_x, src_per_px_y);
+    const uint32_t smem = split_staged_smem_bytes(G);
+    if (!legacy) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(split_staged_kernel<BT_FORMAT_R16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(split_staged_kernel<BT_FORMAT_RGBA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+    }
     for (uint32_t first = 0; first < n_tasks; first += 65535u) {  // gridDim.y limit
         const uint32_t n = (n_tasks - first) < 65535u ? (n_tasks - first) : 65535u;
         const uint32_t row_groups = (T + SPLIT_ROWS - 1) / SPLIT_ROWS;
-        if (format == BT_FORMAT_R16) {
+        if (!legacy) {
+            const uint32_t col_blocks = (T + SPLIT_STAGE_COLS - 1) / SPLIT_STAGE_COLS, band_groups = (row_groups + G.bands - 1) / G.bands;
+            if (format == BT_FORMAT_R16)
+                split_staged_kernel<BT_FORMAT_R16><<<dim3(col_blocks * band_groups, n), StagedCfg<BT_FORMAT_R16>::THREADS, smem, stream>>>(L, tasks + first, datasets, G);
+            else
+                split_staged_kernel<BT_FORMAT_RGBA8><<<dim3(col_blocks * band_groups, n), StagedCfg<BT_FORMAT_RGBA8>::THREADS, smem, stream>>>(L, tasks + first, datasets, G);
+        } else if (format == BT_FORMAT_R16) {
             const uint32_t packets = ((T + SplitCfg<BT_FORMAT_R16>::N - 1) / SplitCfg<BT_FORMAT_R16>::N) * row_groups;
             split_kernel<BT_FORMAT_R16><<<dim3((packets + PYR_THREADS - 1) / PYR_THREADS, n), PYR_THREADS, 0, stream>>>(L, tasks + first, datasets);
         } else {
