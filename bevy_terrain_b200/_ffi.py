@@ -221,6 +221,12 @@ def _declare(lib: C.CDLL) -> None:
         "bt_tile_tree_update": (i32, [vp, P(f64), P(TileLoad), u32, P(u32)]),
         "bt_tile_tree_mark_loaded": (i32, [vp, P(Tile)]),
         "bt_tile_tree_entries": (i32, [vp, P(TileTreeEntry), u32, P(u32), u32]),
+        "bt_clipmap_create": (i32, [vp, vp, P(vp)]),
+        "bt_clipmap_destroy": (None, [vp]),
+        "bt_clipmap_update": (i32, [vp, P(f64), P(TileLoad), u32, P(u32), vp]),
+        "bt_clipmap_entries": (i32, [vp, vp]),
+        "bt_clipmap_download": (i32, [vp, P(TileTreeEntry), u32, P(u32), u32, vp]),
+        "bt_clipmap_transfer_bytes": (None, [vp, P(C.c_uint64), P(C.c_uint64)]),
         "bt_tile_tree_set_approximate_height": (None, [vp, f32]),
         "bt_tile_tree_sample_lookup": (i32, [vp, P(f64), P(TileLookup), P(u32), P(f32)]),
         "bt_atlas_sample": (i32, [vp, u32, P(TileLookup), P(f32)]),

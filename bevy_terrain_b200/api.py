@@ -308,7 +308,9 @@ class TileTree:
     `prepare` produce exactly the uniform/storage contents the reference uploads each frame.
     """
 
-    def __init__(self, tile_atlas: TileAtlas, view_config: F.TerrainViewConfig, max_vertices: int = 0):
+    def __init__(self, tile_atlas: TileAtlas, view_config: F.TerrainViewConfig, max_vertices: int = 0, device_clipmap: bool = False):
+        """device_clipmap=True keeps the slots, origins and best-tile table on the GPU (bt_clipmap): compute_requests and
+        adjust_to_tile_atlas then run the device twins and a frame uploads no table."""
         self.atlas, self.ctx, self.view_config = tile_atlas, tile_atlas.ctx, view_config
         lib = self.ctx.lib
         self.model = tile_atlas.model
@@ -329,10 +331,28 @@ class TileTree:
         self.origins = (F.u32 * (self.side_count * self.lod_count * 2))()
         self.frame = F.ViewFrame()
         self.h2d_bytes = 0
+        self._clipmap = None
+        if device_clipmap:
+            self._clipmap = C.c_void_p()
+            self.ctx.check(lib.bt_clipmap_create(self._view, self._tree, C.byref(self._clipmap)))
 
     @staticmethod
-    def new(tile_atlas: TileAtlas, view_config: F.TerrainViewConfig, max_vertices: int = 0) -> "TileTree":
-        return TileTree(tile_atlas, view_config, max_vertices)
+    def new(tile_atlas: TileAtlas, view_config: F.TerrainViewConfig, max_vertices: int = 0, device_clipmap: bool = False) -> "TileTree":
+        return TileTree(tile_atlas, view_config, max_vertices, device_clipmap)
+
+    def download_table(self, stream: int = 0):
+        """(entries, origins) as the kernels see them: read back from the device with a clipmap, the host copies otherwise"""
+        if self._clipmap is None:
+            return np.frombuffer(self.entries, dtype=np.uint32).reshape(-1, 2).copy(), np.frombuffer(self.origins, dtype=np.uint32).copy()
+        e = (F.TileTreeEntry * self.entry_count)()
+        o = (F.u32 * len(self.origins))()
+        self.ctx.check(self.ctx.lib.bt_clipmap_download(self._clipmap, e, self.entry_count, o, len(o), C.c_void_p(stream)))
+        return np.frombuffer(e, dtype=np.uint32).reshape(-1, 2).copy(), np.frombuffer(o, dtype=np.uint32).copy()
+
+    def clipmap_transfer_bytes(self):
+        h, d = C.c_uint64(), C.c_uint64()
+        self.ctx.lib.bt_clipmap_transfer_bytes(self._clipmap, C.byref(h), C.byref(d))
+        return h.value, d.value
 
     # -- main-world systems (plugin.rs:46-56) -------------------------------------------------------
     def add_existing_tiles(self, tiles: np.ndarray) -> None:
@@ -347,7 +367,10 @@ class TileTree:
         n = F.u32()
         cap = self.atlas.atlas_size
         loads = (F.TileLoad * cap)()
-        self.ctx.check(self.ctx.lib.bt_tile_tree_update(self._tree, vp, loads, cap, C.byref(n)))
+        if self._clipmap is not None:
+            self.ctx.check(self.ctx.lib.bt_clipmap_update(self._clipmap, vp, loads, cap, C.byref(n), None))
+        else:
+            self.ctx.check(self.ctx.lib.bt_tile_tree_update(self._tree, vp, loads, cap, C.byref(n)))
         return [((l.tile.side, l.tile.lod, l.tile.x, l.tile.y), l.atlas_index) for l in loads[: n.value]]
 
     def mark_loaded(self, tile) -> None:
@@ -355,6 +378,9 @@ class TileTree:
         self.ctx.check(self.ctx.lib.bt_tile_tree_mark_loaded(self._tree, C.byref(t)))
 
     def adjust_to_tile_atlas(self) -> None:
+        if self._clipmap is not None:
+            self.ctx.check(self.ctx.lib.bt_clipmap_entries(self._clipmap, None))
+            return
         self.ctx.check(self.ctx.lib.bt_tile_tree_entries(self._tree, self.entries, self.entry_count, self.origins, len(self.origins)))
 
     def sample_attachment(self, attachment: int, sample_world_position) -> np.ndarray:
@@ -396,7 +422,7 @@ class TileTree:
             f.culling.world_position[:] = pos32     # CullingUniform::from(&ExtractedView)
             f.view_world_position[:] = pos32        # bevy view.world_position
             f.tile_tree_entry_count = self.entry_count
-            f.tile_tree = C.cast(self.entries, C.POINTER(F.TileTreeEntry))
+            f.tile_tree = C.cast(self.entries, C.POINTER(F.TileTreeEntry)) if self._clipmap is None else None
             f.origins = C.cast(self.origins, C.POINTER(F.u32))
         else:
             f = frame
@@ -414,7 +440,7 @@ class TileTree:
         f.culling.world_position[:] = pos32
         f.view_world_position[:] = pos32
         f.tile_tree_entry_count = self.entry_count
-        f.tile_tree = C.cast(self.entries, C.POINTER(F.TileTreeEntry))
+        f.tile_tree = C.cast(self.entries, C.POINTER(F.TileTreeEntry)) if self._clipmap is None else None
         f.origins = C.cast(self.origins, C.POINTER(F.u32))
         return f
 
@@ -463,6 +489,9 @@ class TileTree:
         return out
 
     def close(self) -> None:
+        if getattr(self, "_clipmap", None):
+            self.ctx.lib.bt_clipmap_destroy(self._clipmap)
+            self._clipmap = None
         if self._view:
             self.ctx.lib.bt_view_destroy(self._view)
             self._view = C.c_void_p()

@@ -422,7 +422,12 @@ bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) {
     if (!v || !f) return BT_ERR_INVALID_ARG;
     bt_terrain* t = v->terrain;
     bt_context* ctx = t->ctx;
-    if (f->tile_tree_entry_count != v->tile_tree_entries || !f->tile_tree) {
+    const bool host_table = f->tile_tree != nullptr;
+    if (!host_table && !v->device_table) {
+        ctx->set_error("bt_view_update: tile_tree is NULL and no bt_clipmap maintains this view's table on the device");
+        return BT_ERR_INVALID_ARG;
+    }
+    if (host_table && f->tile_tree_entry_count != v->tile_tree_entries) {
         ctx->set_error("bt_view_update: tile_tree_entry_count %u, expected sides*lod_count*tree_size^2 = %u", f->tile_tree_entry_count, v->tile_tree_entries);
         return BT_ERR_INVALID_ARG;
     }
@@ -461,12 +466,15 @@ bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) {
     }
     U.mesh = t->desc.transform;
     std::memcpy(U.view_world_position, f->view_world_position, sizeof(float) * 3);
-    std::memcpy(v->h_tile_tree, f->tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
     cudaStream_t s = (cudaStream_t)stream;
     BT_CUDA(ctx, cudaMemcpyAsync(v->d_uniforms, v->h_uniforms, sizeof(ViewUniforms), cudaMemcpyHostToDevice, s));
-    BT_CUDA(ctx, cudaMemcpyAsync(v->d_tile_tree, v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaMemcpyHostToDevice, s));
+    v->h2d_bytes_last_update = sizeof(ViewUniforms);
+    if (host_table) {   // (with a device clipmap the table is already where the kernels read it)
+        std::memcpy(v->h_tile_tree, f->tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+        BT_CUDA(ctx, cudaMemcpyAsync(v->d_tile_tree, v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaMemcpyHostToDevice, s));
+        v->h2d_bytes_last_update += (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry);
+    }
     BT_CUDA(ctx, cudaEventRecord(v->staging_free, s));
-    v->h2d_bytes_last_update = sizeof(ViewUniforms) + (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry);
     v->updated = true;
     return BT_OK;
 }

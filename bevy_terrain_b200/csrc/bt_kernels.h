@@ -66,6 +66,19 @@ struct GenFilterInputs {
     uint32_t mip_level_count, mip_chain_texels, albedo_attachment, _pad;
 };
 
+// ---- device clipmap (clipmap.cu) ----
+struct ClipmapParams {   // one frame's inputs of clipmap_update_kernel
+    double position[3], scale[3];      // TerrainModel world_from_local (scale, translation) — terrain_model.rs:61-82
+    double view_world_position[3];
+    double view_uv[2];                 // Coordinate::from_world_position(view) — coordinate.rs:69-108 (one f64 evaluation, done by the host)
+    double load_distance;              // pre-multiplied by the model scale (tile_tree.rs:148)
+    float approximate_height;
+    uint32_t view_side, kind, tree_size, lod_count, side_count, _pad;
+};
+struct ClipmapSlot { uint32_t x, y, requested, valid; };                 // TileState of one (side, lod, x % tree, y % tree) slot
+struct ClipmapLists { uint32_t n_released, n_requested, _pad[2]; };        // header of the list buffer: [header | released | requested]
+struct ClipmapLoaded { uint32_t side_lod, x, y, atlas_index; };           // open-addressing set of the loaded tiles; side_lod 0xFFFFFFFF = empty
+
 struct TileHashTask { uint64_t key; uint32_t slot, _pad; };   // key = hash of (attachment-independent) tile coordinate
 
 struct DatasetDevice {

@@ -71,6 +71,7 @@ struct bt_view {
     uint32_t h_tiles_cap = 0;
     size_t h2d_bytes_last_update = 0;
     bool updated = false;
+    bool device_table = false;       // a bt_clipmap writes d_tile_tree on the device: bt_view_update may omit the host table
 };
 
 // several views of one frame refined by ONE select_tiles launch (gridDim.x = views)
@@ -82,6 +83,11 @@ struct bt_view_batch {
 };
 
 extern "C" {
+cudaError_t bt_launch_clipmap_update(const btd::ClipmapParams* params, btd::ClipmapSlot* slots, uint32_t* origins, btd::ClipmapLists* lists,
+                                     bt_tile* released, bt_tile* requested, cudaStream_t stream);
+cudaError_t bt_launch_clipmap_entries(const btd::ClipmapSlot* slots, uint32_t n, uint32_t tree_size, uint32_t lod_count,
+                                      const btd::ClipmapLoaded* loaded, uint32_t hash_capacity, bt_tile_tree_entry* entries, cudaStream_t stream);
+uint32_t bt_clipmap_hash(uint32_t side_lod, uint32_t x, uint32_t y);
 cudaError_t bt_launch_split(void* arena, uint64_t tile_bytes, uint32_t T, uint32_t B, uint32_t format,
                             const btd::PyramidTask* tasks, uint32_t n_tasks, const btd::DatasetDevice* datasets,
                             float src_per_px_x, float src_per_px_y, cudaStream_t stream);

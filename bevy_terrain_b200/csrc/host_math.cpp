@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/bevy_terrain_b200.h"
+#include "bt_runtime.h"   // only the device clipmap at the end of this file touches the GPU
 
 namespace {
 
@@ -424,6 +425,7 @@ struct bt_atlas_state {
     std::deque<std::pair<TileKey, uint32_t>> unused_tiles;  // (coordinate, atlas_index), LRU order
     std::unordered_set<TileKey, TileKeyHash> existing_tiles;
     std::vector<bt_tile_load> pending_loads;
+    uint64_t loaded_version = 0;   // bumped whenever the set of loaded tiles may have changed (device clipmaps re-upload their copy)
 
     explicit bt_atlas_state(uint32_t n) : atlas_size(n) {
         for (uint32_t i = 0; i < n; ++i) unused_tiles.emplace_back(kInvalidTile, i);  // TileAtlasState::new — tile_atlas.rs:302-325
@@ -434,6 +436,7 @@ struct bt_atlas_state {
         auto t = unused_tiles.front();
         unused_tiles.pop_front();
         tile_states.erase(t.first);
+        loaded_version += 1;
         *atlas_index = t.second;
         return true;
     }
@@ -685,6 +688,7 @@ bt_status bt_tile_tree_mark_loaded(bt_tile_tree* tree, const bt_tile* tile) {
     auto it = tree->state->tile_states.find(TileKey{tile->side, tile->lod, tile->x, tile->y});
     if (it == tree->state->tile_states.end()) return BT_ERR_NOT_FOUND;
     it->second.loaded = true;
+    tree->state->loaded_version += 1;
     return BT_OK;
 }
 
@@ -697,6 +701,175 @@ bt_status bt_tile_tree_entries(bt_tile_tree* tree, bt_tile_tree_entry* entries, 
         std::memcpy(origins_xy, tree->origins.data(), tree->origins.size() * sizeof(uint32_t));
     }
     return BT_OK;
+}
+
+
+// ================================================================================================
+// Device clipmap: the per-frame half of TileTree on the GPU (clipmap.cu).  The slots, the origins and the
+// best-tile table stay in device memory; the host keeps what only it can do: Coordinate::from_world_position of the view (one
+// f64 evaluation, with the ellipsoid projection), the TileAtlasState bookkeeping and the loads themselves.
+// ================================================================================================
+struct bt_clipmap {
+    bt_view* view = nullptr;
+    bt_tile_tree* tree = nullptr;
+    bt_context* ctx = nullptr;
+    uint32_t entries = 0, hash_capacity = 0;
+    btd::ClipmapParams* d_params = nullptr;
+    btd::ClipmapParams* h_params = nullptr;      // pinned
+    btd::ClipmapSlot* d_slots = nullptr;
+    uint32_t* d_origins = nullptr;
+    unsigned char* d_lists = nullptr;            // [ClipmapLists | released[entries] | requested[entries]]
+    unsigned char* h_lists = nullptr;            // pinned
+    size_t lists_bytes = 0;
+    btd::ClipmapLoaded* d_loaded = nullptr;
+    btd::ClipmapLoaded* h_loaded = nullptr;      // pinned
+    uint64_t uploaded_version = ~0ull;
+    size_t h2d_bytes_last_update = 0, d2h_bytes_last_update = 0;
+};
+
+bt_status bt_clipmap_create(bt_view* view, bt_tile_tree* tree, bt_clipmap** out) {
+    if (!view || !tree || !out) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = view->terrain->ctx;
+    const uint32_t entries = tree->side_count * tree->lod_count * tree->cfg.tree_size * tree->cfg.tree_size;
+    if (entries != view->tile_tree_entries || tree->cfg.tree_size != view->desc.tree_size) {
+        ctx->set_error("bt_clipmap_create: the tree has %u entries (tree_size %u), the view %u (tree_size %u)", entries, tree->cfg.tree_size,
+                       view->tile_tree_entries, view->desc.tree_size);
+        return BT_ERR_INVALID_ARG;
+    }
+    for (const TreeSlot& slot : tree->tiles) if (slot.requested) {
+        ctx->set_error("bt_clipmap_create: the tree has already been updated on the host; create the clipmap first");
+        return BT_ERR_INVALID_ARG;
+    }
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    bt_clipmap* c = new bt_clipmap();
+    c->view = view; c->tree = tree; c->ctx = ctx; c->entries = entries;
+    c->hash_capacity = 64;
+    while (c->hash_capacity < 4u * tree->atlas_size) c->hash_capacity *= 2u;
+    c->lists_bytes = sizeof(btd::ClipmapLists) + 2 * (size_t)entries * sizeof(bt_tile);
+    auto fail = [&](cudaError_t e) { ctx->set_error("bt_clipmap_create: %s", cudaGetErrorString(e)); bt_clipmap_destroy(c); return e == cudaErrorMemoryAllocation ? BT_ERR_OUT_OF_MEMORY : BT_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&c->d_params, sizeof(btd::ClipmapParams))) != cudaSuccess) return fail(e);
+    if ((e = cudaMallocHost((void**)&c->h_params, sizeof(btd::ClipmapParams))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void**)&c->d_slots, (size_t)entries * sizeof(btd::ClipmapSlot))) != cudaSuccess) return fail(e);
+    if ((e = cudaMemset(c->d_slots, 0, (size_t)entries * sizeof(btd::ClipmapSlot))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void**)&c->d_origins, (size_t)tree->side_count * tree->lod_count * 2 * sizeof(uint32_t))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void**)&c->d_lists, c->lists_bytes)) != cudaSuccess) return fail(e);
+    if ((e = cudaMallocHost((void**)&c->h_lists, c->lists_bytes)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void**)&c->d_loaded, (size_t)c->hash_capacity * sizeof(btd::ClipmapLoaded))) != cudaSuccess) return fail(e);
+    if ((e = cudaMallocHost((void**)&c->h_loaded, (size_t)c->hash_capacity * sizeof(btd::ClipmapLoaded))) != cudaSuccess) return fail(e);
+    view->device_table = true;
+    *out = c;
+    return BT_OK;
+}
+
+void bt_clipmap_destroy(bt_clipmap* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    // the view's outstanding requests go back to the shared state, as bt_tile_tree_destroy does for host-side slots
+    if (c->d_slots && c->tree) {
+        std::vector<btd::ClipmapSlot> slots(c->entries);
+        if (cudaMemcpy(slots.data(), c->d_slots, slots.size() * sizeof(btd::ClipmapSlot), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const uint32_t per = c->tree->cfg.tree_size * c->tree->cfg.tree_size;
+            for (uint32_t i = 0; i < c->entries; ++i) if (slots[i].valid && slots[i].requested) {
+                const uint32_t sl = i / per, side = sl / c->tree->lod_count, lod = sl - side * c->tree->lod_count;
+                c->tree->state->release_tile(TileKey{side, lod, slots[i].x, slots[i].y});
+            }
+        }
+    }
+    if (c->view) c->view->device_table = false;
+    cudaFree(c->d_params); cudaFreeHost(c->h_params); cudaFree(c->d_slots); cudaFree(c->d_origins); cudaFree(c->d_lists);
+    cudaFreeHost(c->h_lists); cudaFree(c->d_loaded); cudaFreeHost(c->h_loaded);
+    delete c;
+}
+
+// Twin of bt_tile_tree_update: one parameter block up, one kernel, the request / release lists down; the TileAtlasState
+// bookkeeping (same order: released first, then requested — tile_atlas.rs:574-601) runs on the host and reports the loads.
+bt_status bt_clipmap_update(bt_clipmap* c, const double view_world_position[3], bt_tile_load* loads, uint32_t cap, uint32_t* count, void* stream) {
+    if (!c || !view_world_position) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = c->ctx;
+    bt_tile_tree& t = *c->tree;
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    t.view_world_position = D3{view_world_position[0], view_world_position[1], view_world_position[2]};
+    const Coordinate view = coordinate_from_world(t.model, t.view_world_position);
+    btd::ClipmapParams& P = *c->h_params;
+    for (int i = 0; i < 3; ++i) { P.position[i] = t.model.position[i]; P.scale[i] = t.model.scale[i]; P.view_world_position[i] = view_world_position[i]; }
+    P.view_uv[0] = view.uv.x; P.view_uv[1] = view.uv.y;
+    P.load_distance = t.load_distance;
+    P.approximate_height = t.approximate_height;
+    P.view_side = view.side; P.kind = t.model.kind; P.tree_size = t.cfg.tree_size; P.lod_count = t.lod_count; P.side_count = t.side_count; P._pad = 0;
+    BT_CUDA(ctx, cudaMemcpyAsync(c->d_params, c->h_params, sizeof(P), cudaMemcpyHostToDevice, s));
+    bt_tile* d_released = reinterpret_cast<bt_tile*>(c->d_lists + sizeof(btd::ClipmapLists));
+    BT_CUDA(ctx, bt_launch_clipmap_update(c->d_params, c->d_slots, c->d_origins, reinterpret_cast<btd::ClipmapLists*>(c->d_lists), d_released,
+                                          d_released + c->entries, s));
+    BT_CUDA(ctx, cudaMemcpyAsync(c->h_lists, c->d_lists, c->lists_bytes, cudaMemcpyDeviceToHost, s));
+    BT_CUDA(ctx, cudaStreamSynchronize(s));
+    c->h2d_bytes_last_update = sizeof(P);
+    c->d2h_bytes_last_update = c->lists_bytes;
+    const btd::ClipmapLists& H = *reinterpret_cast<const btd::ClipmapLists*>(c->h_lists);
+    const bt_tile* released = reinterpret_cast<const bt_tile*>(c->h_lists + sizeof(btd::ClipmapLists));
+    const bt_tile* requested = released + c->entries;
+    bt_atlas_state& as = *t.state;
+    for (uint32_t i = 0; i < H.n_released; ++i) as.release_tile(TileKey{released[i].side, released[i].lod, released[i].x, released[i].y});
+    bt_status st = BT_OK;
+    for (uint32_t i = 0; i < H.n_requested; ++i)
+        if (!as.request_tile(TileKey{requested[i].side, requested[i].lod, requested[i].x, requested[i].y})) st = BT_ERR_CAPACITY;
+    const uint32_t n = (uint32_t)as.pending_loads.size();
+    if (count) *count = n;
+    if (loads) for (uint32_t i = 0; i < n && i < cap; ++i) loads[i] = as.pending_loads[i];
+    if (loads && cap >= n) as.pending_loads.clear();
+    if (st != BT_OK) ctx->set_error("bt_clipmap_update: atlas out of indices");
+    return st;
+}
+
+// Twin of bt_tile_tree_entries (TileTree::adjust_to_tile_atlas): writes the view's table in place.  The set of loaded tiles
+// goes up only when it changed since the last call.
+bt_status bt_clipmap_entries(bt_clipmap* c, void* stream) {
+    if (!c) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = c->ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    bt_atlas_state& as = *c->tree->state;
+    c->h2d_bytes_last_update = 0;
+    if (as.loaded_version != c->uploaded_version) {
+        BT_CUDA(ctx, cudaStreamSynchronize(s));   // the previous upload out of h_loaded has finished
+        const uint32_t mask = c->hash_capacity - 1u;
+        std::memset(c->h_loaded, 0xFF, (size_t)c->hash_capacity * sizeof(btd::ClipmapLoaded));
+        for (const auto& kv : as.tile_states) {
+            if (!kv.second.loaded) continue;
+            const uint32_t key = (kv.first.side << 8) | kv.first.lod;
+            uint32_t i = bt_clipmap_hash(key, kv.first.x, kv.first.y) & mask;
+            while (c->h_loaded[i].side_lod != 0xFFFFFFFFu) i = (i + 1u) & mask;
+            c->h_loaded[i] = btd::ClipmapLoaded{key, kv.first.x, kv.first.y, kv.second.atlas_index};
+        }
+        BT_CUDA(ctx, cudaMemcpyAsync(c->d_loaded, c->h_loaded, (size_t)c->hash_capacity * sizeof(btd::ClipmapLoaded), cudaMemcpyHostToDevice, s));
+        c->uploaded_version = as.loaded_version;
+        c->h2d_bytes_last_update = (size_t)c->hash_capacity * sizeof(btd::ClipmapLoaded);
+    }
+    BT_CUDA(ctx, bt_launch_clipmap_entries(c->d_slots, c->entries, c->tree->cfg.tree_size, c->tree->lod_count, c->d_loaded, c->hash_capacity,
+                                           c->view->d_tile_tree, s));
+    return BT_OK;
+}
+
+// test / debugging read-back of what the kernels maintain (table + origins)
+bt_status bt_clipmap_download(bt_clipmap* c, bt_tile_tree_entry* entries, uint32_t entry_cap, uint32_t* origins_xy, uint32_t origin_cap, void* stream) {
+    if (!c || !entries || entry_cap < c->entries) return BT_ERR_INVALID_ARG;
+    bt_context* ctx = c->ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    BT_CUDA(ctx, cudaSetDevice(ctx->device));
+    BT_CUDA(ctx, cudaMemcpyAsync(entries, c->view->d_tile_tree, (size_t)c->entries * sizeof(bt_tile_tree_entry), cudaMemcpyDeviceToHost, s));
+    if (origins_xy) {
+        const uint32_t n = c->tree->side_count * c->tree->lod_count * 2u;
+        if (origin_cap < n) return BT_ERR_INVALID_ARG;
+        BT_CUDA(ctx, cudaMemcpyAsync(origins_xy, c->d_origins, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    BT_CUDA(ctx, cudaStreamSynchronize(s));
+    return BT_OK;
+}
+
+void bt_clipmap_transfer_bytes(const bt_clipmap* c, uint64_t* h2d, uint64_t* d2h) {
+    if (h2d) *h2d = c ? c->h2d_bytes_last_update : 0;
+    if (d2h) *d2h = c ? c->d2h_bytes_last_update : 0;
 }
 
 }  // extern "C"

@@ -55,7 +55,8 @@ template <> struct Fmt<BT_FORMAT_RGBA8> {
     using texel = uchar4;
     static constexpr int PX_PER_THREAD = 4;
     static __device__ __forceinline__ Px4 decode(uchar4 t) {
-        const float2 xy = unorm8x2_to_float(t.x, t.y), zw = unorm8x2_to_float(t.z, t.w);   // == (float)c / 255.0f, two per instruction
+        float2 xy, zw;   // == (float)c / 255.0f, two per instruction, without the XU pipe (16 I2F per output pixel bound the Rgba8 downsample)
+        unorm8x4_to_float(*reinterpret_cast<const uint32_t*>(&t), xy, zw);
         return Px4{{xy.x, xy.y, zw.x, zw.y}};
     }
     static __device__ __forceinline__ uchar4 zero() { return make_uchar4(0, 0, 0, 0); }
@@ -510,6 +511,10 @@ __global__ void selftest_kernel(const float* __restrict__ x, float* __restrict__
         if (p16.x != (float)i / m16 || p16.y != (float)(65535u - i) / m16) atomicAdd(&mismatches[0], 1u);
         if (i < 256u) {
             if (unorm8_to_float(i) != (float)i / m8) atomicAdd(&mismatches[1], 1u);
+            float2 q0, q1;
+            unorm8x4_to_float(i | ((255u - i) << 8) | (((i * 7u) & 255u) << 16) | (((i * 13u + 5u) & 255u) << 24), q0, q1);
+            if (q0.x != (float)i / m8 || q0.y != (float)(255u - i) / m8 || q1.x != (float)((i * 7u) & 255u) / m8 || q1.y != (float)((i * 13u + 5u) & 255u) / m8)
+                atomicAdd(&mismatches[1], 1u);
             const float2 p8 = unorm8x2_to_float(i, 255u - i);
             if (p8.x != (float)i / m8 || p8.y != (float)(255u - i) / m8) atomicAdd(&mismatches[1], 1u);
         }

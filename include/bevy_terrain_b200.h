@@ -408,6 +408,30 @@ bt_status bt_tile_tree_mark_loaded(bt_tile_tree* tree, const bt_tile* tile);
 /* TileTree::adjust_to_tile_atlas (tile_tree.rs:363-374) -> entries + origins for bt_view_frame */
 bt_status bt_tile_tree_entries(bt_tile_tree* tree, bt_tile_tree_entry* entries, uint32_t entry_cap,
                                uint32_t* origins_xy, uint32_t origin_cap);
+
+/* ---- the same clipmap on the DEVICE --------------------------------------------------------------------
+ * bt_clipmap is the GPU twin of the per-frame half of bt_tile_tree for ONE view: the slots (TileState per side x lod x
+ * tree_size^2), the origins and the best-tile table live in device memory, the table directly in the view's buffer that
+ * select_tiles / gen_vertices read.  A frame costs one 152-byte parameter upload, one single-CTA kernel (origins, f64 tile
+ * distances, the request / release state machine of tile_tree.rs:268-333, lists compacted in the reference's loop order)
+ * and the list read-back; TileAtlasState (slot allocation, LRU, load queue) stays on the host because only the host can
+ * load tiles.  Results are those of bt_tile_tree_update / bt_tile_tree_entries on the same inputs (tests/test_gpu_clipmap.py).
+ * Create the clipmap on a tree that has not been updated yet; from then on drive the tree through the clipmap only.
+ * With a clipmap attached, bt_view_update accepts frame->tile_tree == NULL (no per-frame table upload).                    */
+typedef struct bt_clipmap bt_clipmap;
+bt_status bt_clipmap_create(bt_view* view, bt_tile_tree* tree, bt_clipmap** out);
+void      bt_clipmap_destroy(bt_clipmap* clipmap);     /* releases the view's outstanding requests, like bt_tile_tree_destroy */
+/* twin of bt_tile_tree_update (same outputs, same order of the load requests) */
+bt_status bt_clipmap_update(bt_clipmap* clipmap, const double view_world_position[3],
+                            bt_tile_load* loads, uint32_t cap, uint32_t* count, void* stream);
+/* twin of bt_tile_tree_entries: recomputes the view's device table (call after bt_tile_tree_mark_loaded of the new tiles);
+ * the set of loaded tiles is re-uploaded only when it changed                                                              */
+bt_status bt_clipmap_entries(bt_clipmap* clipmap, void* stream);
+/* read-back of the device table + origins (tests, debugging) */
+bt_status bt_clipmap_download(bt_clipmap* clipmap, bt_tile_tree_entry* entries, uint32_t entry_cap,
+                              uint32_t* origins_xy, uint32_t origin_cap, void* stream);
+/* bytes the last bt_clipmap_update / bt_clipmap_entries call moved host->device and device->host */
+void      bt_clipmap_transfer_bytes(const bt_clipmap* clipmap, uint64_t* h2d, uint64_t* d2h);
 void      bt_tile_tree_set_approximate_height(bt_tile_tree* tree, float h);
 /* CPU-side sampling chain of TileTree::approximate_height (tile_tree.rs:376-386 -> sample_attachment,
  * terrain_data/mod.rs:267-295): surface position, TileTree::compute_blend (tile_tree.rs:223-237) and TileTree::lookup_tile

@@ -30,7 +30,7 @@ pub const BT_FLAG_ALBEDO: u32 = 1 << 8;          // per-vertex albedo stream (bt
 pub const BT_FLAG_MINMAX_CULL: u32 = 1 << 9;     // frustum cull with per-tile (min, max) height bounds
 
 macro_rules! opaque { ($($n:ident),*) => { $( #[repr(C)] pub struct $n { _p: [u8; 0] } )* } }
-opaque!(bt_context, bt_terrain, bt_view, bt_preprocessor, bt_tile_tree, bt_atlas_state, bt_comm, bt_view_batch);
+opaque!(bt_context, bt_terrain, bt_view, bt_preprocessor, bt_tile_tree, bt_atlas_state, bt_comm, bt_view_batch, bt_clipmap);
 pub const BT_COMM_UNIQUE_ID_BYTES: usize = 128;
 
 /// `TileCoordinate` (src/math/coordinate.rs:156-166)

@@ -314,6 +314,26 @@ impl TerrainView {
 
 impl Drop for TerrainView { fn drop(&mut self) { unsafe { ffi::bt_view_destroy(self.raw) } } }
 
+/// The device twin of the per-frame half of `TileTree` (`bt_clipmap`): slots, origins and the best-tile table stay in GPU
+/// memory; `update` = `TileTree::compute_requests` + `TileAtlas::update`, `adjust_to_tile_atlas` writes the view's table in place.
+pub struct DeviceClipmap { ctx: *const ffi::bt_context, raw: *mut ffi::bt_clipmap }
+impl DeviceClipmap {
+    pub fn new(view: &TerrainView, tree: &TileTree) -> Result<Self> {
+        let mut raw = ptr::null_mut();
+        check(view.ctx, unsafe { ffi::bt_clipmap_create(view.raw, tree.raw, &mut raw) })?;
+        Ok(Self { ctx: view.ctx, raw })
+    }
+    pub fn update(&mut self, view_world_position: [f64; 3], atlas_size: u32) -> Result<Vec<ffi::bt_tile_load>> {
+        let mut loads = vec![ffi::bt_tile_load::default(); atlas_size as usize];
+        let mut n = 0u32;
+        check(self.ctx, unsafe { ffi::bt_clipmap_update(self.raw, view_world_position.as_ptr(), loads.as_mut_ptr(), atlas_size, &mut n, ptr::null_mut()) })?;
+        loads.truncate(n as usize);
+        Ok(loads)
+    }
+    pub fn adjust_to_tile_atlas(&mut self) -> Result<()> { check(self.ctx, unsafe { ffi::bt_clipmap_entries(self.raw, ptr::null_mut()) }) }
+}
+impl Drop for DeviceClipmap { fn drop(&mut self) { unsafe { ffi::bt_clipmap_destroy(self.raw) } } }
+
 /// `TilingPrepassNode::run` (src/render/tiling_prepass.rs:204-271) for every (terrain, view) pair of a frame: the reference loops on the
 /// host with 63 dispatches per pair; here all views are refined by ONE launch (one CTA per view).
 pub struct TilingPrepass { ctx: *const ffi::bt_context, raw: *mut ffi::bt_view_batch }
@@ -333,6 +353,6 @@ impl Drop for TilingPrepass { fn drop(&mut self) { unsafe { ffi::bt_view_batch_d
 /// `TerrainMaterialPlugin` and `TerrainPreprocessPlugin` are Bevy ECS glue (plugin.rs:32, terrain.rs:62-98, terrain_material.rs:437,
 /// preprocess/mod.rs:255): they stay in the reference crate and call the types above at the points INTEGRATION.md lists.
 pub mod prelude {
-    pub use crate::{AttachmentConfig, AttachmentFormat, Comm, Context, PreprocessDataset, Preprocessor, SourceImage, SphericalDataset, TerrainConfig,
+    pub use crate::{AttachmentConfig, AttachmentFormat, Comm, Context, DeviceClipmap, PreprocessDataset, Preprocessor, SourceImage, SphericalDataset, TerrainConfig,
                     TerrainModel, TerrainView, TerrainViewConfig, TileAtlas, TileTree, TilingPrepass};
 }
