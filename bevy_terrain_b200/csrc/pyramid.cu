@@ -647,14 +647,14 @@ extern "C" cudaError_t bt_launch_tile_hash(const void* arena, uint64_t tile_byte
 }
 
 // ------------------------------------------------------------------------------------------------
-// (min, max) table of one height tile for the min / max-height cull: block e = region e (0: centre, 1..64: 8 x 8 cells)
+// (min, max) table of one height tile for the min / max-height cull: region 0 = centre, 1..64 = 8 x 8 cells.  Block e computes cell
+// e + 1; the grown cells cover the grown centre exactly, so region 0 is the min / max over the 64 cells (second, one-warp launch).
 // ------------------------------------------------------------------------------------------------
 namespace btd {
 __global__ void __launch_bounds__(128) tile_minmax_kernel(const uint16_t* __restrict__ tile, uint32_t T, uint32_t B, uint16_t* __restrict__ out) {
-    const uint32_t e = blockIdx.x, C_ = T - 2u * B;
+    const uint32_t e = blockIdx.x + 1u, C_ = T - 2u * B;
     uint32_t x0, x1, y0, y1;
-    if (e == 0u) { x0 = B; x1 = B + C_; y0 = B; y1 = B + C_; }
-    else {
+    {
         const uint32_t cx = (e - 1u) % 8u, cy = (e - 1u) / 8u;
         x0 = B + cx * C_ / 8u; x1 = B + (cx + 1u) * C_ / 8u;
         y0 = B + cy * C_ / 8u; y1 = B + (cy + 1u) * C_ / 8u;
@@ -680,10 +680,25 @@ __global__ void __launch_bounds__(128) tile_minmax_kernel(const uint16_t* __rest
         out[2u * e + 1u] = (uint16_t)mx;
     }
 }
+__global__ void __launch_bounds__(64) tile_minmax_whole_kernel(uint16_t* __restrict__ out) {
+    uint32_t mn = out[2u * (threadIdx.x + 1u)], mx = out[2u * (threadIdx.x + 1u) + 1u];
+    if (mx == 0u) mn = 0xFFFFu;   // a cell without data
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    __shared__ uint32_t smn[2], smx[2];
+    smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        mn = min(smn[0], smn[1]); mx = max(smx[0], smx[1]);
+        if (mx == 0u) mn = 0u;
+        out[0] = (uint16_t)mn;
+        out[1] = (uint16_t)mx;
+    }
+}
 }  // namespace btd
 
 extern "C" cudaError_t bt_launch_tile_minmax(const uint16_t* tile, uint32_t T, uint32_t B, uint16_t* out130, cudaStream_t stream) {
-    btd::tile_minmax_kernel<<<65, 128, 0, stream>>>(tile, T, B, out130);
+    btd::tile_minmax_kernel<<<64, 128, 0, stream>>>(tile, T, B, out130);
+    btd::tile_minmax_whole_kernel<<<1, 64, 0, stream>>>(out130);
     return cudaGetLastError();
 }
 

@@ -412,7 +412,7 @@ bt_status bt_tile_tree_entries(bt_tile_tree* tree, bt_tile_tree_entry* entries, 
 /* ---- the same clipmap on the DEVICE --------------------------------------------------------------------
  * bt_clipmap is the GPU twin of the per-frame half of bt_tile_tree for ONE view: the slots (TileState per side x lod x
  * tree_size^2), the origins and the best-tile table live in device memory, the table directly in the view's buffer that
- * select_tiles / gen_vertices read.  A frame costs one 152-byte parameter upload, one single-CTA kernel (origins, f64 tile
+ * select_tiles / gen_vertices read.  A frame costs one 128-byte parameter upload, one single-CTA kernel (origins, f64 tile
  * distances, the request / release state machine of tile_tree.rs:268-333, lists compacted in the reference's loop order)
  * and the list read-back; TileAtlasState (slot allocation, LRU, load queue) stays on the host because only the host can
  * load tiles.  Results are those of bt_tile_tree_update / bt_tile_tree_entries on the same inputs (tests/test_gpu_clipmap.py).
