@@ -823,14 +823,28 @@ bt_status bt_preprocessor_run_sharded(bt_preprocessor* p, bt_comm* comm, void* s
     cudaStream_t stream = (cudaStream_t)stream_;
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (p->shard.world == 1) return bt_preprocessor_run(p, stream_);
+    // BT_SHARDED_TIMING=1: per-phase device times of every wave on stderr (diagnostics; synchronises at the end of the call)
+    static const bool timing = [] { const char* e = getenv("BT_SHARDED_TIMING"); return e && e[0] == '1'; }();
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* name) {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        marks.emplace_back(name, e);
+    };
     for (;;) {
         const std::vector<uint32_t> wave = next_wave(p);
         if (wave.empty()) break;
         bt_status st;
+        mark("start");
         for (uint32_t ji : wave) if ((st = p->prepare_job(ji, stream)) != BT_OK) return st;
         if ((st = build_exchange_tables(p, wave, stream)) != BT_OK) return st;
         // 1. communication-free part: split + downsample of this rank's band, down to the shard boundary level
+        // (the jobs of a wave run one after the other: launching the R16 and the Rgba8 split side by side on two streams was
+        //  measured 12 % SLOWER at N = 2 - their CTAs partition an SM's shared memory and registers badly)
         for (uint32_t ji : wave) if ((st = p->run_split_downsample_job(ji, stream)) != BT_OK) return st;
+        mark("split+downsample");
         // 2. pack every job's sub-root tiles and border strips
         std::vector<bt_comm_segment> segs;
         for (uint32_t ji : wave) {
@@ -841,6 +855,7 @@ bt_status bt_preprocessor_run_sharded(bt_preprocessor* p, bt_comm* comm, void* s
                 segs.push_back(bt_comm_segment{p->d_send + j.xt.send_off[k], p->d_recv + j.xt.recv_off[k], (size_t)j.xt.bytes[k]});
             }
         }
+        mark("pack");
         // 3. ONE grouped collective for the whole wave, on the communicator's stream ...
         BT_CUDA(ctx, cudaEventRecord(comm->ready, stream));
         BT_CUDA(ctx, cudaStreamWaitEvent(comm->stream, comm->ready, 0));
@@ -848,8 +863,10 @@ bt_status bt_preprocessor_run_sharded(bt_preprocessor* p, bt_comm* comm, void* s
         BT_CUDA(ctx, cudaEventRecord(comm->done, comm->stream));
         // 4. ... while the compute stream stitches every tile whose neighbours are all local
         for (uint32_t ji : wave) if ((st = p->run_stitch_job(ji, stream, 0)) != BT_OK) return st;
+        mark("interior stitch");
         // 5. behind the collective: unpack, the replicated top levels, and the boundary tiles' stitch
         BT_CUDA(ctx, cudaStreamWaitEvent(stream, comm->done, 0));
+        mark("wait for all-gather");
         for (uint32_t ji : wave) {
             Job& j = p->jobs[ji];
             if (j.xt.bytes[1]) {
@@ -861,6 +878,20 @@ bt_status bt_preprocessor_run_sharded(bt_preprocessor* p, bt_comm* comm, void* s
             j.halo_done = true;
             if ((st = p->run_stitch_job(ji, stream, 1)) != BT_OK) return st;
         }
+        mark("unpack + top levels + boundary stitch");
+    }
+    if (timing && !marks.empty()) {
+        cudaStreamSynchronize(stream);
+        std::string line = "bt_preprocessor_run_sharded rank " + std::to_string(comm->rank) + ":";
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            char buf[96];
+            snprintf(buf, sizeof(buf), " %s %.3f ms;", marks[i].first, ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto& m : marks) cudaEventDestroy(m.second);
     }
     return BT_OK;
 }
