@@ -197,6 +197,10 @@ split_staged_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks, cons
 #pragma unroll
             for (int i = 0; i < N; ++i) c0[i] = (col_centre >> i & 1u) != 0u ? c0[i] - cwin0 : 0u;
         }
+        bool adjacent[N];   // column i samples the texel right of column i - 1's (staged offsets: c0[i] == c0[i - 1] + one texel)
+        adjacent[0] = false;
+#pragma unroll
+        for (int i = 1; i < N; ++i) adjacent[i] = c0[i] == c0[i - 1] + (uint32_t)sizeof(texel);
         float2 hA[V2], hB[V2];
         float mA[N], mB[N];            // product of the two texels' red channels: > 0 iff both are valid (textureGather(0, ..) != 0)
         int rowA = -1, rowB = -1;
@@ -242,7 +246,10 @@ split_staged_kernel(PyramidLayout L, const PyramidTask* __restrict__ tasks, cons
                         a = __ldg(static_cast<const uint32_t*>(ptr_add_u32(r, c0[i])));
                         b = __ldg(static_cast<const uint32_t*>(ptr_add_u32(r, c1[i])));
                     }
-                    unorm8x4_to_float(a, t0[2 * i], t0[2 * i + 1]);
+                    // the x0 texel of column i is the x1 texel of column i - 1 unless the source skips a column between them
+                    // (every ~127 columns at the native ratio): reuse its decode (the same bits) instead of repeating it
+                    if (STAGED && i > 0 && adjacent[i]) { t0[2 * i] = t1[2 * i - 2]; t0[2 * i + 1] = t1[2 * i - 1]; }
+                    else unorm8x4_to_float(a, t0[2 * i], t0[2 * i + 1]);
                     unorm8x4_to_float(b, t1[2 * i], t1[2 * i + 1]);
                     m[i] = t0[2 * i].x * t1[2 * i].x;
                 }
