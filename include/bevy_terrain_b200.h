@@ -420,7 +420,8 @@ bt_status bt_tile_tree_entries(bt_tile_tree* tree, bt_tile_tree_entry* entries, 
  * With a clipmap attached, bt_view_update accepts frame->tile_tree == NULL (no per-frame table upload).                    */
 typedef struct bt_clipmap bt_clipmap;
 bt_status bt_clipmap_create(bt_view* view, bt_tile_tree* tree, bt_clipmap** out);
-void      bt_clipmap_destroy(bt_clipmap* clipmap);     /* releases the view's outstanding requests, like bt_tile_tree_destroy */
+void      bt_clipmap_destroy(bt_clipmap* clipmap);     /* releases the view's outstanding requests, like bt_tile_tree_destroy;
+                                                          destroy the clipmap BEFORE its view and its tree                      */
 /* twin of bt_tile_tree_update (same outputs, same order of the load requests) */
 bt_status bt_clipmap_update(bt_clipmap* clipmap, const double view_world_position[3],
                             bt_tile_load* loads, uint32_t cap, uint32_t* count, void* stream);
