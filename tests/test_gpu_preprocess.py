@@ -208,3 +208,29 @@ def test_preprocess_errors_are_reported_not_fatal(ctx):
         assert ctx.lib.bt_preprocessor_get_tile(pre._h, 0, C.byref(F.Tile(0, 0, 0, 0)), C.c_void_p(1), 32 * 32 * 2) == F.BT_ERR_NOT_FOUND
     finally:
         pre.close()
+
+
+@pytest.mark.parametrize("fmt,src_w,src_h,T,B,L", [
+    (F.BT_FORMAT_R16, 256, 256, 64, 2, 3),      # ratio 1.07, 512-byte rows: the TMA-staged form of the split
+    (F.BT_FORMAT_R16, 128, 136, 64, 2, 3),      # source coarser than the tile grid (ratio 0.53 / 0.57): windows of ~10 rows
+    (F.BT_FORMAT_R16, 928, 904, 64, 2, 3),      # ratio 3.87 / 3.77: the largest windows the stage geometry accepts (limit 4)
+    (F.BT_FORMAT_R16, 1008, 1000, 64, 2, 3),    # ratio 4.2: no staging, every CTA gathers from global memory
+    (F.BT_FORMAT_RGBA8, 252, 260, 64, 2, 3),    # Rgba8, 1008-byte rows (16-byte aligned): staged, one stage, shared-texel decode reuse
+    (F.BT_FORMAT_RGBA8, 250, 250, 64, 2, 3),    # Rgba8, 1000-byte rows: not 16-byte aligned -> global form
+    (F.BT_FORMAT_R16, 1400, 1320, 640, 2, 2),   # tiles wider than 512 pixels: two column blocks per band group
+    (F.BT_FORMAT_RGBA8, 1024, 1024, 520, 4, 2), # ratio exactly 1 (C = 512), two column blocks, Rgba8
+])
+def test_split_forms_and_stage_geometries(ctx, fmt, src_w, src_h, T, B, L):
+    """Both instantiations of split_staged_kernel (TMA-staged windows / global gather), windows from half a source row per output
+    row to four, one and two column blocks: every tile byte-exact against the oracle."""
+    from bevy_terrain_b200 import api
+    src = O.synth_source(fmt, src_w, src_h, seed=0x5EED0000 + src_w, holes=(src_w % 16 == 0))
+    pyr = O.Pyramid(F.BT_KIND_PLANAR, fmt, T, B, L)
+    pyr.add_datasets([O.make_dataset(src, lod_range=(0, L))])
+    pyr.run()
+    pre = api.Preprocessor(ctx, _config(api, F.BT_KIND_PLANAR, L, T, B, fmt))
+    try:
+        pre.preprocess_tile(api.PreprocessDataset(pixels=src, lod_range=range(0, L))).run()
+        assert _compare(pre, pyr) == (4 ** L - 1) // 3
+    finally:
+        pre.close()
