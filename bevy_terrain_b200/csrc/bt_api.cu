@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "bt_device.cuh"
 #include "bt_kernels.h"
 #include "bt_runtime.h"
@@ -338,7 +340,8 @@ bt_status bt_atlas_device_ptr(bt_terrain* t, uint32_t attachment, void** out) {
 // ------------------------------------------------------------------------------------------------
 static btd::SelectViewParams select_params_of(const bt_view* v) {
     return btd::SelectViewParams{v->d_uniforms, v->d_final_tiles, v->d_temporary_tiles, v->d_indirect, v->d_select_status, v->desc.geometry_tile_count,
-                                 v->terrain->desc.atlas_size, v->d_tile_tree, v->terrain->d_minmax};
+                                 v->terrain->desc.atlas_size, v->d_tile_tree, v->terrain->d_minmax,
+                                 v->d_host_uniforms, v->d_host_table, v->tile_tree_entries, 0u};
 }
 
 bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out) {
@@ -369,13 +372,16 @@ bt_status bt_view_create(bt_terrain* t, const bt_view_desc* desc, bt_view** out)
     if (e == cudaSuccess) e = cudaMemset(v->d_select_status, 0, sizeof(btd::SelectStatus));
     if (e == cudaSuccess) e = cudaMemset(v->d_gen_status, 0, sizeof(btd::GenStatus));
     if (e == cudaSuccess) e = cudaMemset(v->d_tile_tree, 0xFF, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+    // pinned staging so bt_view_update is a pair of truly asynchronous copies; mapped, so that bt_view_run_frame's select kernel
+    // can fetch the frame's inputs itself
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_uniforms, sizeof(ViewUniforms), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&v->d_host_uniforms, v->h_uniforms, 0);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&v->d_host_table, v->h_tile_tree, 0);
     if (e == cudaSuccess) {
         const btd::SelectViewParams sp = select_params_of(v);
         e = cudaMemcpy(v->d_select_params, &sp, sizeof(sp), cudaMemcpyHostToDevice);
     }
-    // pinned staging so bt_view_update is a pair of truly asynchronous copies
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_uniforms, sizeof(ViewUniforms), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&v->h_readback, sizeof(btd::SelectStatus) + sizeof(bt_indirect) + sizeof(btd::GenStatus), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->staging_free, cudaEventDisableTiming);
     // everything bt_view_run_frame needs is created HERE: no allocation on the per-frame path (SURVEY 8b ownership rule)
@@ -418,11 +424,14 @@ void bt_view_destroy(bt_view* v) {
     delete v;
 }
 
-bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) {
+// The Prepare-stage payload of a frame: validated and written into the view's pinned staging blocks.  push = true: two stream-ordered
+// host-to-device copies follow (bt_view_update); push = false: the caller's select kernel fetches the blocks itself (bt_view_run_frame).
+static bt_status view_stage(bt_view* v, const bt_view_frame* f, void* stream, bool push, bool* table_staged) {
     if (!v || !f) return BT_ERR_INVALID_ARG;
     bt_terrain* t = v->terrain;
     bt_context* ctx = t->ctx;
     const bool host_table = f->tile_tree != nullptr;
+    if (table_staged) *table_staged = host_table;
     if (!host_table && !v->device_table) {
         ctx->set_error("bt_view_update: tile_tree is NULL and no bt_clipmap maintains this view's table on the device");
         return BT_ERR_INVALID_ARG;
@@ -467,24 +476,27 @@ bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) {
     U.mesh = t->desc.transform;
     std::memcpy(U.view_world_position, f->view_world_position, sizeof(float) * 3);
     cudaStream_t s = (cudaStream_t)stream;
-    BT_CUDA(ctx, cudaMemcpyAsync(v->d_uniforms, v->h_uniforms, sizeof(ViewUniforms), cudaMemcpyHostToDevice, s));
-    v->h2d_bytes_last_update = sizeof(ViewUniforms);
-    if (host_table) {   // (with a device clipmap the table is already where the kernels read it)
-        std::memcpy(v->h_tile_tree, f->tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
-        BT_CUDA(ctx, cudaMemcpyAsync(v->d_tile_tree, v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaMemcpyHostToDevice, s));
-        v->h2d_bytes_last_update += (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry);
+    if (host_table) std::memcpy(v->h_tile_tree, f->tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry));
+    v->h2d_bytes_last_update = sizeof(ViewUniforms) + (host_table ? (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry) : 0);
+    if (push) {
+        BT_CUDA(ctx, cudaMemcpyAsync(v->d_uniforms, v->h_uniforms, sizeof(ViewUniforms), cudaMemcpyHostToDevice, s));
+        if (host_table)   // (with a device clipmap the table is already where the kernels read it)
+            BT_CUDA(ctx, cudaMemcpyAsync(v->d_tile_tree, v->h_tile_tree, (size_t)v->tile_tree_entries * sizeof(bt_tile_tree_entry), cudaMemcpyHostToDevice, s));
+        BT_CUDA(ctx, cudaEventRecord(v->staging_free, s));
     }
-    BT_CUDA(ctx, cudaEventRecord(v->staging_free, s));
     v->updated = true;
     return BT_OK;
 }
+
+bt_status bt_view_update(bt_view* v, const bt_view_frame* f, void* stream) { return view_stage(v, f, stream, true, nullptr); }
 
 bt_status bt_select_tiles(bt_view* v, uint32_t flags, void* stream) {
     if (!v) return BT_ERR_INVALID_ARG;
     bt_context* ctx = v->terrain->ctx;
     if (!v->updated) { ctx->set_error("bt_select_tiles: bt_view_update has not been called"); return BT_ERR_INVALID_ARG; }
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
-    BT_CUDA(ctx, bt_launch_select_tiles(v->d_select_params, 1u, v->terrain->desc.kind == BT_KIND_SPHERICAL, flags, (cudaStream_t)stream));
+    BT_CUDA(ctx, bt_launch_select_tiles(v->d_select_params, 1u, v->terrain->desc.kind == BT_KIND_SPHERICAL,
+                                        flags & ~(btd::kSelectFetchUniforms | btd::kSelectFetchTable), (cudaStream_t)stream));
     return BT_OK;
 }
 
@@ -526,7 +538,8 @@ bt_status bt_select_tiles_batch(bt_view_batch* b, uint32_t flags, void* stream) 
     for (bt_view* v : b->views)
         if (!v->updated) { ctx->set_error("bt_select_tiles_batch: bt_view_update has not been called on every view"); return BT_ERR_INVALID_ARG; }
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
-    BT_CUDA(ctx, bt_launch_select_tiles(b->d_params, (uint32_t)b->views.size(), b->spherical, flags, (cudaStream_t)stream));
+    BT_CUDA(ctx, bt_launch_select_tiles(b->d_params, (uint32_t)b->views.size(), b->spherical,
+                                        flags & ~(btd::kSelectFetchUniforms | btd::kSelectFetchTable), (cudaStream_t)stream));
     return BT_OK;
 }
 
@@ -631,10 +644,22 @@ bt_status bt_view_run_frame(bt_view* v, const bt_view_frame* frame, uint32_t sel
     BT_CUDA(ctx, cudaSetDevice(ctx->device));
     // the pinned read-back buffer was sized by bt_view_create (bt_view_desc.readback_tile_capacity): nothing is allocated here
     const uint32_t want = tiles ? (capacity < v->h_tiles_cap ? capacity : v->h_tiles_cap) : 0u;
-    bt_status st = bt_view_update(v, frame, stream);
+    // The frame's inputs go into the pinned staging blocks and the select kernel - the first kernel of the frame - pulls them over PCIe
+    // itself (BT_FRAME_FETCH=0 falls back to two copy-engine operations in front of it, the bt_view_update path): same bytes, but no
+    // engine hand-overs on the critical path.
+    static const bool kernel_fetch = [] { const char* e = getenv("BT_FRAME_FETCH"); return !(e && e[0] == '0'); }();
+    bool table_staged = false;
+    bt_status st = view_stage(v, frame, stream, !kernel_fetch, &table_staged);
     if (st != BT_OK) return st;
-    st = bt_select_tiles(v, select_flags, stream);
-    if (st != BT_OK) return st;
+    if (kernel_fetch) {
+        const uint32_t fetch = btd::kSelectFetchUniforms | (table_staged ? btd::kSelectFetchTable : 0u);
+        BT_CUDA(ctx, bt_launch_select_tiles(v->d_select_params, 1u, v->terrain->desc.kind == BT_KIND_SPHERICAL,
+                                            (select_flags & ~(btd::kSelectFetchUniforms | btd::kSelectFetchTable)) | fetch, s));
+        BT_CUDA(ctx, cudaEventRecord(v->staging_free, s));   // the staging blocks may be rewritten once this kernel has run
+    } else {
+        st = bt_select_tiles(v, select_flags, stream);
+        if (st != BT_OK) return st;
+    }
     BT_CUDA(ctx, cudaEventRecord(v->select_done, s));
     BT_CUDA(ctx, cudaStreamWaitEvent(v->copy_stream, v->select_done, 0));
     unsigned char* hb = static_cast<unsigned char*>(v->h_readback);

@@ -27,7 +27,15 @@ struct SelectViewParams {
     uint32_t atlas_size;
     const bt_tile_tree_entry* tile_tree;   // the view's table (BT_FLAG_MINMAX_CULL)
     const uint16_t* minmax;                // the terrain's [atlas_size][65][2] (min, max) table, or nullptr
+    // bt_view_run_frame: the frame's inputs are pulled by the select kernel itself from the view's pinned (mapped) staging block instead
+    // of being pushed by two copy-engine operations in front of it (kSelectFetch* bits of the launch flags)
+    const void* host_uniforms;             // device alias of the pinned ViewUniforms staging
+    const void* host_table;                // device alias of the pinned tile-tree staging
+    uint32_t table_entries;
+    uint32_t _pad;
 };
+constexpr uint32_t kSelectFetchUniforms = 1u << 30;   // internal launch flags (masked off the public flags)
+constexpr uint32_t kSelectFetchTable = 1u << 31;
 
 struct GenStatus {
     uint32_t vertex_count_lo, vertex_count_hi;

@@ -62,6 +62,8 @@ struct bt_view {
     uint64_t albedo_capacity = 0;
     void* h_uniforms = nullptr;
     void* h_tile_tree = nullptr;
+    void* d_host_uniforms = nullptr;   // device aliases of the two pinned staging blocks (mapped host memory)
+    void* d_host_table = nullptr;
     void* h_readback = nullptr;
     cudaEvent_t staging_free = nullptr;
     // bt_view_frame: the tile-list readback runs on its own stream so that it overlaps gen_vertices

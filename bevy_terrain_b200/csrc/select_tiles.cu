@@ -135,14 +135,30 @@ select_tiles_kernel(const SelectViewParams* __restrict__ views, uint32_t flags) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // bt_view_run_frame: this kernel is the first of the frame and fetches the frame's inputs itself - the uniform block by the TMA load
+    // below (source = the pinned staging block, mapped into the device address space), the tile-tree table with volatile loads - and
+    // leaves both in device memory for gen_vertices.  That removes two copy-engine operations (and their engine hand-overs) from
+    // the frame's critical path; the bytes that cross PCIe are the same.
+    const bool fetch_uniforms = (flags & kSelectFetchUniforms) != 0u, fetch_table = (flags & kSelectFetchTable) != 0u;
     if (tid == 0) {
         mbar_expect_tx(&S.bar, (uint32_t)sizeof(ViewUniforms));
-        bulk_load(&S.U, uniforms, (uint32_t)sizeof(ViewUniforms), &S.bar);
+        bulk_load(&S.U, fetch_uniforms ? static_cast<const ViewUniforms*>(V.host_uniforms) : uniforms, (uint32_t)sizeof(ViewUniforms), &S.bar);
+    }
+    if (fetch_table) {
+        const uint2* src = static_cast<const uint2*>(V.host_table);
+        uint2* dst = reinterpret_cast<uint2*>(const_cast<bt_tile_tree_entry*>(V.tile_tree));
+        for (uint32_t i = tid; i < V.table_entries; i += SELECT_THREADS) dst[i] = __ldcv(src + i);
     }
     // prepare_root — prepare_prepass.wgsl:4-23 (overlaps the bulk copy)
     const uint32_t n_roots = SPHERICAL ? 6u : 1u;
     if (tid < (int)n_roots) S.frontier[0][tid] = bt_tile{(uint32_t)tid, 0u, 0u, 0u};
-    mbar_wait_cta(&S.bar, 0);
+    mbar_wait_cta(&S.bar, 0);   // (its block barrier also orders the table stores above before this CTA's reads of the table)
+    if (fetch_uniforms) {
+        static_assert(sizeof(ViewUniforms) % 16 == 0, "uniform block is copied in 16-byte pieces");
+        uint4* dst = reinterpret_cast<uint4*>(const_cast<void*>(V.uniforms));
+        const uint4* src = reinterpret_cast<const uint4*>(&S.U);
+        for (uint32_t i = tid; i < (uint32_t)(sizeof(ViewUniforms) / 16); i += SELECT_THREADS) dst[i] = src[i];
+    }
 
     const ViewUniforms& U = S.U;
     const Vec3 planar_normal = SPHERICAL ? Vec3{0.0f, 0.0f, 0.0f} : normal_local_to_world<false>(U.mesh, Vec3{0.0f, 0.0f, 0.0f});
