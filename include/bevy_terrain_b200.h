@@ -316,7 +316,8 @@ bt_status bt_gen_vertices(bt_view* view, uint32_t flags, void* stream, bt_vertex
  * on the device, stream-ordered on `stream`.  Needs a view created with max_vertices > 0.  Allocates nothing: the copy
  * stream, events and pinned buffers belong to the view (bt_view_create); at most readback_tile_capacity tiles are
  * returned (*count still receives the true number).  The 1.5 GB vertex stream is NOT copied back: like the reference's
- * draw, its consumer reads it on the device.                                                                       */
+ * draw, its consumer reads it on the device.  The frame's inputs (uniform block, tile-tree table) are written to the view's
+ * pinned staging blocks and FETCHED by the select kernel itself over PCIe (no copy operation in front of the kernels).      */
 bt_status bt_view_run_frame(bt_view* view, const bt_view_frame* frame, uint32_t select_flags, uint32_t gen_flags, void* stream,
                         bt_tile* tiles, uint32_t capacity, uint32_t* count, bt_indirect* indirect, bt_vertex_buffer* vertices);
 /* blocking D2H of final_tiles + indirect (the reference never reads these back; the draw
