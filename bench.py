@@ -448,7 +448,7 @@ def run_b200(args):
             "e2e": {"value": e2e_verts_all / (e2e_ms_max * 1e-3) / 1e6, "unit": "Mverts/s",
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(16 * e2e_tiles / args.steps + 32),
                     "ms_per_step": e2e_ms_max / args.steps,
-                    "note": "bt_view_run_frame per step; the D2H is the tile list + indirect record, the vertex stream stays in HBM for its on-device consumer (as the reference's draw)"},
+                    "note": "bt_view_run_frame per step; the H2D bytes (uniform block + tile-tree table) are written to pinned host memory every step and pulled over PCIe by the select kernel itself (BT_FRAME_FETCH=0: two cudaMemcpyAsync instead); the D2H is the tile list + indirect record, the vertex stream stays in HBM for its on-device consumer (as the reference's draw)"},
             "gpu_launches": 2 * args.steps,
             # the reference's DEFAULT vertex flags (MORPH | BLEND, terrain_material.rs:404-409) + the fused normals: first-class beside `value`
             "value_reference_default_flags": {"value": dv_verts_all / (dv_ms_max * 1e-3) / 1e6, "unit": "Mverts/s", "flags": "MORPH|BLEND|NORMALS",
